@@ -1,0 +1,96 @@
+"""ctypes binding of libb200snark.so (the C ABI of include/b200snark.h)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so")
+
+B200_OK = 0
+ERRORS = {-1: "ENODEVICE", -2: "ECUDA", -3: "EINVAL", -4: "ERANGE", -5: "EDIVZERO", -6: "ENOMEM"}
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb200snark error {code} ({ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_int = ctypes.c_int
+_h = ctypes.c_uint64
+
+_SIGNATURES = {
+    "b200_init": [_int],
+    "b200_shutdown": [],
+    "b200_version": [],
+    "b200_g1_bases_load": [_vp, _sz, _int, ctypes.POINTER(_h)],
+    "b200_g2_bases_load": [_vp, _sz, _int, ctypes.POINTER(_h)],
+    "b200_bases_free": [_h],
+    "b200_bases_info": [_h, ctypes.POINTER(_sz), ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)],
+    "b200_g1_msm": [_h, _vp, _sz, _vp],
+    "b200_g2_msm": [_h, _vp, _sz, _vp],
+    "b200_msm_device": [_h, _vp, _sz, _int, _vp, _vp],
+    "b200_g1_sum_partials": [_vp, _sz, _vp, _vp],
+    "b200_g2_sum_partials": [_vp, _sz, _vp, _vp],
+    "b200_g1_mul_batch": [_vp, _vp, _sz, _vp],
+    "b200_g2_mul_batch": [_vp, _vp, _sz, _vp],
+    "b200_g1_mul_batch_bcast": [_vp, _vp, _sz, _vp],
+    "b200_g2_mul_batch_bcast": [_vp, _vp, _sz, _vp],
+}
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "go-snark-study_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.b200_last_error.restype = ctypes.c_char_p
+        for name, args in _SIGNATURES.items():
+            if not hasattr(L, name):
+                continue                       # newer header than library: symbol test catches it
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != B200_OK:
+        raise B200Error(rc, lib().b200_last_error().decode())
+
+
+def init(device=None):
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "-1"))
+    check(lib().b200_init(device))
+
+
+# ---- big-int <-> limb marshalling (what the cgo shim does with big.Int.Bits()) ----
+def ints_to_limbs(vals, words_per_val=4):
+    """list[int] -> contiguous uint64 array (len, words_per_val), little endian."""
+    nbytes = 8 * words_per_val
+    buf = bytearray(len(vals) * nbytes)
+    for i, v in enumerate(vals):
+        buf[i * nbytes:(i + 1) * nbytes] = int(v).to_bytes(nbytes, "little")
+    return np.frombuffer(bytes(buf), dtype=np.uint64).reshape(len(vals), words_per_val).copy()
+
+
+def limbs_to_ints(arr, words_per_val=4):
+    raw = np.ascontiguousarray(arr, dtype=np.uint64).tobytes()
+    nbytes = 8 * words_per_val
+    return [int.from_bytes(raw[i:i + nbytes], "little") for i in range(0, len(raw), nbytes)]
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)

@@ -1,0 +1,378 @@
+// libb200snark: C-ABI entry points (include/b200snark.h) and the host-side
+// orchestration of the CUDA kernels.  Device-only: there is no CPU fallback —
+// every entry point fails with B200_ENODEVICE when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b200snark.h"
+#include "msm.cuh"
+
+using namespace b200;
+
+namespace {
+
+std::mutex g_mu;
+std::string g_err;
+bool g_init = false;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r)
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(e_ == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA, "%s:%d %s: %s", \
+                  __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
+  } while (0)
+
+#define NEED_INIT()                                                                      \
+  do {                                                                                   \
+    if (!g_init) {                                                                       \
+      int rc_ = init_locked(-1);                                                         \
+      if (rc_) return rc_;                                                               \
+    } else {                                                                             \
+      cudaSetDevice(g_device);                                                           \
+    }                                                                                    \
+  } while (0)
+
+int init_locked(int device) {
+  if (g_init) {
+    if (device >= 0 && device != g_device) return fail(B200_EINVAL, "already initialised on device %d", g_device);
+    return B200_OK;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(B200_ENODEVICE, "no CUDA device (%s); libb200snark has no CPU fallback",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= count) return fail(B200_EINVAL, "device %d out of range (%d devices)", device, count);
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&g_d_err, sizeof(int)));
+  CU(cudaMemset(g_d_err, 0, sizeof(int)));
+  g_device = device;
+  g_init = true;
+  return B200_OK;
+}
+
+// field type used inside the bucket-accumulation kernel (same storage; F_q multiply inlined)
+template <class F> struct Hot { using type = F; };
+template <> struct Hot<Fq> { using type = FqH; };
+
+inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// device buffer with RAII
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t b) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = b;
+    return b ? cudaMalloc(&p, b) : cudaSuccess;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int pick_window_bits(size_t n) {
+  // cost model: nwin*n bucket adds (~10 M) + 2*2^(c-1) reduction adds (~14 M), see DESIGN.md §3
+  int best = 8;
+  double best_cost = 1e300;
+  for (int c = 8; c <= 18; c++) {
+    double nwin = (255 + c - 1) / c;
+    double cost = nwin * (double)n * 10.0 + 2.0 * (double)(1u << (c - 1)) * 14.0 * 4.0;
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+struct Bases {
+  int group = 0;  // 1: G1 (Fq), 2: G2 (Fq2)
+  size_t n = 0;
+  MsmShape sh{};
+  DevBuf table;    // [nwin][n] Affine<F>
+  // per-MSM scratch (MSMs on one base set are serialised on a stream)
+  DevBuf scalars;  // n * 32 B (host-scalar entry points)
+  DevBuf counts, offsets, cursor, entries, buckets, partials, result, out_std;
+  uint32_t nseg = 0, seg = 0;
+};
+
+std::map<uint64_t, std::unique_ptr<Bases>> g_bases;
+uint64_t g_next_handle = 1;
+
+template <class F>
+int check_err_flag(const char* what) {
+  int h = 0;
+  CU(cudaMemcpyAsync(&h, g_d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaStreamSynchronize(g_stream));
+  if (h) {
+    CU(cudaMemset(g_d_err, 0, sizeof(int)));
+    return fail(B200_ERANGE, "%s: %s", what, (h & 1) ? "point coordinate >= q" : "scalar >= r");
+  }
+  return B200_OK;
+}
+
+template <class F>
+int bases_load(const uint64_t* pts, size_t n, int c, int group, b200_bases_t* out) {
+  if (!pts || !out || n == 0 || n > (1u << 26)) return fail(B200_EINVAL, "bases_load: bad arguments");
+  if (c == 0) c = pick_window_bits(n);
+  if (c < 2 || c > 24) return fail(B200_EINVAL, "window_bits must be in [2,24]");
+  auto b = std::make_unique<Bases>();
+  b->group = group;
+  b->n = n;
+  MsmShape& sh = b->sh;
+  sh.n = (uint32_t)n;
+  sh.c = (uint32_t)c;
+  sh.nwin = (255 + c - 1) / c;
+  sh.nbuckets = 1u << (c - 1);
+  sh.table_stride = (uint32_t)n;
+  if ((uint64_t)sh.nwin * n >= (1ull << 31)) return fail(B200_EINVAL, "nwin*n exceeds 2^31 entries");
+  size_t entries = (size_t)sh.nwin * n;
+  CU(b->table.alloc(entries * sizeof(Affine<F>)));
+  CU(b->scalars.alloc(n * sizeof(Fr)));
+  CU(b->counts.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
+  CU(b->offsets.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
+  CU(b->cursor.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
+  CU(b->entries.alloc(entries * sizeof(uint32_t)));
+  CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
+  b->seg = sh.nbuckets >= 4096 ? 16 : (sh.nbuckets >= 256 ? 4 : 1);
+  b->nseg = (sh.nbuckets + b->seg - 1) / b->seg;
+  CU(b->partials.alloc((size_t)b->nseg * sizeof(XYZZ<F>)));
+  CU(b->result.alloc(sizeof(XYZZ<F>)));
+  CU(b->out_std.alloc(3 * sizeof(F)));
+
+  // upload + normalise + window precompute
+  DevBuf staging, state;
+  CU(staging.alloc(n * 3 * sizeof(F)));
+  CU(state.alloc(n * sizeof(XYZZ<F>)));
+  CU(cudaMemcpyAsync(staging.p, pts, n * 3 * sizeof(F), cudaMemcpyHostToDevice, g_stream));
+  Affine<F>* table = b->table.as<Affine<F>>();
+  k_load_bases<F><<<nblocks(n, 128), 128, 0, g_stream>>>(staging.as<F>(), n, table, g_d_err);
+  k_affine_to_xyzz<F><<<nblocks(n, 128), 128, 0, g_stream>>>(table, state.as<XYZZ<F>>(), n);
+  for (uint32_t w = 1; w < sh.nwin; w++) {
+    k_window_step<F><<<nblocks(n, 128), 128, 0, g_stream>>>(state.as<XYZZ<F>>(), n, c);
+    constexpr int K = 8;
+    k_batch_to_affine<F, K><<<nblocks((n + K - 1) / K, 128), 128, 0, g_stream>>>(state.as<XYZZ<F>>(), table + (size_t)w * n, n);
+  }
+  CU(cudaGetLastError());
+  int rc = check_err_flag<F>("bases_load");
+  if (rc) return rc;
+  uint64_t h = g_next_handle++;
+  g_bases[h] = std::move(b);
+  *out = h;
+  return B200_OK;
+}
+
+Bases* find_bases(b200_bases_t h, int group) {
+  auto it = g_bases.find(h);
+  if (it == g_bases.end()) return nullptr;
+  if (group && it->second->group != group) return nullptr;
+  return it->second.get();
+}
+
+// Enqueue one MSM on `st`; result XYZZ written to d_out (device).
+template <class F>
+int msm_enqueue(Bases* b, const Fr* d_scalars, size_t n, int mont, XYZZ<F>* d_out, cudaStream_t st) {
+  if (n > b->n) return fail(B200_EINVAL, "msm: n=%zu exceeds base set size %zu", n, b->n);
+  MsmShape sh = b->sh;
+  sh.n = (uint32_t)n;
+  uint32_t* counts = b->counts.as<uint32_t>();
+  uint32_t* offsets = b->offsets.as<uint32_t>();
+  uint32_t* cursor = b->cursor.as<uint32_t>();
+  uint32_t* entries = b->entries.as<uint32_t>();
+  XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
+  XYZZ<F>* partials = b->partials.as<XYZZ<F>>();
+  uint32_t m = sh.nbuckets + 1;  // counts[0] unused (digit 0), buckets 1..B
+  CU(cudaMemsetAsync(counts, 0, (m + 1) * sizeof(uint32_t), st));
+  if (n) {
+    k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
+    k_scan<<<1, 1024, 0, st>>>(counts, m, offsets, cursor);
+    k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, cursor, entries, g_d_err);
+  } else {
+    CU(cudaMemsetAsync(offsets, 0, (m + 2) * sizeof(uint32_t), st));
+  }
+  constexpr int LPB = 8;
+  using FH = typename Hot<F>::type;
+  k_accumulate<FH, LPB><<<nblocks((size_t)sh.nbuckets * LPB, 128), 128, 0, st>>>(
+      b->table.as<Affine<FH>>(), entries, offsets, sh.nbuckets, reinterpret_cast<XYZZ<FH>*>(buckets));
+  k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
+  k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+template <class F>
+int msm_host(b200_bases_t h, int group, const uint64_t* scalars, size_t n, uint64_t* out) {
+  Bases* b = find_bases(h, group);
+  if (!b) return fail(B200_EINVAL, "msm: bad handle");
+  if ((!scalars && n) || !out) return fail(B200_EINVAL, "msm: null pointer");
+  if (n) CU(cudaMemcpyAsync(b->scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  int rc = msm_enqueue<F>(b, b->scalars.as<Fr>(), n, 0, b->result.as<XYZZ<F>>(), g_stream);
+  if (rc) return rc;
+  k_finalize<F><<<1, 32, 0, g_stream>>>(b->result.as<XYZZ<F>>(), b->out_std.as<F>());
+  CU(cudaMemcpyAsync(out, b->out_std.p, 3 * sizeof(F), cudaMemcpyDeviceToHost, g_stream));
+  rc = check_err_flag<F>("msm");  // synchronises the stream
+  return rc;
+}
+
+template <class F>
+int sum_partials(const void* d_xyzz, size_t count, uint64_t* out, cudaStream_t st) {
+  if (!d_xyzz || !out || count == 0 || count > (1u << 20)) return fail(B200_EINVAL, "sum_partials: bad arguments");
+  DevBuf res, std_out;
+  CU(res.alloc(sizeof(XYZZ<F>)));
+  CU(std_out.alloc(3 * sizeof(F)));
+  k_sum_points<F><<<1, 256, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_xyzz), (uint32_t)count, res.as<XYZZ<F>>());
+  k_finalize<F><<<1, 32, 0, st>>>(res.as<XYZZ<F>>(), std_out.as<F>());
+  CU(cudaMemcpyAsync(out, std_out.p, 3 * sizeof(F), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return B200_OK;
+}
+
+template <class F>
+int mul_batch(const uint64_t* pts, int bcast, const uint64_t* scalars, size_t n, uint64_t* out) {
+  if (!pts || !scalars || !out) return fail(B200_EINVAL, "mul_batch: null pointer");
+  if (n == 0) return B200_OK;
+  DevBuf dp, ds, dout;
+  size_t np = bcast ? 1 : n;
+  CU(dp.alloc(np * 3 * sizeof(F)));
+  CU(ds.alloc(n * sizeof(Fr)));
+  CU(dout.alloc(n * 3 * sizeof(F)));
+  CU(cudaMemcpyAsync(dp.p, pts, np * 3 * sizeof(F), cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(ds.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  k_mul_batch_ref<F><<<nblocks(n, 128), 128, 0, g_stream>>>(dp.as<F>(), bcast, ds.as<Fr>(), n, dout.as<F>(), g_d_err);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, n * 3 * sizeof(F), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<F>("mul_batch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_version(void) { return 100; }
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return init_locked(device);
+}
+
+int b200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_init) return B200_OK;
+  cudaSetDevice(g_device);
+  g_bases.clear();
+  if (g_d_err) cudaFree(g_d_err);
+  if (g_stream) cudaStreamDestroy(g_stream);
+  g_d_err = nullptr;
+  g_stream = nullptr;
+  g_init = false;
+  return B200_OK;
+}
+
+int b200_g1_bases_load(const uint64_t* p, size_t n, int c, b200_bases_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return bases_load<Fq>(p, n, c, 1, out);
+}
+int b200_g2_bases_load(const uint64_t* p, size_t n, int c, b200_bases_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return bases_load<Fq2>(p, n, c, 2, out);
+}
+int b200_bases_free(b200_bases_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_init) return fail(B200_EINVAL, "not initialised");
+  cudaSetDevice(g_device);
+  cudaStreamSynchronize(g_stream);
+  return g_bases.erase(h) ? B200_OK : fail(B200_EINVAL, "bases_free: bad handle");
+}
+int b200_bases_info(b200_bases_t h, size_t* n, int* group, int* window_bits, int* n_windows) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Bases* b = find_bases(h, 0);
+  if (!b) return fail(B200_EINVAL, "bases_info: bad handle");
+  if (n) *n = b->n;
+  if (group) *group = b->group;
+  if (window_bits) *window_bits = (int)b->sh.c;
+  if (n_windows) *n_windows = (int)b->sh.nwin;
+  return B200_OK;
+}
+
+int b200_g1_msm(b200_bases_t h, const uint64_t* s, size_t n, uint64_t out[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return msm_host<Fq>(h, 1, s, n, out);
+}
+int b200_g2_msm(b200_bases_t h, const uint64_t* s, size_t n, uint64_t out[24]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return msm_host<Fq2>(h, 2, s, n, out);
+}
+
+int b200_msm_device(b200_bases_t h, const void* d_scalars, size_t n, int mont, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  Bases* b = find_bases(h, 0);
+  if (!b || !d_out || (!d_scalars && n)) return fail(B200_EINVAL, "msm_device: bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : g_stream;
+  if (b->group == 1) return msm_enqueue<Fq>(b, (const Fr*)d_scalars, n, mont, (XYZZ<Fq>*)d_out, st);
+  return msm_enqueue<Fq2>(b, (const Fr*)d_scalars, n, mont, (XYZZ<Fq2>*)d_out, st);
+}
+
+int b200_g1_sum_partials(const void* d, size_t count, uint64_t out[12], void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return sum_partials<Fq>(d, count, out, stream ? (cudaStream_t)stream : g_stream);
+}
+int b200_g2_sum_partials(const void* d, size_t count, uint64_t out[24], void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return sum_partials<Fq2>(d, count, out, stream ? (cudaStream_t)stream : g_stream);
+}
+
+int b200_g1_mul_batch(const uint64_t* p, const uint64_t* s, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return mul_batch<Fq>(p, 0, s, n, out);
+}
+int b200_g2_mul_batch(const uint64_t* p, const uint64_t* s, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return mul_batch<Fq2>(p, 0, s, n, out);
+}
+int b200_g1_mul_batch_bcast(const uint64_t* p, const uint64_t* s, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return mul_batch<Fq>(p, 1, s, n, out);
+}
+int b200_g2_mul_batch_bcast(const uint64_t* p, const uint64_t* s, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return mul_batch<Fq2>(p, 1, s, n, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// 254-bit prime-field arithmetic in Montgomery form, 8 x 32-bit limbs.
+//
+// Replaces the reference's big.Int field ops (fields/fq.go:32-98: Add, Sub,
+// Neg, Mul, Square, Inverse — each a big.Int op followed by big.Int.Mod) for
+// the two BN254 moduli of bn128/bn128.go:40,46.  Values are kept fully reduced
+// in [0, p) so equality and zero tests are limb compares, and converting out
+// of Montgomery form yields exactly the canonical residue the reference holds.
+//
+// Multiplication is operand-scanning Montgomery (CIOS) with the partial
+// products of even- and odd-indexed limbs accumulated in two separate carry
+// chains (each 32x32->64 product then occupies a private column pair, so a
+// chain is mad.lo.cc / madc.hi.cc alternating with no carry conflicts; ptxas
+// fuses each pair into one IMAD.WIDE.U32 with carry-in/out).
+#pragma once
+#include "constants.cuh"
+#include "hd.cuh"
+
+namespace b200 {
+
+// INL = true : multiplication is force-inlined into the caller (hot kernels).
+// INL = false: multiplication is one out-of-line device function per field
+//              (register-passed, no stack traffic); keeps cold kernels and the
+//              F_q^2 tower small and the build fast.  Same storage either way.
+template <class P, bool INL>
+struct Fp;
+#ifdef __CUDACC__
+template <class P>
+__device__ __noinline__ Fp<P, false> fp_mul_outlined(Fp<P, false> a, Fp<P, false> b);
+template <class P, bool INL>
+__device__ __noinline__ Fp<P, INL> fp_inverse_outlined(Fp<P, INL> a);
+#endif
+
+template <class P, bool INL = false>
+struct alignas(32) Fp {
+  uint32_t l[8];
+
+  static HD Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    return r;
+  }
+  static HD Fp one() {  // Montgomery form of 1
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::ONE(i);
+    return r;
+  }
+  static HD Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::R2(i);
+    return r;
+  }
+
+  HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= l[i];
+    return o == 0;
+  }
+  HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= l[i] ^ b.l[i];
+    return o == 0;
+  }
+  HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+  // r = a - p if a >= p else a     (a < 2p)
+  static HD void final_sub(uint32_t* a) {
+    uint32_t t[8];
+    t[0] = cc::sub_cc(a[0], P::MOD(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = cc::subc_cc(a[i], P::MOD(i));
+    uint32_t borrow = cc::subc(0u, 0u);  // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
+  }
+
+  friend HD Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    r.l[0] = cc::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = cc::addc_cc(a.l[i], b.l[i]);
+    r.l[7] = cc::addc(a.l[7], b.l[7]);  // < 2^255: no carry out
+    final_sub(r.l);
+    return r;
+  }
+  friend HD Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    r.l[0] = cc::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.l[i] = cc::subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = cc::subc(0u, 0u);  // all-ones if a < b
+    r.l[0] = cc::add_cc(r.l[0], P::MOD(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = cc::addc_cc(r.l[i], P::MOD(i) & borrow);
+    r.l[7] = cc::addc(r.l[7], P::MOD(7) & borrow);
+    return r;
+  }
+  HD Fp neg() const { return zero() - *this; }
+  HD Fp dbl() const { return *this + *this; }
+
+  // ---- Montgomery multiplication ------------------------------------------
+  // One operand-scanning step: (E, O) += a * bi, then += mi * p so that the
+  // lowest column becomes zero.  E holds columns j (32-bit columns), O holds
+  // columns j+1; on entry (non-first) the roles were swapped by the previous
+  // step, whose zeroed low column is dropped here (the ">> 32" of Montgomery).
+  static HD void mad_n_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
+    using namespace cc;
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) mul_wide(a[j + 1], bi, O[j], O[j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) mul_wide(a[j], bi, E[j], E[j + 1]);
+    } else {
+      E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+      for (int j = 0; j < 6; j += 2) {
+        O[j] = madc_lo_cc(a[j + 1], bi, O[j + 2]);
+        O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 3]);
+      }
+      O[6] = madc_lo_cc(a[7], bi, 0u);
+      O[7] = madc_hi_cc(a[7], bi, 0u);  // (.cc so the pair fuses; the carry out is always 0)
+      E[0] = mad_lo_cc(a[0], bi, E[0]);
+      E[1] = madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        E[j] = madc_lo_cc(a[j], bi, E[j]);
+        E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1]);
+      }
+      O[7] = addc(O[7], 0u);
+    }
+    uint32_t mi = mul_lo(E[0], P::INV);
+    O[0] = mad_lo_cc(P::MOD(1), mi, O[0]);
+    O[1] = madc_hi_cc(P::MOD(1), mi, O[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      O[j] = madc_lo_cc(P::MOD(j + 1), mi, O[j]);
+      O[j + 1] = madc_hi_cc(P::MOD(j + 1), mi, O[j + 1]);
+    }
+    E[0] = mad_lo_cc(P::MOD(0), mi, E[0]);
+    E[1] = madc_hi_cc(P::MOD(0), mi, E[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+      E[j] = madc_lo_cc(P::MOD(j), mi, E[j]);
+      E[j + 1] = madc_hi_cc(P::MOD(j), mi, E[j + 1]);
+    }
+    O[7] = addc(O[7], 0u);
+  }
+
+  friend HD Fp operator*(const Fp& a, const Fp& b) {
+#ifdef __CUDA_ARCH__
+    if constexpr (!INL) return fp_mul_outlined<P>(a, b);
+#endif
+    return mul_impl(a, b);
+  }
+  static HD Fp mul_impl(const Fp& a, const Fp& b) {
+    using namespace cc;
+    uint32_t even[8], odd[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      mad_n_redc(even, odd, a.l, b.l[i], i == 0);
+      mad_n_redc(odd, even, a.l, b.l[i + 1], false);
+    }
+    Fp r;
+    r.l[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
+    r.l[7] = addc(even[7], 0u);
+    final_sub(r.l);
+    return r;
+  }
+  HD Fp sqr() const { return (*this) * (*this); }
+
+  HD Fp to_mont() const { return (*this) * r2(); }
+  HD Fp from_mont() const {
+    Fp o = zero();
+    o.l[0] = 1;
+    return (*this) * o;
+  }
+
+  // a^(p-2): Fermat inversion (0 -> 0).  Same value as fields/fq.go:66-68
+  // (big.Int.ModInverse) for every non-zero a.
+  HD Fp inverse() const {
+#ifdef __CUDA_ARCH__
+    return fp_inverse_outlined<P, INL>(*this);
+#else
+    return inverse_impl();
+#endif
+  }
+  HD Fp inverse_impl() const {
+    Fp res = one();
+    Fp base = *this;
+    for (int w = 0; w < 8; w++) {
+      uint32_t e = P::PM2(0);
+      // select limb w without dynamic constexpr indexing
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k == w) e = P::PM2(k);
+      for (int b = 0; b < 32; b++) {
+        if ((e >> b) & 1) res = res * base;
+        base = base.sqr();
+      }
+    }
+    return res;
+  }
+
+  // value >= p ?  (for validating standard-form inputs)
+  HD bool geq_modulus() const {
+    using namespace cc;
+    sub_cc(l[0], P::MOD(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) subc_cc(l[i], P::MOD(i));
+    uint32_t borrow = subc(0u, 0u);
+    return borrow == 0;
+  }
+};
+
+#ifdef __CUDACC__
+template <class P>
+__device__ __noinline__ Fp<P, false> fp_mul_outlined(Fp<P, false> a, Fp<P, false> b) {
+  return Fp<P, false>::mul_impl(a, b);
+}
+template <class P, bool INL>
+__device__ __noinline__ Fp<P, INL> fp_inverse_outlined(Fp<P, INL> a) {
+  // always built on the out-of-line multiply: inversion is never on a hot path
+  Fp<P, false> t;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l[i] = a.l[i];
+  t = t.inverse_impl();
+  Fp<P, INL> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = t.l[i];
+  return r;
+}
+#endif
+
+using Fq = Fp<FqParams, false>;   // coordinates of G1 points      (fields over bn128.Q)
+using FqH = Fp<FqParams, true>;   // same, multiplication inlined (hot kernels)
+using Fr = Fp<FrParams, false>;   // scalars / polynomial coeffs   (fields over bn128.R)
+using FrH = Fp<FrParams, true>;
+
+}  // namespace b200

@@ -1,0 +1,80 @@
+// Host build of the kernel arithmetic headers, for CPU unit tests only
+// (tests/test_host_arith.py loads this via ctypes and compares with the
+// oracle).  Not part of the product library.
+#include <cstring>
+#include "ec.cuh"
+
+using namespace b200;
+
+namespace {
+template <class F> F load(const uint32_t* p) { F r; std::memcpy(&r, p, sizeof(F)); return r; }
+template <class F> void store(uint32_t* p, const F& v) { std::memcpy(p, &v, sizeof(F)); }
+
+template <class F>
+void ec_ops(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  // a: XYZZ (4 F, std form) ; b: affine (2 F) or XYZZ (4 F) ; out: affine (2 F, std form)
+  constexpr int W = sizeof(F) / 4;
+  XYZZ<F> A{load<F>(a).to_mont(), load<F>(a + W).to_mont(), load<F>(a + 2 * W).to_mont(), load<F>(a + 3 * W).to_mont()};
+  if (op == 0) {  // madd
+    Affine<F> B{load<F>(b).to_mont(), load<F>(b + W).to_mont()};
+    xyzz_madd(A, B);
+  } else if (op == 1) {  // add
+    XYZZ<F> B{load<F>(b).to_mont(), load<F>(b + W).to_mont(), load<F>(b + 2 * W).to_mont(), load<F>(b + 3 * W).to_mont()};
+    xyzz_add(A, B);
+  } else if (op == 2) {
+    A = xyzz_dbl(A);
+  } else if (op == 3) {  // via jacobian round trip
+    A = jacobian_to_xyzz(xyzz_to_jacobian(A));
+  }
+  Affine<F> r = xyzz_to_affine(A);
+  store(out, r.x.from_mont());
+  store(out + W, r.y.from_mont());
+}
+
+template <class F>
+void jac_ops(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  constexpr int W = sizeof(F) / 4;
+  Jacobian<F> A{load<F>(a).to_mont(), load<F>(a + W).to_mont(), load<F>(a + 2 * W).to_mont()};
+  Jacobian<F> B{load<F>(b).to_mont(), load<F>(b + W).to_mont(), load<F>(b + 2 * W).to_mont()};
+  Jacobian<F> r = op == 0 ? jac_add_ref(A, B) : jac_double_ref(A);
+  store(out, r.X.from_mont());
+  store(out + W, r.Y.from_mont());
+  store(out + 2 * W, r.Z.from_mont());
+}
+}  // namespace
+
+extern "C" {
+// op: 0 add 1 sub 2 mul 3 inverse 4 neg ; field: 0 Fq, 1 Fr ; standard-form in/out
+void t_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  auto run = [&](auto tag) {
+    using F = decltype(tag);
+    F x = load<F>(a).to_mont(), y = load<F>(b).to_mont(), r;
+    switch (op) {
+      case 0: r = x + y; break;
+      case 1: r = x - y; break;
+      case 2: r = x * y; break;
+      case 3: r = x.inverse(); break;
+      default: r = x.neg(); break;
+    }
+    store(out, r.from_mont());
+  };
+  if (field == 0) run(Fq{}); else run(Fr{});
+}
+void t_fq2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq2 x = load<Fq2>(a).to_mont(), y = load<Fq2>(b).to_mont(), r;
+  switch (op) {
+    case 0: r = x + y; break;
+    case 1: r = x - y; break;
+    case 2: r = x * y; break;
+    case 3: r = x.inverse(); break;
+    case 4: r = x.sqr(); break;
+    default: r = x.neg(); break;
+  }
+  store(out, r.from_mont());
+}
+int t_geq(int field, const uint32_t* a) { return field == 0 ? load<Fq>(a).geq_modulus() : load<Fr>(a).geq_modulus(); }
+void t_g1_xyzz(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { ec_ops<Fq>(op, a, b, out); }
+void t_g2_xyzz(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { ec_ops<Fq2>(op, a, b, out); }
+void t_g1_jac(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { jac_ops<Fq>(op, a, b, out); }
+void t_g2_jac(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { jac_ops<Fq2>(op, a, b, out); }
+}
