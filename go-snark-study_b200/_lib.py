@@ -42,6 +42,15 @@ _SIGNATURES = {
     "b200_g2_mul_batch": [_vp, _vp, _sz, _vp],
     "b200_g1_mul_batch_bcast": [_vp, _vp, _sz, _vp],
     "b200_g2_mul_batch_bcast": [_vp, _vp, _sz, _vp],
+    "b200_poly_mul": [_vp, _sz, _vp, _sz, _vp],
+    "b200_poly_div": [_vp, _sz, _vp, _sz, _vp, _vp],
+    "b200_groth16_pk_load": [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _sz, _int,
+                             ctypes.POINTER(_h)],
+    "b200_groth16_prove": [_h, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "b200_pinocchio_pk_load": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _int,
+                               ctypes.POINTER(_h)],
+    "b200_pinocchio_prove": [_h, _vp, _sz, _vp, _sz, _vp, _vp],
+    "b200_pk_free": [_h],
 }
 
 

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -14,6 +15,7 @@
 
 #include "b200snark.h"
 #include "msm.cuh"
+#include "poly_host.cuh"
 
 using namespace b200;
 
@@ -24,7 +26,8 @@ std::string g_err;
 bool g_init = false;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
-int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r)
+int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
+std::unique_ptr<PolyCtx> g_poly;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -72,6 +75,7 @@ int init_locked(int device) {
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   CU(cudaMalloc(&g_d_err, sizeof(int)));
   CU(cudaMemset(g_d_err, 0, sizeof(int)));
+  g_poly = std::make_unique<PolyCtx>();
   g_device = device;
   g_init = true;
   return B200_OK;
@@ -81,21 +85,7 @@ int init_locked(int device) {
 template <class F> struct Hot { using type = F; };
 template <> struct Hot<Fq> { using type = FqH; };
 
-inline unsigned nblocks(size_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
-
-// device buffer with RAII
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t b) {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = b;
-    return b ? cudaMalloc(&p, b) : cudaSuccess;
-  }
-  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
+inline unsigned nblocks(size_t n, unsigned bs) { return nblk(n, bs); }
 
 int pick_window_bits(size_t n) {
   // cost model: nwin*n bucket adds (~10 M) + 2*2^(c-1) reduction adds (~14 M), see DESIGN.md §3
@@ -117,6 +107,8 @@ struct Bases {
   // per-MSM scratch (MSMs on one base set are serialised on a stream)
   DevBuf scalars;  // n * 32 B (host-scalar entry points)
   DevBuf counts, offsets, cursor, entries, buckets, partials, result, out_std;
+  DevBuf slice_off, slice_start, slice_end, slice_out;
+  uint32_t max_slices = 0;
   uint32_t nseg = 0, seg = 0;
 };
 
@@ -130,14 +122,15 @@ int check_err_flag(const char* what) {
   CU(cudaStreamSynchronize(g_stream));
   if (h) {
     CU(cudaMemset(g_d_err, 0, sizeof(int)));
-    return fail(B200_ERANGE, "%s: %s", what, (h & 1) ? "point coordinate >= q" : "scalar >= r");
+    if (h & 4) return fail(B200_EDIVZERO, "%s: divisor has a zero leading coefficient", what);
+    return fail(B200_ERANGE, "%s: %s", what, (h & 1) ? "point coordinate >= q" : "scalar / coefficient >= r");
   }
   return B200_OK;
 }
 
 template <class F>
-int bases_load(const uint64_t* pts, size_t n, int c, int group, b200_bases_t* out) {
-  if (!pts || !out || n == 0 || n > (1u << 26)) return fail(B200_EINVAL, "bases_load: bad arguments");
+int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_ptr<Bases>& out_b) {
+  if (!pts || n == 0 || n > (1u << 26)) return fail(B200_EINVAL, "bases_load: bad arguments");
   if (c == 0) c = pick_window_bits(n);
   if (c < 2 || c > 24) return fail(B200_EINVAL, "window_bits must be in [2,24]");
   auto b = std::make_unique<Bases>();
@@ -158,6 +151,12 @@ int bases_load(const uint64_t* pts, size_t n, int c, int group, b200_bases_t* ou
   CU(b->cursor.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
   CU(b->entries.alloc(entries * sizeof(uint32_t)));
   CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
+  // slices: every bucket owns >= 1; a bucket above cap = 2*mean entries is cut => at most B + B/2 + 1
+  b->max_slices = sh.nbuckets + sh.nbuckets / 2 + 2;
+  CU(b->slice_off.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
+  CU(b->slice_start.alloc((size_t)b->max_slices * sizeof(uint32_t)));
+  CU(b->slice_end.alloc((size_t)b->max_slices * sizeof(uint32_t)));
+  CU(b->slice_out.alloc((size_t)b->max_slices * sizeof(XYZZ<F>)));
   b->seg = sh.nbuckets >= 4096 ? 16 : (sh.nbuckets >= 256 ? 4 : 1);
   b->nseg = (sh.nbuckets + b->seg - 1) / b->seg;
   CU(b->partials.alloc((size_t)b->nseg * sizeof(XYZZ<F>)));
@@ -179,6 +178,16 @@ int bases_load(const uint64_t* pts, size_t n, int c, int group, b200_bases_t* ou
   }
   CU(cudaGetLastError());
   int rc = check_err_flag<F>("bases_load");
+  if (rc) return rc;
+  out_b = std::move(b);
+  return B200_OK;
+}
+
+template <class F>
+int bases_load(const uint64_t* pts, size_t n, int c, int group, b200_bases_t* out) {
+  if (!out) return fail(B200_EINVAL, "bases_load: null handle pointer");
+  std::unique_ptr<Bases> b;
+  int rc = bases_create<F>(pts, n, c, group, b);
   if (rc) return rc;
   uint64_t h = g_next_handle++;
   g_bases[h] = std::move(b);
@@ -206,18 +215,27 @@ int msm_enqueue(Bases* b, const Fr* d_scalars, size_t n, int mont, XYZZ<F>* d_ou
   XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
   XYZZ<F>* partials = b->partials.as<XYZZ<F>>();
   uint32_t m = sh.nbuckets + 1;  // counts[0] unused (digit 0), buckets 1..B
-  CU(cudaMemsetAsync(counts, 0, (m + 1) * sizeof(uint32_t), st));
-  if (n) {
-    k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
-    k_scan<<<1, 1024, 0, st>>>(counts, m, offsets, cursor);
-    k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, cursor, entries, g_d_err);
-  } else {
-    CU(cudaMemsetAsync(offsets, 0, (m + 2) * sizeof(uint32_t), st));
-  }
   constexpr int LPB = 8;
+  // slice cap: twice the mean bucket population (uniform scalars never split), at least 4 per lane
+  uint64_t mean = ((uint64_t)sh.nwin * n + sh.nbuckets - 1) / sh.nbuckets;
+  uint32_t cap = (uint32_t)(2 * mean < 4 * LPB ? 4 * LPB : 2 * mean);
+  SliceTables stb{b->slice_off.as<uint32_t>(), b->slice_start.as<uint32_t>(), b->slice_end.as<uint32_t>()};
+  CU(cudaMemsetAsync(counts, 0, (m + 1) * sizeof(uint32_t), st));
+  if (n) k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
+  k_scan<<<1, 1024, 0, st>>>(counts, m, cap, offsets, cursor, stb);
+  if (n) k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, cursor, entries, g_d_err);
   using FH = typename Hot<F>::type;
-  k_accumulate<FH, LPB><<<nblocks((size_t)sh.nbuckets * LPB, 128), 128, 0, st>>>(
-      b->table.as<Affine<FH>>(), entries, offsets, sh.nbuckets, reinterpret_cast<XYZZ<FH>*>(buckets));
+  static const int variant = getenv("B200_ACC_VARIANT") ? atoi(getenv("B200_ACC_VARIANT")) : 0;  // tuning knob
+  unsigned grid = nblocks((size_t)b->max_slices * LPB, 128);
+  if (variant == 1)
+    k_accumulate<F, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
+  else if (variant == 2)
+    k_accumulate<FH, LPB, 4><<<grid, 128, 0, st>>>(b->table.as<Affine<FH>>(), entries, stb, m, b->slice_out.as<XYZZ<FH>>());
+  else if (variant == 3)
+    k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
+  else
+    k_accumulate<FH, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<FH>>(), entries, stb, m, b->slice_out.as<XYZZ<FH>>());
+  k_merge_slices<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(b->slice_out.as<XYZZ<F>>(), stb, sh.nbuckets, buckets);
   k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
   k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
   CU(cudaGetLastError());
@@ -268,9 +286,110 @@ int mul_batch(const uint64_t* pts, int bcast, const uint64_t* scalars, size_t n,
   return check_err_flag<F>("mul_batch");
 }
 
+int poly_mul_host(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) {
+  if (!a || !b || !out || na == 0 || nb == 0) return fail(B200_EINVAL, "poly_mul: bad arguments");
+  if (na + nb - 1 > ((size_t)1 << 27)) return fail(B200_EINVAL, "poly_mul: product too long");
+  DevBuf da, db, dout;
+  CU(da.alloc(na * sizeof(Fr)));
+  CU(db.alloc(nb * sizeof(Fr)));
+  CU(dout.alloc((na + nb - 1) * sizeof(Fr)));
+  CU(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  CU(poly_mul_device(*g_poly, da.as<Fr>(), na, 0, db.as<Fr>(), nb, 0, dout.as<Fr>(), g_d_err, g_stream));
+  CU(cudaMemcpyAsync(out, dout.p, (na + nb - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("poly_mul");
+}
+
+int divisor_init(Divisor& dv, const uint64_t* b, size_t nb) {
+  DevBuf tmp;
+  CU(tmp.alloc(nb * sizeof(Fr)));
+  CU(dv.b_mont.alloc(nb * sizeof(Fr)));
+  CU(cudaMemcpyAsync(tmp.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  k_poly_load<<<nblk(nb, 256), 256, 0, g_stream>>>(tmp.as<Fr>(), (uint32_t)nb, (uint32_t)nb, 0, 0, dv.b_mont.as<Fr>(),
+                                                    (uint32_t)nb, g_d_err);
+  CU(cudaStreamSynchronize(g_stream));
+  dv.nb = nb;
+  return B200_OK;
+}
+
+int poly_div_host(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* q, uint64_t* rem) {
+  if (!a || !b || na == 0 || nb == 0) return fail(B200_EINVAL, "poly_div: bad arguments");
+  if (na < nb) {  // reference: empty quotient, rem = a (r1csqap.go:70-84 loop never runs)
+    if (rem) memcpy(rem, a, na * sizeof(Fr));
+    return B200_OK;
+  }
+  if (!q) return fail(B200_EINVAL, "poly_div: null quotient buffer");
+  Divisor dv;
+  int rc = divisor_init(dv, b, nb);
+  if (rc) return rc;
+  size_t nq = na - nb + 1;
+  DevBuf da, dq, dr;
+  CU(da.alloc(na * sizeof(Fr)));
+  CU(dq.alloc(nq * sizeof(Fr)));
+  if (rem && nb > 1) CU(dr.alloc((nb - 1) * sizeof(Fr)));
+  CU(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  CU(poly_div_device(*g_poly, dv, da.as<Fr>(), na, 0, dq.as<Fr>(), dr.as<Fr>(), g_d_err, g_stream));
+  CU(cudaMemcpyAsync(q, dq.p, nq * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  if (rem && nb > 1) CU(cudaMemcpyAsync(rem, dr.p, (nb - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("poly_div");
+}
+
+#include "prove_host.cuh"
+
 }  // namespace
 
 extern "C" {
+
+int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
+                         size_t m, const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz,
+                         const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
+                         const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
+                         b200_pk_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return groth16_pk_load(at, b1, b2, bacdelta, m, ptd, n_ptd, z, nz, alpha1, beta1, delta1, beta2, delta2, npublic,
+                         window_bits, out);
+}
+int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
+                       const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
+                       uint64_t pi_c[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return groth16_prove(pk, w, nw, px, npx, r, s, pi_a, pi_b, pi_c);
+}
+int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
+                           const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
+                           const uint64_t* g1t, size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic,
+                           int window_bits, b200_pk_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return pinocchio_pk_load(a, ap, b2, bp, c, cp, kp, m, g1t, n_g1t, z, nz, npublic, window_bits, out);
+}
+int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
+                         uint64_t* out_g1 /* 7 x 12: PiA PiAp PiBp PiC PiCp PiH PiKp */, uint64_t pi_b[24]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return pinocchio_prove(pk, w, nw, px, npx, out_g1, pi_b);
+}
+int b200_pk_free(b200_pk_t pk) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_init) return fail(B200_EINVAL, "not initialised");
+  cudaSetDevice(g_device);
+  cudaStreamSynchronize(g_stream);
+  return g_pks.erase(pk) ? B200_OK : fail(B200_EINVAL, "pk_free: bad handle");
+}
+
+int b200_poly_mul(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return poly_mul_host(a, na, b, nb, out);
+}
+int b200_poly_div(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* q, uint64_t* rem) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return poly_div_host(a, na, b, nb, q, rem);
+}
+
 
 int b200_version(void) { return 100; }
 
@@ -286,6 +405,8 @@ int b200_shutdown(void) {
   if (!g_init) return B200_OK;
   cudaSetDevice(g_device);
   g_bases.clear();
+  g_pks.clear();
+  g_poly.reset();
   if (g_d_err) cudaFree(g_d_err);
   if (g_stream) cudaStreamDestroy(g_stream);
   g_d_err = nullptr;

@@ -20,8 +20,9 @@
 //   k_digits_count   signed-digit recode, histogram of bucket sizes (RED.ADD)
 //   k_scan           exclusive prefix sum -> bucket offsets
 //   k_digits_scatter recode again, scatter entry ids into bucket order
-//   k_accumulate     LPB lanes per bucket: gather + XYZZ mixed add, then a
+//   k_accumulate     LPB lanes per bucket slice: gather + XYZZ mixed add, then a
 //                    warp-shuffle tree merges the LPB partial sums
+//   k_merge_slices   buckets that were cut into slices (skewed scalars) are re-joined
 //   k_bucket_reduce  sum_b b*S_b by segments (running sums + small scalar mul)
 //   k_sum_points     tree-sum of the segment results -> one XYZZ record
 #pragma once
@@ -189,44 +190,78 @@ __global__ void k_digits_scatter(const Fr* __restrict__ scalars, MsmShape sh, in
   });
 }
 
-// Exclusive scan of counts[0..m) -> offsets[0..m], cursor = copy of offsets. One block.
-__global__ void k_scan(const uint32_t* __restrict__ counts, uint32_t m, uint32_t* offsets, uint32_t* cursor) {
+// Exclusive scan of counts[0..m) -> offsets[0..m], cursor = copy of offsets, and
+// the SLICE tables: a bucket holding more than `cap` entries is cut into
+// ceil(cnt/cap) equal slices so that skewed scalar distributions (small witness
+// values, a sparse top window, all-ones) cannot serialise on one bucket.  One
+// block; thread t owns a contiguous run of buckets.
+struct SliceTables {
+  uint32_t* slice_off;     // [m+1] first slice id of each bucket (bucket 0 owns none)
+  uint32_t* slice_start;   // [max_slices]
+  uint32_t* slice_end;     // [max_slices]
+};
+__global__ void k_scan(const uint32_t* __restrict__ counts, uint32_t m, uint32_t cap, uint32_t* offsets,
+                       uint32_t* cursor, SliceTables st) {
   __shared__ uint32_t part[1024];
+  __shared__ uint32_t spart[1024];
   uint32_t t = threadIdx.x, T = blockDim.x;
   uint32_t per = (m + T - 1) / T;
   uint32_t lo = t * per, hi = lo + per < m ? lo + per : m;
-  uint32_t sum = 0;
-  for (uint32_t k = lo; k < hi; k++) sum += counts[k];
+  uint32_t sum = 0, ssum = 0;
+  for (uint32_t k = lo; k < hi; k++) {
+    uint32_t c = counts[k];
+    sum += c;
+    ssum += k == 0 ? 0 : (c <= cap ? 1 : (c + cap - 1) / cap);
+  }
   part[t] = sum;
+  spart[t] = ssum;
   __syncthreads();
   for (uint32_t off = 1; off < T; off <<= 1) {  // Hillis-Steele inclusive scan
     uint32_t v = t >= off ? part[t - off] : 0;
+    uint32_t sv = t >= off ? spart[t - off] : 0;
     __syncthreads();
     part[t] += v;
+    spart[t] += sv;
     __syncthreads();
   }
-  uint32_t run = part[t] - sum;
+  uint32_t run = part[t] - sum, srun = spart[t] - ssum;
   for (uint32_t k = lo; k < hi; k++) {
+    uint32_t c = counts[k];
     offsets[k] = run;
     cursor[k] = run;
-    run += counts[k];
+    st.slice_off[k] = srun;
+    if (k) {
+      uint32_t ns = c <= cap ? 1 : (c + cap - 1) / cap;
+      uint32_t each = (c + ns - 1) / ns;
+      for (uint32_t j = 0; j < ns; j++) {
+        uint32_t b0 = run + j * each, b1 = b0 + each;
+        st.slice_start[srun + j] = b0 < run + c ? b0 : run + c;
+        st.slice_end[srun + j] = b1 < run + c ? b1 : run + c;
+      }
+      srun += ns;
+    }
+    run += c;
   }
-  if (t == T - 1) offsets[m] = part[T - 1];
+  if (t == T - 1) {
+    offsets[m] = part[T - 1];
+    st.slice_off[m] = spart[T - 1];
+  }
 }
 
 // ------------------------------------------------------- bucket accumulate
-// LPB lanes cooperate on one bucket: lane l takes entries l, l+LPB, ... of the
-// bucket's slice (coalesced reads of `entries`), gathers the precomputed affine
+// LPB lanes cooperate on one slice (normally = one bucket): lane l takes entries
+// l, l+LPB, ... (coalesced reads of `entries`), gathers the precomputed affine
 // points and mixed-adds them; a warp-shuffle tree then merges the LPB partials.
-template <class F, int LPB>
-__global__ void __launch_bounds__(128)
-k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
-             const uint32_t* __restrict__ offsets, uint32_t nbuckets, XYZZ<F>* __restrict__ buckets) {
+template <class F, int LPB, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB)
+k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries, SliceTables st,
+             uint32_t m, XYZZ<F>* __restrict__ slice_out) {
   uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t b = gt / LPB + 1;  // bucket ids are 1..nbuckets
+  uint32_t sid = gt / LPB;
   uint32_t lane = gt % LPB;
-  bool live = b <= nbuckets;
-  uint32_t start = live ? offsets[b] : 0, end = live ? offsets[b + 1] : 0;
+  uint32_t nslices = st.slice_off[m];
+  bool live = sid < nslices;
+  uint32_t start = live ? st.slice_start[sid] : 0, end = live ? st.slice_end[sid] : 0;
   XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t k = start + lane;
   if (k < end) {
@@ -249,7 +284,39 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
     XYZZ<F> other = shfl_down_struct(acc, off, LPB);
     xyzz_add(acc, other);
   }
-  if (live && lane == 0) buckets[b - 1] = acc;
+  if (live && lane == 0) slice_out[sid] = acc;
+}
+
+// buckets[b-1] = sum of the slices of bucket b.  Thread per bucket copies the
+// common single-slice case; buckets that were split are then summed by the whole
+// warp, one after another.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_merge_slices(const XYZZ<F>* __restrict__ slice_out, SliceTables st, uint32_t nbuckets,
+               XYZZ<F>* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  uint32_t lane = threadIdx.x & 31;
+  uint32_t first = 0, cnt = 0;
+  if (b <= nbuckets) {
+    first = st.slice_off[b];
+    cnt = st.slice_off[b + 1] - first;
+    if (cnt == 1) buckets[b - 1] = slice_out[first];
+  }
+  uint32_t multi = __ballot_sync(0xffffffffu, cnt > 1);
+  while (multi) {
+    int j = __ffs(multi) - 1;
+    multi &= multi - 1;
+    uint32_t f = __shfl_sync(0xffffffffu, first, j), c = __shfl_sync(0xffffffffu, cnt, j);
+    uint32_t bj = __shfl_sync(0xffffffffu, b, j);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lane; k < c; k += 32) xyzz_add(acc, slice_out[f + k]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      XYZZ<F> other = shfl_down_struct(acc, off, 32);
+      xyzz_add(acc, other);
+    }
+    if (lane == 0) buckets[bj - 1] = acc;
+  }
 }
 
 // acc <- m * acc for a small integer m (MSB-first double-and-add)

@@ -93,6 +93,50 @@ int b200_g2_mul_batch(const uint64_t* points_jac, const uint64_t* scalars, size_
 int b200_g1_mul_batch_bcast(const uint64_t* point_jac, const uint64_t* scalars, size_t n, uint64_t* out_jac);
 int b200_g2_mul_batch_bcast(const uint64_t* point_jac, const uint64_t* scalars, size_t n, uint64_t* out_jac);
 
+/* ---- proving keys and the prove path -------------------------------------- */
+/* Upload a Groth16 proving key (groth16.Pk, groth16/groth16.go:15-32) once:
+ *   at        = Pk.G1.At[0..m)            b1 = Pk.G1.BACGamma[0..m)   (G1, 12 u64 each)
+ *   b2        = Pk.G2.BACGamma[0..m)      (G2, 24 u64 each)
+ *   bacdelta  = Pk.BACDelta[0..m)         (entries 0..npublic are ignored, as in groth16.go:248)
+ *   ptd       = Pk.PowersTauDelta[0..n_ptd)
+ *   z         = Pk.Z[0..nz) coefficients  alpha1/beta1/delta1 = Pk.G1.{Alpha,Beta,Delta}
+ *   beta2/delta2 = Pk.G2.{Beta,Delta}     npublic = circuit.NPublic, m = circuit.NVars
+ * The blinding points are appended to the MSM base sets so that
+ * A = sum w_i At_i + alpha + r*delta etc. are single MSMs.          */
+int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
+                         size_t m, const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz,
+                         const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
+                         const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
+                         b200_pk_t* out);
+/* groth16.GenerateProofs (groth16/groth16.go:225-278) with the randomness r, s
+ * supplied by the caller (the Go shim draws them with Fq.Rand, fields/fq.go:116-132,
+ * exactly as the reference does at groth16.go:231-238).  w: nw = NVars witness
+ * scalars (|w_i| mod r); px: npx coefficients.  Outputs are Jacobian points (Z != 1
+ * in general, like the reference's own), standard form.                           */
+int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
+                       const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
+                       uint64_t pi_c[12]);
+/* Pinocchio proving key (snark.Pk, snark.go:16-26): A, Ap, Bp, C, Cp, Kp in G1 and
+ * B in G2, each m points; G1T n_g1t points; Z.                                     */
+int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
+                           const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
+                           const uint64_t* g1t, size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic,
+                           int window_bits, b200_pk_t* out);
+/* snark.GenerateProofs (snark.go:254-289).  out_g1 = 7 Jacobian G1 points in the
+ * order PiA, PiAp, PiBp, PiC, PiCp, PiH, PiKp (84 u64); pi_b = PiB (G2).           */
+int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
+                         uint64_t* out_g1, uint64_t pi_b[24]);
+int b200_pk_free(b200_pk_t pk);
+
+/* ---- polynomials over F_r (coefficient arrays, index = power of x) -------- */
+/* out[0..na+nb-1) = a * b.   Replaces PolynomialField.Mul (r1csqap/r1csqap.go:57-67). */
+int b200_poly_mul(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out);
+/* q[0..na-nb+1) = a div b, rem[0..nb-1) = a mod b (rem may be NULL).
+ * Replaces PolynomialField.Div / DivisorPolynomial (r1csqap/r1csqap.go:70-84,213-216).
+ * b[nb-1] must be non-zero (B200_EDIVZERO; the reference panics on ModInverse(0)).
+ * na < nb: quotient is empty and rem = a (na coefficients), as in the reference. */
+int b200_poly_div(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* q, uint64_t* rem);
+
 #ifdef __cplusplus
 }
 #endif

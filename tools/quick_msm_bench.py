@@ -56,7 +56,9 @@ def main():
     # device-resident timing
     d_s = torch.from_numpy(ss.view(np.int64)).cuda()
     d_out = torch.zeros(64, dtype=torch.int64, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     for _ in range(3):
         _lib.check(L.b200_msm_device(bs.handle, d_s.data_ptr(), n, 0, d_out.data_ptr(), st))
     torch.cuda.synchronize()
