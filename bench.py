@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py — Groth16 prove throughput on B200 (the driver's contract).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--logn 20]
+
+A "step" is one groth16.GenerateProofs (groth16/groth16.go:225-278) on the synthetic
+R1CS shape of SURVEY §8(d): n = 2^logn constraints, m = n+2 signals, NPublic = 1,
+full-width witness, px = h0*Z.  Default workload: n = 2^20 — the size
+BASELINE.json's metric is quoted at; it fits one GPU.
+
+  value   proofs/s with witness, px and CRS resident in HBM (CUDA events, max over ranks)
+  e2e     proofs/s through the host-pointer C ABI (b200_groth16_prove): pinned host
+          buffers, H2D of w and px and D2H of the proof inside the timed region
+  N > 1   the MSMs are sharded by index range, one 1 KB NCCL all-gather of partial
+          sums per proof, final adds on every rank (strong scaling)
+
+`--impl reference` times the reference's own algorithm (oracle/ref_c.c: per-term
+MSB-first double-and-add + add-2007-bl accumulate, exactly groth16.go:243-271) on the
+host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--logn", type=int, default=20)
+    ap.add_argument("--no-extras", action="store_true", help="skip MSM-only / cpu_baseline side measurements")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------- CPU reference arm
+def cpu_reference(syn, budget_s=16.0):
+    """Time the reference algorithm (C restatement, oracle/ref_c.c) on a bounded sample of THIS
+    workload with every host core, and extrapolate linearly in the term count (the cost is exactly
+    linear for full-width scalars).  Returns (proofs_per_sec, info)."""
+    import build as b200build
+    oc = ctypes.CDLL(b200build.build_oracle())
+    threads = max(1, min(os.cpu_count() or 1, 256))
+    from gosnark_b200._lib import ptr
+
+    def run(group, pts, sc, k):
+        fn = oc.oc_g1_msm_loop if group == 1 else oc.oc_g2_msm_loop
+        out = np.zeros(24, dtype=np.uint64)
+        t0 = time.perf_counter()
+        fn(ptr(pts), ptr(sc), ctypes.c_long(k), threads, ptr(out))
+        return time.perf_counter() - t0
+
+    m, n = syn.m, syn.n
+    at = np.ascontiguousarray(syn.at[2:])       # skip the (0,0,0)/tiny entries at the front
+    b2 = np.ascontiguousarray(syn.b2[2:])
+    w = np.ascontiguousarray(syn.w[2:])
+    avail = min(at.shape[0], b2.shape[0], w.shape[0])
+    probe = min(avail, 8 * threads)
+    t1 = run(1, at, w, probe) / probe           # seconds per G1 term (all threads busy)
+    t2 = run(2, b2, w, probe) / probe
+    k1 = int(max(probe, min(avail, budget_s * 0.5 / t1)))
+    k2 = int(max(probe, min(avail, budget_s * 0.5 / t2)))
+    t1 = run(1, at, w, k1) / k1
+    t2 = run(2, b2, w, k2) / k2
+    g1_terms = m + m + (m - 2) + (n - 1)        # A, B1, C, H loops (groth16.go:243-250,269-271)
+    g2_terms = m
+    secs = t1 * g1_terms + t2 * g2_terms
+    info = {"kind": "port", "cores": threads,
+            "sample": f"reference double-and-add loops on {k1} G1 + {k2} G2 terms of this workload, "
+                      f"{threads} threads, extrapolated linearly to {g1_terms} G1 + {g2_terms} G2 terms; "
+                      "h=px/Z (O(n^3) in the reference, r1csqap.go:70-84) excluded in the CPU's favour",
+            "g1_us_per_term": t1 * 1e6, "g2_us_per_term": t2 * 1e6}
+    return 1.0 / secs, info
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    logn = args.logn
+    n = 1 << logn
+    config = {"workload": f"synthetic R1CS 2^{logn} constraints Groth16 prove (m=n+2 signals, NPublic=1, full-width "
+                          "witness, px=h0*Z), CRS points k_i*G with known discrete logs",
+              "constraints": n, "parallelism": f"msm-index-shard x{world}" if world > 1 else "single-gpu",
+              "l2": "inputs larger than L2 (>= 1 GB of precomputed CRS tables gathered per MSM)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from gosnark_b200.synthetic import SyntheticGroth16
+        # the reference arm needs CRS points; mint a bounded slice with the C oracle-free GPU minting if a
+        # GPU is present, else with the Python oracle (tiny)
+        import torch
+        sample_log = min(logn, 14)
+        syn_small = SyntheticGroth16(sample_log, mint=False)
+        if torch.cuda.is_available():
+            from gosnark_b200 import _lib
+            _lib.init(local)
+            syn_small.mint()
+        else:
+            raise SystemExit("reference arm needs the GPU box only to mint sample CRS points")
+        # extrapolate to the full workload size
+        syn_small.m, syn_small.n = n + 2, n
+        vals, info = [], None
+        for i in range(args.warmup + args.steps):
+            v, info = cpu_reference(syn_small, budget_s=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+            if i >= args.warmup:
+                vals.append(v)
+        v = statistics.median(vals)
+        info["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "groth16_proofs_per_sec", "value": v, "unit": "proofs/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)",
+                          "data": "synthetic", "config": config, "cpu_baseline": info,
+                          "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from gosnark_b200 import _lib
+    from gosnark_b200.synthetic import SyntheticGroth16
+    from gosnark_b200._lib import check, ints_to_limbs, lib, limbs_to_ints, ptr
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.init(local)
+    L = lib()
+    syn = SyntheticGroth16(logn)
+    pk = syn.load_pk(rank, world)
+    m = syn.m
+    npx = 2 * n - 1
+    r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
+    d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
+    d_part = torch.zeros(128, dtype=torch.int64, device="cuda")          # 1 KB partial record
+    d_gather = torch.zeros(128 * world, dtype=torch.int64, device="cuda")
+    d_out = torch.zeros(48, dtype=torch.int64, device="cuda")
+    h_w = torch.from_numpy(syn.w.view(np.int64)).pin_memory()
+    h_px = torch.from_numpy(syn.px.view(np.int64)).pin_memory()
+
+    def step_device():
+        if world == 1:
+            check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
+                                              d_out.data_ptr(), st))
+        else:
+            check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
+                                              d_part.data_ptr(), st))
+            dist.all_gather_into_tensor(d_gather, d_part)
+            check(L.b200_groth16_finalize_device(pk, d_gather.data_ptr(), world, ptr(r_l), ptr(s_l),
+                                                 d_out.data_ptr(), st))
+
+    host_out = (np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64))
+
+    def step_e2e():
+        if world == 1:      # the reference-facing call: host pointers in, proof out
+            check(L.b200_groth16_prove(pk, h_w.data_ptr(), m, h_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
+                                       ptr(host_out[0]), ptr(host_out[1]), ptr(host_out[2])))
+            return None
+        d_w.copy_(h_w, non_blocking=True)
+        d_px.copy_(h_px, non_blocking=True)
+        step_device()
+        return d_out.cpu()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        if fn is step_e2e and world == 1:
+            ms = wall      # the host-pointer call synchronises internally on the library's own stream
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- correctness of what we time: proof == the known-discrete-log expectation (rank 0)
+    for _ in range(1):
+        step_device()
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        from oracle import ref_py as o          # checker only
+        out = d_out.cpu().numpy().view(np.uint64)
+        from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+        pa, pc = _unflatten_g1(out[:24])
+        pb = _unflatten_g2(out[24:])[0]
+        ea, eb, ec = syn.expected_dlogs()
+        G1o, G2o = o.BN.G1, o.BN.G2
+        parity = (G1o.affine(pa) == G1o.affine(G1o.mul_scalar(G1o.G, ea))
+                  and G2o.affine(pb) == G2o.affine(G2o.mul_scalar(G2o.G, eb))
+                  and G1o.affine(pc) == G1o.affine(G1o.mul_scalar(G1o.G, ec)))
+        if not parity:
+            print(json.dumps({"error": "proof does not match the known-discrete-log expectation"}))
+            return 1
+
+    # ---- timed region: device-resident
+    for _ in range(args.warmup):
+        step_device()
+    check(L.b200_profile(1))
+    prof0 = (ctypes.c_double * 8)()
+    check(L.b200_profile_read(prof0))          # reset counters
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(step_device, args.steps)
+    prof = (ctypes.c_double * 8)()
+    check(L.b200_profile_read(prof))
+    check(L.b200_profile(0))
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # ---- e2e through the host-pointer API
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+
+    if rank != 0:
+        return 0
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    g1_ms, g1_l, g1_terms = prof[0], max(prof[1], 1), prof[2]
+    ach = 96.0 * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3) / 1e9 if g1_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_accumulate_g1_dram_bytes_per_term", None)
+            if traffic is not None:
+                traffic = traffic * (g1_terms / g1_l)
+    except Exception:
+        pass
+    line = {
+        "metric": "groth16_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)", "data": "synthetic", "config": config,
+        "constraints_per_sec": value * n, "parity_vs_known_dlog": parity,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": "proofs/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 32 * m + 32 * npx, "d2h_bytes_per_step": 384},
+        "gpu_launches": int(prof[6]),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "k_accumulate<Fq> (G1 bucket accumulation)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "traffic": traffic,
+                     "launches_per_step": g1_l / args.steps, "avg_launch_ms": g1_ms / g1_l,
+                     "share_of_step": g1_ms / ms_total,
+                     "note": "integer-ALU bound by construction (SURVEY H8): ~2.2k issue slots per bucket add; "
+                             "HBM fraction is reported as the contract asks, not as the limiter",
+                     "g2": {"avg_launch_ms": prof[3] / max(prof[4], 1), "share_of_step": prof[3] / ms_total}},
+        "algorithmic_bytes_per_proof": syn.algorithmic_bytes(),
+    }
+    if not args.no_extras and world == 1:
+        try:
+            v, info = cpu_reference(syn, budget_s=16.0)
+            info["value"] = v
+            info["unit"] = "proofs/s"
+            line["cpu_baseline"] = info
+        except Exception as e:   # the checker must never take the bench line down
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

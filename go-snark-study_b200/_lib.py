@@ -51,6 +51,12 @@ _SIGNATURES = {
                                ctypes.POINTER(_h)],
     "b200_pinocchio_prove": [_h, _vp, _sz, _vp, _sz, _vp, _vp],
     "b200_pk_free": [_h],
+    "b200_groth16_prove_device": [_h, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp],
+    "b200_groth16_pk_load_shard": [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _sz, _int,
+                                   _int, _int, ctypes.POINTER(_h)],
+    "b200_groth16_finalize_device": [_h, _vp, _int, _vp, _vp, _vp, _vp],
+    "b200_profile": [_int],
+    "b200_profile_read": [ctypes.POINTER(ctypes.c_double)],
 }
 
 

@@ -29,6 +29,20 @@ cudaStream_t g_stream = nullptr;
 int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
 std::unique_ptr<PolyCtx> g_poly;
 
+// ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
+// timing of the dominant kernel (k_accumulate), per group.
+unsigned long long g_launches = 0;
+bool g_prof = false;
+struct ProfRec { cudaEvent_t e0, e1; int group; size_t terms; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -76,14 +90,11 @@ int init_locked(int device) {
   CU(cudaMalloc(&g_d_err, sizeof(int)));
   CU(cudaMemset(g_d_err, 0, sizeof(int)));
   g_poly = std::make_unique<PolyCtx>();
+  g_poly->launch_counter = &g_launches;
   g_device = device;
   g_init = true;
   return B200_OK;
 }
-
-// field type used inside the bucket-accumulation kernel (same storage; F_q multiply inlined)
-template <class F> struct Hot { using type = F; };
-template <> struct Hot<Fq> { using type = FqH; };
 
 inline unsigned nblocks(size_t n, unsigned bs) { return nblk(n, bs); }
 
@@ -224,17 +235,20 @@ int msm_enqueue(Bases* b, const Fr* d_scalars, size_t n, int mont, XYZZ<F>* d_ou
   if (n) k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
   k_scan<<<1, 1024, 0, st>>>(counts, m, cap, offsets, cursor, stb);
   if (n) k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, cursor, entries, g_d_err);
-  using FH = typename Hot<F>::type;
-  static const int variant = getenv("B200_ACC_VARIANT") ? atoi(getenv("B200_ACC_VARIANT")) : 0;  // tuning knob
+  // The out-of-line F_q multiply wins here: the fully inlined madd body (~38 KB of SASS) thrashes the
+  // instruction caches (measured 5.85 ms vs 4.80 ms at 2^20, profiles/r1_notes.md).
   unsigned grid = nblocks((size_t)b->max_slices * LPB, 128);
-  if (variant == 1)
-    k_accumulate<F, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
-  else if (variant == 2)
-    k_accumulate<FH, LPB, 4><<<grid, 128, 0, st>>>(b->table.as<Affine<FH>>(), entries, stb, m, b->slice_out.as<XYZZ<FH>>());
-  else if (variant == 3)
-    k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
-  else
-    k_accumulate<FH, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<FH>>(), entries, stb, m, b->slice_out.as<XYZZ<FH>>());
+  ProfRec pr{};
+  if (g_prof) {
+    pr = ProfRec{prof_event(), prof_event(), b->group, n};
+    cudaEventRecord(pr.e0, st);
+  }
+  k_accumulate<F, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
+  if (g_prof) {
+    cudaEventRecord(pr.e1, st);
+    g_prof_recs.push_back(pr);
+  }
+  g_launches += n ? 7 : 5;
   k_merge_slices<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(b->slice_out.as<XYZZ<F>>(), stb, sh.nbuckets, buckets);
   k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
   k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
@@ -348,7 +362,26 @@ int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t*
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();
   return groth16_pk_load(at, b1, b2, bacdelta, m, ptd, n_ptd, z, nz, alpha1, beta1, delta1, beta2, delta2, npublic,
-                         window_bits, out);
+                         window_bits, 0, 1, out);
+}
+int b200_groth16_pk_load_shard(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
+                               size_t m, const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz,
+                               const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
+                               const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
+                               int rank, int world, b200_pk_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return groth16_pk_load(at, b1, b2, bacdelta, m, ptd, n_ptd, z, nz, alpha1, beta1, delta1, beta2, delta2, npublic,
+                         window_bits, rank, world, out);
+}
+int b200_groth16_finalize_device(b200_pk_t pk, const void* d_parts, int nparts, const uint64_t r[4],
+                                 const uint64_t s[4], void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  ProvingKey* p = find_pk(pk, 1);
+  if (!p || !d_parts || nparts < 1 || !r || !s || !d_out) return fail(B200_EINVAL, "groth16_finalize_device: bad arguments");
+  return groth16_finalize_enqueue(p, (const uint8_t*)d_parts, nparts, r, s, (Fq*)d_out,
+                                  stream ? (cudaStream_t)stream : g_stream);
 }
 int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                        const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
@@ -370,6 +403,41 @@ int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint6
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();
   return pinocchio_prove(pk, w, nw, px, npx, out_g1, pi_b);
+}
+int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const void* d_px, size_t npx,
+                              const uint64_t r[4], const uint64_t s[4], void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  ProvingKey* p = find_pk(pk, 1);
+  if (!p || !d_w || !d_px || !r || !s || !d_out) return fail(B200_EINVAL, "groth16_prove_device: bad arguments");
+  return groth16_enqueue(p, (const Fr*)d_w, nw, (const Fr*)d_px, npx, r, s, (Fq*)d_out,
+                         stream ? (cudaStream_t)stream : g_stream);
+}
+int b200_profile(int enable) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_prof = enable != 0;
+  return B200_OK;
+}
+int b200_profile_read(double out[8]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  if (!out) return fail(B200_EINVAL, "profile_read: null pointer");
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  CU(cudaDeviceSynchronize());
+  for (auto& r : g_prof_recs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    int o = r.group == 1 ? 0 : 3;
+    out[o] += ms;
+    out[o + 1] += 1;
+    out[o + 2] += (double)r.terms;
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  out[6] = (double)g_launches;
+  g_launches = 0;
+  return B200_OK;
 }
 int b200_pk_free(b200_pk_t pk) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -52,6 +52,8 @@ struct NttPlan {
 };
 
 struct PolyCtx {
+  unsigned long long* launch_counter = nullptr;
+  void note(unsigned n) { if (launch_counter) *launch_counter += n; }
   std::map<int, std::unique_ptr<NttPlan>> plans;
   DevBuf bufA, bufB, bufC;  // transform workspaces
 
@@ -88,6 +90,7 @@ struct PolyCtx {
     uint32_t N = 1u << logn, n_half = N >> 1;
     for (uint32_t half = n_half; half >= 1; half >>= 1)
       k_ntt_dif_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw.as<Fr>(), n_half, half, n_half / half);
+    note(logn);
     return cudaGetLastError();
   }
   // bit-reversed -> natural, WITHOUT the 1/N scale (callers fold it into a pointwise product)
@@ -98,6 +101,7 @@ struct PolyCtx {
     uint32_t N = 1u << logn, n_half = N >> 1;
     for (uint32_t half = 1; half <= n_half; half <<= 1)
       k_ntt_dit_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw_inv.as<Fr>(), n_half, half, n_half / half);
+    note(logn);
     return cudaGetLastError();
   }
   // a <- a * b (both already forward-transformed, size N), scaled by 1/N so that
@@ -108,6 +112,7 @@ struct PolyCtx {
     if (e != cudaSuccess) return e;
     uint32_t N = 1u << logn;
     k_pointwise_mul<<<nblk(N, 256), 256, 0, st>>>(a, b, N, pl->n_inv, scale ? 1 : 0);
+    note(1);
     return cudaGetLastError();
   }
 };
@@ -202,6 +207,7 @@ inline cudaError_t poly_div_device(PolyCtx& pc, Divisor& dv, const Fr* d_a, size
   PCU(pc.inverse_unscaled(X, logn, st));
   // rev(q) = X[0..nq)  ->  q natural order, standard form
   k_poly_store<<<nblk(nq, 256), 256, 0, st>>>(X, (uint32_t)nq, 1, 1, d_q_std);
+  pc.note(2);
   if (d_rem_std && nb > 1) {
     int lr = ceil_log2(na);
     size_t Nr = (size_t)1 << lr;

@@ -21,10 +21,16 @@
 struct ProvingKey {
   int kind = 0;  // 1 Groth16, 2 Pinocchio
   size_t m = 0, npublic = 0, n_h_bases = 0;
+  // index-range shard of this rank (world == 1: everything)
+  int rank = 0, world = 1;
+  size_t lo = 0, hi = 0;      // slice of [0, m) for the A / B1 / B2 sets
+  size_t clo = 0;             // slice [clo, hi) of BACDelta (clo >= npublic + 1)
+  size_t plo = 0, phi = 0;    // slice of [0, n_h_bases) for PowersTauDelta
+  DevBuf h_full;              // full quotient (sharded mode)
   std::unique_ptr<Bases> g[8];  // Groth16: A, B1, B2(G2), CH   Pinocchio: A, Ap, B(G2), Bp, C, Cp, Kp, H
   Divisor Z;
   DevBuf s1, s2, s3;   // scalar vectors
-  DevBuf px;           // px coefficients (device)
+  DevBuf px, w_stage;  // px coefficients / witness staging (host-pointer entry points)
   DevBuf res;          // XYZZ results (8 x 256 B)
   DevBuf out_std;      // standard-form Jacobian outputs
   DevBuf rs;           // r, s on device (standard form)
@@ -59,26 +65,38 @@ __device__ void store_jacobian_std(const XYZZ<F>& p, F* out) {
   out[2] = j.Z.from_mont();
 }
 
-// res: [0] A (G1 XYZZ @ +0), [1] B1 (@ +256), [2] B2 (G2 XYZZ @ +512), [3] CH (@ +768)
-// out: PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2)
-__global__ void k_groth16_finalize(const uint8_t* res, const Fr* rs, Fq* out_a, Fq* out_c, Fq2* out_b) {
-  __shared__ XYZZ<Fq> prod[2];
-  const XYZZ<Fq>& A = *reinterpret_cast<const XYZZ<Fq>*>(res);
-  const XYZZ<Fq>& B1 = *reinterpret_cast<const XYZZ<Fq>*>(res + 256);
-  const XYZZ<Fq2>& B2 = *reinterpret_cast<const XYZZ<Fq2>*>(res + 512);
-  const XYZZ<Fq>& CH = *reinterpret_cast<const XYZZ<Fq>*>(res + 768);
+// Partial-result record of one rank: A (G1 XYZZ @ +0), B1 (@ +256), B2 (G2 XYZZ @ +512),
+// CH (@ +768) — 1 KB; `parts` holds nparts consecutive records (1 on a single GPU,
+// world_size after the NCCL all-gather).  rs = {r, s} standard form.
+// out: PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2), Jacobian, standard form.
+constexpr size_t kPartialBytes = 1024;
+__global__ void k_groth16_finalize(const uint8_t* parts, int nparts, const Fr* rs, Fq* out_a, Fq* out_c, Fq2* out_b) {
+  __shared__ XYZZ<Fq> sh[4];  // A, B1, CH, then products reuse [0],[1]
   uint32_t t = threadIdx.x;
-  if (t == 0) prod[0] = xyzz_mul_scalar(A, rs[1]);    // s * PiA     (groth16.go:272)
-  if (t == 32) prod[1] = xyzz_mul_scalar(B1, rs[0]);  // r * piBG1   (groth16.go:273)
+  auto g1_at = [&](int p, int off) { return *reinterpret_cast<const XYZZ<Fq>*>(parts + kPartialBytes * p + off); };
+  if (t == 0 || t == 32 || t == 96) {
+    int off = t == 0 ? 0 : (t == 32 ? 256 : 768);
+    XYZZ<Fq> acc = g1_at(0, off);
+    for (int p = 1; p < nparts; p++) xyzz_add(acc, g1_at(p, off));
+    sh[t == 0 ? 0 : (t == 32 ? 1 : 2)] = acc;
+  }
   if (t == 64) {
-    store_jacobian_std(A, out_a);
-    store_jacobian_std(B2, out_b);
+    XYZZ<Fq2> acc = *reinterpret_cast<const XYZZ<Fq2>*>(parts + 512);
+    for (int p = 1; p < nparts; p++) xyzz_add(acc, *reinterpret_cast<const XYZZ<Fq2>*>(parts + kPartialBytes * p + 512));
+    store_jacobian_std(acc, out_b);
   }
   __syncthreads();
+  XYZZ<Fq> prod;
+  if (t == 0) prod = xyzz_mul_scalar(sh[0], rs[1]);   // s * PiA     (groth16.go:272)
+  if (t == 32) prod = xyzz_mul_scalar(sh[1], rs[0]);  // r * piBG1   (groth16.go:273)
+  if (t == 64) store_jacobian_std(sh[0], out_a);
+  __syncthreads();
+  if (t == 32) sh[3] = prod;
+  __syncthreads();
   if (t == 0) {
-    XYZZ<Fq> c = CH;
-    xyzz_add(c, prod[0]);
-    xyzz_add(c, prod[1]);
+    XYZZ<Fq> c = sh[2];
+    xyzz_add(c, prod);
+    xyzz_add(c, sh[3]);
     store_jacobian_std(c, out_c);
   }
 }
@@ -107,17 +125,18 @@ int pk_common_init(ProvingKey& pk, const uint64_t* z, size_t nz, size_t m) {
   CU(pk.s2.alloc((m + 4) * sizeof(Fr)));
   CU(pk.res.alloc(8 * 256));
   CU(pk.out_std.alloc(64 * sizeof(Fq)));
-  CU(pk.rs.alloc(4 * sizeof(Fr)));
+  CU(pk.rs.alloc(8 * sizeof(Fr)));
   return check_err_flag<Fr>("pk_load(Z)");
 }
 
 int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta, size_t m,
                     const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz, const uint64_t* alpha1,
                     const uint64_t* beta1, const uint64_t* delta1, const uint64_t* beta2, const uint64_t* delta2,
-                    size_t npublic, int c, b200_pk_t* out) {
+                    size_t npublic, int c, int rank, int world, b200_pk_t* out) {
   if (!at || !b1 || !b2 || !bacdelta || !ptd || !alpha1 || !beta1 || !delta1 || !beta2 || !delta2 || !out)
     return fail(B200_EINVAL, "groth16_pk_load: null pointer");
   if (m == 0 || npublic + 1 > m || n_ptd == 0) return fail(B200_EINVAL, "groth16_pk_load: bad sizes");
+  if (world < 1 || rank < 0 || rank >= world) return fail(B200_EINVAL, "groth16_pk_load: bad shard %d/%d", rank, world);
   auto pk = std::make_unique<ProvingKey>();
   pk->kind = 1;
   pk->m = m;
@@ -125,27 +144,37 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   pk->n_h_bases = n_ptd;
   int rc = pk_common_init(*pk, z, nz, m);
   if (rc) return rc;
+  // contiguous index-range shard; the blinding points ride on rank 0 only
+  pk->rank = rank;
+  pk->world = world;
+  size_t lo = pk->lo = m * (size_t)rank / world, hi = pk->hi = m * (size_t)(rank + 1) / world;
+  size_t clo = pk->clo = lo > npublic + 1 ? lo : npublic + 1;
+  if (clo > hi) clo = pk->clo = hi;
+  size_t plo = pk->plo = n_ptd * (size_t)rank / world, phi = pk->phi = n_ptd * (size_t)(rank + 1) / world;
+  static const uint64_t inf1[12] = {0}, inf2[24] = {0};
+  const bool lead = rank == 0;
   {
     PointCat cat(12);
-    cat.add(at, m); cat.add(alpha1, 1); cat.add(delta1, 1);
+    cat.add(at + 12 * lo, hi - lo); cat.add(lead ? alpha1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0]))) return rc;
   }
   {
     PointCat cat(12);
-    cat.add(b1, m); cat.add(beta1, 1); cat.add(delta1, 1);
+    cat.add(b1 + 12 * lo, hi - lo); cat.add(lead ? beta1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1]))) return rc;
   }
   {
     PointCat cat(24);
-    cat.add(b2, m); cat.add(beta2, 1); cat.add(delta2, 1);
+    cat.add(b2 + 24 * lo, hi - lo); cat.add(lead ? beta2 : inf2, 1); cat.add(lead ? delta2 : inf2, 1);
     if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2]))) return rc;
   }
   {
     PointCat cat(12);
-    cat.add(bacdelta + 12 * (npublic + 1), m - npublic - 1); cat.add(ptd, n_ptd); cat.add(delta1, 1);
+    cat.add(bacdelta + 12 * clo, hi - clo); cat.add(ptd + 12 * plo, phi - plo); cat.add(lead ? delta1 : inf1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3]))) return rc;
   }
   CU(pk->s3.alloc((m + n_ptd + 4) * sizeof(Fr)));
+  if (world > 1) CU(pk->h_full.alloc((m + n_ptd + 4) * sizeof(Fr)));
   uint64_t h = g_next_pk++;
   g_pks[h] = std::move(pk);
   *out = h;
@@ -165,49 +194,101 @@ Fr fr_load_std(const uint64_t* v) {
   return r;
 }
 
-int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx, const uint64_t* r,
-                  const uint64_t* s, uint64_t* pi_a, uint64_t* pi_b, uint64_t* pi_c) {
-  ProvingKey* pk = find_pk(h, 1);
-  if (!pk) return fail(B200_EINVAL, "groth16_prove: bad proving-key handle");
-  if (!w || !px || !r || !s || !pi_a || !pi_b || !pi_c) return fail(B200_EINVAL, "groth16_prove: null pointer");
+// tails of the scalar vectors: v = [1, r, 1, s, -rs]
+__global__ void k_groth16_tails(const Fr* v, Fr* sA_tail, Fr* sB_tail, Fr* sCH_last) {
+  if (threadIdx.x | blockIdx.x) return;
+  sA_tail[0] = v[0];
+  sA_tail[1] = v[1];
+  sB_tail[0] = v[2];
+  sB_tail[1] = v[3];
+  sCH_last[0] = v[4];
+}
+
+// Enqueue one Groth16 proof on `st` from DEVICE-resident witness / px (standard
+// form).  d_out receives PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2) in standard form.
+// No host synchronisation.
+int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, size_t npx, const uint64_t* r,
+                    const uint64_t* s, Fq* d_out, cudaStream_t st) {
   size_t m = pk->m, l1 = pk->npublic + 1;
   if (nw != m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, m);
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "groth16_prove: len(px) < len(Z)");
   size_t nq = npx - pk->Z.nb + 1;
   // groth16.go:269-270 indexes PowersTauDelta[i] for i < len(hx): out of range panics in the reference
-  if (nq > pk->n_h_bases) return fail(B200_EINVAL, "groth16_prove: len(hx)=%zu exceeds len(PowersTauDelta)=%zu", nq, pk->n_h_bases);
+  if (nq > pk->n_h_bases)
+    return fail(B200_EINVAL, "groth16_prove: len(hx)=%zu exceeds len(PowersTauDelta)=%zu", nq, pk->n_h_bases);
   Fr fr_r = fr_load_std(r), fr_s = fr_load_std(s);
   if (fr_r.geq_modulus() || fr_s.geq_modulus()) return fail(B200_ERANGE, "groth16_prove: r or s >= field order");
   Fr neg_rs = (fr_r.to_mont() * fr_s.to_mont()).neg().from_mont();  // -(r*s) mod r  (groth16.go:274)
   Fr one = Fr::zero();
   one.l[0] = 1;
-  cudaStream_t st = g_stream;
   Fr* sA = pk->s1.as<Fr>();
   Fr* sB = pk->s2.as<Fr>();
   Fr* sCH = pk->s3.as<Fr>();
-  size_t n_c = m - l1, n_ch = n_c + pk->n_h_bases + 1;
-  Fr tailA[2] = {one, fr_r}, tailB[2] = {one, fr_s}, rs_host[2] = {fr_r, fr_s};
-  CU(pk->px.ensure(npx * sizeof(Fr)));
-  CU(cudaMemcpyAsync(sA, w, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(sA + m, tailA, sizeof tailA, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(sB + m, tailB, sizeof tailB, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(pk->rs.p, rs_host, sizeof rs_host, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(sCH + n_ch - 1, &neg_rs, sizeof(Fr), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(sB, sA, m * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  if (n_c) CU(cudaMemcpyAsync(sCH, sA + l1, n_c * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  if (pk->n_h_bases > nq) CU(cudaMemsetAsync(sCH + n_c + nq, 0, (pk->n_h_bases - nq) * sizeof(Fr), st));
+  (void)l1;
+  const size_t lo = pk->lo, hi = pk->hi, clo = pk->clo, plo = pk->plo, phi = pk->phi;
+  const size_t n_ab = hi - lo, n_c = hi - clo, n_p = phi - plo, n_ch = n_c + n_p + 1;
+  Fr small[7] = {one, fr_r, one, fr_s, neg_rs, fr_r, fr_s};
+  CU(cudaMemcpyAsync(pk->rs.p, small, sizeof small, cudaMemcpyHostToDevice, st));
+  k_groth16_tails<<<1, 32, 0, st>>>(pk->rs.as<Fr>(), sA + n_ab, sB + n_ab, sCH + n_ch - 1);
+  if (n_ab) {
+    CU(cudaMemcpyAsync(sA, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(sB, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+  }
+  if (n_c) CU(cudaMemcpyAsync(sCH, d_w + clo, n_c * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
   uint8_t* res = pk->res.as<uint8_t>();
   int rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[0].get(), sA, m + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[1].get(), sB, m + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res + 256), st))) return rc;
-  if ((rc = msm_enqueue<Fq2>(pk->g[2].get(), sB, m + 2, 0, reinterpret_cast<XYZZ<Fq2>*>(res + 512), st))) return rc;
-  // hx = px / Z  (groth16.go:266) written straight into the CH scalar vector
-  CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, sCH + n_c, nullptr, g_d_err, st));
+  if ((rc = msm_enqueue<Fq>(pk->g[0].get(), sA, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
+  if ((rc = msm_enqueue<Fq>(pk->g[1].get(), sB, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res + 256), st))) return rc;
+  if ((rc = msm_enqueue<Fq2>(pk->g[2].get(), sB, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq2>*>(res + 512), st))) return rc;
+  // hx = px / Z  (groth16.go:266).  Single GPU: written straight into the CH scalar vector.  Sharded: every
+  // rank repeats the (cheap) division and keeps its slice h[plo, phi) — no inter-GPU traffic.
+  Fr* h_dst = pk->world == 1 ? sCH + n_c : pk->h_full.as<Fr>();
+  CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, st));
+  size_t have = nq > plo ? (nq < phi ? nq - plo : n_p) : 0;   // valid h coefficients inside this rank's slice
+  if (pk->world > 1 && have)
+    CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + plo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+  if (n_p > have) CU(cudaMemsetAsync(sCH + n_c + have, 0, (n_p - have) * sizeof(Fr), st));
   if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, n_ch, 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), st))) return rc;
-  Fq* o = pk->out_std.as<Fq>();
-  k_groth16_finalize<<<1, 96, 0, st>>>(res, pk->rs.as<Fr>(), o, o + 3, reinterpret_cast<Fq2*>(o + 6));
+  if (pk->world == 1) {
+    k_groth16_finalize<<<1, 128, 0, st>>>(res, 1, pk->rs.as<Fr>() + 5, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
+  } else {  // hand the 1 KB partial record to the caller's all-gather
+    CU(cudaMemcpyAsync(d_out, res, kPartialBytes, cudaMemcpyDeviceToDevice, st));
+  }
+  g_launches += 2;
   CU(cudaGetLastError());
+  return B200_OK;
+}
+
+// Sharded mode, after the all-gather: sum the `world` partial records and finish the proof.
+int groth16_finalize_enqueue(ProvingKey* pk, const uint8_t* d_parts, int nparts, const uint64_t* r, const uint64_t* s,
+                             Fq* d_out, cudaStream_t st) {
+  Fr rs_host[2] = {fr_load_std(r), fr_load_std(s)};
+  if (rs_host[0].geq_modulus() || rs_host[1].geq_modulus()) return fail(B200_ERANGE, "groth16_finalize: r or s >= field order");
+  CU(cudaMemcpyAsync(pk->rs.as<Fr>() + 5, rs_host, sizeof rs_host, cudaMemcpyHostToDevice, st));
+  k_groth16_finalize<<<1, 128, 0, st>>>(d_parts, nparts, pk->rs.as<Fr>() + 5, d_out, d_out + 3,
+                                        reinterpret_cast<Fq2*>(d_out + 6));
+  g_launches += 1;
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx, const uint64_t* r,
+                  const uint64_t* s, uint64_t* pi_a, uint64_t* pi_b, uint64_t* pi_c) {
+  ProvingKey* pk = find_pk(h, 1);
+  if (!pk) return fail(B200_EINVAL, "groth16_prove: bad proving-key handle");
+  if (!w || !px || !r || !s || !pi_a || !pi_b || !pi_c) return fail(B200_EINVAL, "groth16_prove: null pointer");
+  if (nw != pk->m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, pk->m);
+  if (pk->world != 1)
+    return fail(B200_EINVAL, "groth16_prove: sharded key (rank %d/%d): use b200_groth16_prove_device + "
+                             "b200_groth16_finalize_device around the all-gather", pk->rank, pk->world);
+  cudaStream_t st = g_stream;
+  CU(pk->px.ensure(npx * sizeof(Fr)));
+  CU(pk->w_stage.ensure(nw * sizeof(Fr)));
+  CU(cudaMemcpyAsync(pk->w_stage.p, w, nw * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  Fq* o = pk->out_std.as<Fq>();
+  int rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, pk->px.as<Fr>(), npx, r, s, o, st);
+  if (rc) return rc;
   uint64_t host_out[48];
   CU(cudaMemcpyAsync(host_out, o, sizeof host_out, cudaMemcpyDeviceToHost, st));
   rc = check_err_flag<Fr>("groth16_prove");  // synchronises

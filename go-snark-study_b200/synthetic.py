@@ -1,0 +1,114 @@
+"""Synthetic Groth16 workloads with KNOWN DISCRETE LOGS.
+
+Shape: n constraints, m = n + 2 signals, NPublic = 1 (the only shape the
+reference supports).  Every CRS point is k*G for a seeded k, minted on
+the GPU with the reference-order batch MulScalar, so the exact proof the
+reference's GenerateProofs would return on the same (pk, w, px, r, s) is known
+in the exponent and costs one CPU scalar multiplication per proof element to
+check — bit-exact parity at 2^16 / 2^20 without an O(n) CPU run.
+
+px is minted as h0 * Z (GPU product) for a seeded h0 and a seeded monic Z of
+degree n, so the division is exact and h must come back equal to h0.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import check, ints_to_limbs, lib, limbs_to_ints, ptr
+from .bn128 import G1, G2, R, _flatten_g1, _flatten_g2
+
+SEED_WITNESS, SEED_TOXIC, SEED_RS, SEED_POINTS, SEED_SCALARS = 0x5EED0001, 0x5EED0002, 0x5EED0003, 0x5EED0004, 0x5EED0005
+
+
+def rand_limbs(n, seed):
+    """n scalars uniform in [0, 2^253) (< r), as (n, 4) uint64 limbs."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return np.ascontiguousarray(a)
+
+
+def mint_points(group, dlog_limbs):
+    """[k_i * G] as Jacobian standard-form limbs, via b200_g*_mul_batch_bcast."""
+    n = dlog_limbs.shape[0]
+    words = 12 if group == 1 else 24
+    gen = _flatten_g1([G1.G]) if group == 1 else _flatten_g2([G2.G])
+    out = np.zeros((n, words), dtype=np.uint64)
+    fn = lib().b200_g1_mul_batch_bcast if group == 1 else lib().b200_g2_mul_batch_bcast
+    check(fn(ptr(gen), ptr(dlog_limbs), n, ptr(out)))
+    return out
+
+
+class SyntheticGroth16:
+    def __init__(self, logn, mint=True):
+        self.logn = logn
+        n = self.n = 1 << logn
+        m = self.m = n + 2
+        self.npublic = 1
+        self.n_ptd = m - 1
+        # discrete logs of the CRS arrays
+        self.k_at = rand_limbs(m, SEED_POINTS)
+        self.k_b = rand_limbs(m, SEED_POINTS + 1)
+        self.k_c = rand_limbs(m, SEED_POINTS + 2)
+        self.k_c[: self.npublic + 1] = 0                      # BACDelta[0..NPublic] = (0,0,0), groth16.go:177-180
+        self.k_ptd = rand_limbs(self.n_ptd, SEED_POINTS + 3)
+        tox = rand_limbs(3, SEED_TOXIC)
+        self.k_alpha, self.k_beta, self.k_delta = (tox[i:i + 1] for i in range(3))
+        self.w = rand_limbs(m, SEED_WITNESS)
+        self.w[0] = (1, 0, 0, 0)                              # signal "one"
+        rs = limbs_to_ints(rand_limbs(2, SEED_RS))
+        self.r, self.s = rs[0] >> 13, rs[1] >> 13             # 240-bit, the range of Fq.Rand (H2)
+        self.h0 = rand_limbs(n - 1, SEED_SCALARS)
+        self.z = rand_limbs(n + 1, SEED_SCALARS + 1)
+        self.z[n] = (1, 0, 0, 0)                              # monic, degree n = m - 2 (groth16.go:122-132)
+        if mint:
+            self.mint()
+
+    def mint(self):
+        self.at = mint_points(1, self.k_at)
+        self.b1 = mint_points(1, self.k_b)
+        self.b2 = mint_points(2, self.k_b)
+        self.cd = mint_points(1, self.k_c)
+        self.ptd = mint_points(1, self.k_ptd)
+        self.alpha1, self.beta1, self.delta1 = (mint_points(1, k) for k in (self.k_alpha, self.k_beta, self.k_delta))
+        self.beta2, self.delta2 = (mint_points(2, k) for k in (self.k_beta, self.k_delta))
+        n = self.n
+        self.px = np.zeros((2 * n - 1, 4), dtype=np.uint64)
+        check(lib().b200_poly_mul(ptr(self.h0), n - 1, ptr(self.z), n + 1, ptr(self.px)))
+
+    def load_pk(self, rank=0, world=1, window_bits=0):
+        h = _lib._h(0)
+        check(lib().b200_groth16_pk_load_shard(
+            ptr(self.at), ptr(self.b1), ptr(self.b2), ptr(self.cd), self.m, ptr(self.ptd), self.n_ptd,
+            ptr(self.z), self.n + 1, ptr(self.alpha1), ptr(self.beta1), ptr(self.delta1), ptr(self.beta2),
+            ptr(self.delta2), self.npublic, window_bits, rank, world, h))
+        return h.value
+
+    def pk_dict(self):
+        """The same key as a groth16.Pk-shaped dict of Python ints (small sizes only)."""
+        from .bn128 import _unflatten_g1, _unflatten_g2
+        return {"Z": limbs_to_ints(self.z), "BACDelta": _unflatten_g1(self.cd), "PowersTauDelta": _unflatten_g1(self.ptd),
+                "G1": {"Alpha": _unflatten_g1(self.alpha1)[0], "Beta": _unflatten_g1(self.beta1)[0],
+                       "Delta": _unflatten_g1(self.delta1)[0], "At": _unflatten_g1(self.at),
+                       "BACGamma": _unflatten_g1(self.b1)},
+                "G2": {"Beta": _unflatten_g2(self.beta2)[0], "Delta": _unflatten_g2(self.delta2)[0],
+                       "BACGamma": _unflatten_g2(self.b2)}}
+
+    def expected_dlogs(self):
+        """Discrete logs (w.r.t. the generators) of PiA, PiB, PiC that
+        groth16.GenerateProofs (groth16.go:225-278) yields on this input."""
+        w = limbs_to_ints(self.w)
+        dot = lambda ks, ws: sum(a * b for a, b in zip(limbs_to_ints(ks), ws)) % R
+        alpha, beta, delta = (limbs_to_ints(k)[0] for k in (self.k_alpha, self.k_beta, self.k_delta))
+        r, s = self.r, self.s
+        a = (dot(self.k_at, w) + alpha + r * delta) % R
+        b = (dot(self.k_b, w) + beta + s * delta) % R
+        l1 = self.npublic + 1
+        c_msm = dot(self.k_c[l1:], w[l1:])
+        h_msm = dot(self.k_ptd[: self.n - 1], limbs_to_ints(self.h0))
+        c = (c_msm + h_msm + s * a + r * b - r * s * delta) % R
+        return a, b, c
+
+    def algorithmic_bytes(self):
+        """96 B per G1 term, 160 B per G2 term, each MSM counted independently."""
+        m, n = self.m, self.n
+        return 96 * m + 96 * m + 160 * m + 96 * (m - 2) + 96 * (n - 1)

@@ -116,6 +116,26 @@ int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t*
 int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                        const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
                        uint64_t pi_c[12]);
+/* Same with the witness and px already resident in DEVICE memory (standard form)
+ * and the 48-u64 result (PiA | PiC | PiB) left in device memory on `stream`; no
+ * host synchronisation.  This is the region bench.py times as `value`.            */
+int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const void* d_px, size_t npx,
+                              const uint64_t r[4], const uint64_t s[4], void* d_out, void* stream);
+/* Multi-GPU (one process per GPU): rank `rank` of `world` keeps the contiguous
+ * index slice [m*rank/world, m*(rank+1)/world) of every CRS array (and the same
+ * fraction of PowersTauDelta); the blinding points ride on rank 0.  With such a key
+ * b200_groth16_prove_device leaves a 1024-byte PARTIAL record (XYZZ sums A | B1 |
+ * B2 | CH) in d_out instead of a proof; the caller all-gathers the records of all
+ * ranks (NCCL, 1 KB per rank) and calls b200_groth16_finalize_device, which adds
+ * them and applies groth16.go:272-275.  No EC-point reduction exists in NCCL, hence
+ * gather-then-add.                                                     */
+int b200_groth16_pk_load_shard(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
+                               size_t m, const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz,
+                               const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
+                               const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
+                               int rank, int world, b200_pk_t* out);
+int b200_groth16_finalize_device(b200_pk_t pk, const void* d_parts, int nparts, const uint64_t r[4],
+                                 const uint64_t s[4], void* d_out, void* stream);
 /* Pinocchio proving key (snark.Pk, snark.go:16-26): A, Ap, Bp, C, Cp, Kp in G1 and
  * B in G2, each m points; G1T n_g1t points; Z.                                     */
 int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
@@ -127,6 +147,14 @@ int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t
 int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                          uint64_t* out_g1, uint64_t pi_b[24]);
 int b200_pk_free(b200_pk_t pk);
+
+/* ---- instrumentation (bench.py) -------------------------------------------- */
+/* b200_profile(1) brackets every bucket-accumulation launch (the dominant kernel)
+ * with CUDA events on its stream.  b200_profile_read synchronises and returns
+ * out = { G1 ms total, G1 launches, G1 terms total, G2 ms total, G2 launches,
+ *         G2 terms total, kernel launches since the last read, 0 } and resets.      */
+int b200_profile(int enable);
+int b200_profile_read(double out[8]);
 
 /* ---- polynomials over F_r (coefficient arrays, index = power of x) -------- */
 /* out[0..na+nb-1) = a * b.   Replaces PolynomialField.Mul (r1csqap/r1csqap.go:57-67). */
