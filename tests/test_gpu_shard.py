@@ -1,0 +1,80 @@
+"""GPU: the multi-GPU decomposition run on ONE device — two index-range shards
+of the same proving key (rank 0/2 and 1/2), partial records concatenated as the
+NCCL all-gather would, b200_groth16_finalize_device — must reproduce the
+unsharded proof and the known-discrete-log expectation."""
+import numpy as np
+import pytest
+
+from oracle import ref_py as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("logn,world", [(6, 2), (8, 3), (10, 8)])
+def test_sharded_equals_single(logn, world):
+    import torch
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+    from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+    from gosnark_b200.synthetic import SyntheticGroth16
+    _lib.init()
+    L = lib()
+    syn = SyntheticGroth16(logn)
+    m, npx = syn.m, 2 * syn.n - 1
+    r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
+    d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
+    d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+
+    def read(d):
+        out = d.cpu().numpy().view(np.uint64)
+        pa, pc = _unflatten_g1(out[:24])
+        return pa, _unflatten_g2(out[24:])[0], pc
+
+    pk1 = syn.load_pk(0, 1)
+    d_single = torch.zeros(48, dtype=torch.int64, device="cuda")
+    check(L.b200_groth16_prove_device(pk1, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
+                                      d_single.data_ptr(), None))
+    parts = torch.zeros(128 * world, dtype=torch.int64, device="cuda")
+    pks = [syn.load_pk(rk, world) for rk in range(world)]
+    for rk, pk in enumerate(pks):
+        check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
+                                          parts[128 * rk:].data_ptr(), None))
+    d_out = torch.zeros(48, dtype=torch.int64, device="cuda")
+    check(L.b200_groth16_finalize_device(pks[0], parts.data_ptr(), world, ptr(r_l), ptr(s_l), d_out.data_ptr(), None))
+    check(L.b200_profile_read((__import__("ctypes").c_double * 8)()))      # device sync
+    G1, G2 = o.BN.G1, o.BN.G2
+    a1, b1, c1 = read(d_single)
+    a2, b2, c2 = read(d_out)
+    assert G1.affine(a1) == G1.affine(a2) and G2.affine(b1) == G2.affine(b2) and G1.affine(c1) == G1.affine(c2)
+    ea, eb, ec = syn.expected_dlogs()
+    assert G1.affine(a2) == G1.affine(G1.mul_scalar(G1.G, ea))
+    assert G2.affine(b2) == G2.affine(G2.mul_scalar(G2.G, eb))
+    assert G1.affine(c2) == G1.affine(G1.mul_scalar(G1.G, ec))
+    # host-pointer API refuses a sharded key
+    with pytest.raises(_lib.B200Error):
+        pa, pb, pc = (np.zeros(k, dtype=np.uint64) for k in (12, 24, 12))
+        check(L.b200_groth16_prove(pks[1], ptr(syn.w), m, ptr(syn.px), npx, ptr(r_l), ptr(s_l), ptr(pa), ptr(pb), ptr(pc)))
+    for pk in pks + [pk1]:
+        check(L.b200_pk_free(pk))
+
+
+def test_synthetic_matches_oracle_prove():
+    """The synthetic key as a groth16.Pk dict through the reference-order oracle gives the same proof
+    (ties the known-dlog expectation to groth16.go:225-278 itself), n = 8."""
+    from gosnark_b200 import _lib, groth16
+    from gosnark_b200._lib import limbs_to_ints
+    from gosnark_b200.synthetic import SyntheticGroth16
+    _lib.init()
+    syn = SyntheticGroth16(3)
+    pk = syn.pk_dict()
+    w, px = limbs_to_ints(syn.w), limbs_to_ints(syn.px)
+    ref, raw = o.groth16_prove(syn.m, syn.npublic, pk, w, px, syn.r, syn.s)
+    assert raw["hx"] == limbs_to_ints(syn.h0)
+    ours = groth16.GenerateProofs({"NVars": syn.m, "NPublic": syn.npublic}, pk, w, px, r=syn.r, s=syn.s)
+    G1, G2 = o.BN.G1, o.BN.G2
+    for k, G in (("PiA", G1), ("PiB", G2), ("PiC", G1)):
+        assert G.affine(ours[k]) == G.affine(ref[k])
+    ea, eb, ec = syn.expected_dlogs()
+    assert G1.affine(ref["PiA"]) == G1.affine(G1.mul_scalar(G1.G, ea))
+    assert G1.affine(ref["PiC"]) == G1.affine(G1.mul_scalar(G1.G, ec))
