@@ -26,6 +26,7 @@ std::string g_err;
 bool g_init = false;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
+cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};  // side streams: independent MSMs of one proof overlap
 int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
 std::unique_ptr<PolyCtx> g_poly;
 
@@ -87,6 +88,7 @@ int init_locked(int device) {
   if (device >= count) return fail(B200_EINVAL, "device %d out of range (%d devices)", device, count);
   CU(cudaSetDevice(device));
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
   CU(cudaMalloc(&g_d_err, sizeof(int)));
   CU(cudaMemset(g_d_err, 0, sizeof(int)));
   g_poly = std::make_unique<PolyCtx>();
@@ -110,18 +112,42 @@ int pick_window_bits(size_t n) {
   return best;
 }
 
+// Output of the digit-recode / counting-sort front end for one scalar vector.  It depends only on the
+// scalars and the window shape, so base sets that consume the SAME scalars (A, B1, B2 of a Groth16
+// proof) share one SortScratch read-only.
+struct SortScratch {
+  MsmShape sh{};            // shape it was allocated for (n = capacity)
+  DevBuf counts, offsets, cursor, entries, slice_off, slice_start, slice_end;
+  uint32_t max_slices = 0;
+  SliceTables tables() const { return SliceTables{slice_off.as<uint32_t>(), slice_start.as<uint32_t>(), slice_end.as<uint32_t>()}; }
+};
+
 struct Bases {
   int group = 0;  // 1: G1 (Fq), 2: G2 (Fq2)
   size_t n = 0;
   MsmShape sh{};
   DevBuf table;    // [nwin][n] Affine<F>
-  // per-MSM scratch (MSMs on one base set are serialised on a stream)
+  // per-base-set scratch of the bucket phase (different base sets may run concurrently)
   DevBuf scalars;  // n * 32 B (host-scalar entry points)
-  DevBuf counts, offsets, cursor, entries, buckets, partials, result, out_std;
-  DevBuf slice_off, slice_start, slice_end, slice_out;
-  uint32_t max_slices = 0;
+  DevBuf slice_out, buckets, partials, result, out_std;
+  SortScratch sort;  // own front-end scratch (stand-alone MSMs)
   uint32_t nseg = 0, seg = 0;
 };
+
+int sort_alloc(SortScratch& ss, const MsmShape& sh) {
+  ss.sh = sh;
+  size_t entries = (size_t)sh.nwin * sh.n;
+  CU(ss.counts.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
+  CU(ss.offsets.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
+  CU(ss.cursor.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
+  CU(ss.entries.alloc(entries * sizeof(uint32_t)));
+  // slices: every bucket owns >= 1; a bucket above cap = 2*mean entries is cut => at most B + B/2 + 1
+  ss.max_slices = sh.nbuckets + sh.nbuckets / 2 + 2;
+  CU(ss.slice_off.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
+  CU(ss.slice_start.alloc((size_t)ss.max_slices * sizeof(uint32_t)));
+  CU(ss.slice_end.alloc((size_t)ss.max_slices * sizeof(uint32_t)));
+  return B200_OK;
+}
 
 std::map<uint64_t, std::unique_ptr<Bases>> g_bases;
 uint64_t g_next_handle = 1;
@@ -157,17 +183,12 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
   size_t entries = (size_t)sh.nwin * n;
   CU(b->table.alloc(entries * sizeof(Affine<F>)));
   CU(b->scalars.alloc(n * sizeof(Fr)));
-  CU(b->counts.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
-  CU(b->offsets.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
-  CU(b->cursor.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
-  CU(b->entries.alloc(entries * sizeof(uint32_t)));
   CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
-  // slices: every bucket owns >= 1; a bucket above cap = 2*mean entries is cut => at most B + B/2 + 1
-  b->max_slices = sh.nbuckets + sh.nbuckets / 2 + 2;
-  CU(b->slice_off.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
-  CU(b->slice_start.alloc((size_t)b->max_slices * sizeof(uint32_t)));
-  CU(b->slice_end.alloc((size_t)b->max_slices * sizeof(uint32_t)));
-  CU(b->slice_out.alloc((size_t)b->max_slices * sizeof(XYZZ<F>)));
+  {
+    int rc_ = sort_alloc(b->sort, sh);
+    if (rc_) return rc_;
+  }
+  CU(b->slice_out.alloc((size_t)b->sort.max_slices * sizeof(XYZZ<F>)));
   b->seg = sh.nbuckets >= 4096 ? 16 : (sh.nbuckets >= 256 ? 4 : 1);
   b->nseg = (sh.nbuckets + b->seg - 1) / b->seg;
   CU(b->partials.alloc((size_t)b->nseg * sizeof(XYZZ<F>)));
@@ -214,46 +235,96 @@ Bases* find_bases(b200_bases_t h, int group) {
 }
 
 // Enqueue one MSM on `st`; result XYZZ written to d_out (device).
+// Accumulate launch: LPB lanes per bucket slice (2 / 4 / 8 by mean bucket population).  Register budget:
+// G1 runs at 128 regs (4 CTAs/SM); occupancy / prefetch variants measured within 2% of each other
+// (profiles/r1_notes.md) — the kernel is bound by the IMAD.WIDE issue rate, not by latency hiding.
+template <class F, int LPB>
+void launch_accumulate_l(const Affine<F>* table, const uint32_t* entries, SliceTables stb, uint32_t m,
+                         XYZZ<F>* out, uint32_t max_slices, cudaStream_t st) {
+  unsigned grid = nblocks((size_t)max_slices * LPB, 128);
+  if constexpr (sizeof(F) == sizeof(Fq)) {
+    k_accumulate<F, LPB, 4, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+  } else {
+    static const int minb = getenv("B200_ACC_MINB_G2") ? atoi(getenv("B200_ACC_MINB_G2")) : 1;  // tuning knob
+    if (minb >= 4) k_accumulate<F, LPB, 4, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    else if (minb >= 2) k_accumulate<F, LPB, 2, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    else k_accumulate<F, LPB, 1, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+  }
+}
 template <class F>
-int msm_enqueue(Bases* b, const Fr* d_scalars, size_t n, int mont, XYZZ<F>* d_out, cudaStream_t st) {
-  if (n > b->n) return fail(B200_EINVAL, "msm: n=%zu exceeds base set size %zu", n, b->n);
-  MsmShape sh = b->sh;
+void launch_accumulate(int lpb, const Affine<F>* table, const uint32_t* entries, SliceTables stb, uint32_t m,
+                       XYZZ<F>* out, uint32_t max_slices, cudaStream_t st) {
+  switch (lpb) {
+    case 2: launch_accumulate_l<F, 2>(table, entries, stb, m, out, max_slices, st); break;
+    case 4: launch_accumulate_l<F, 4>(table, entries, stb, m, out, max_slices, st); break;
+    default: launch_accumulate_l<F, 8>(table, entries, stb, m, out, max_slices, st); break;
+  }
+}
+
+constexpr int kLPB = 8;
+
+// Front end: signed-digit recode + counting sort of n scalars into bucket order (3 launches).
+int msm_sort(SortScratch& ss, const MsmShape& shape, const Fr* d_scalars, size_t n, int mont, cudaStream_t st) {
+  if (n > ss.sh.n || shape.c != ss.sh.c || shape.table_stride != ss.sh.table_stride)
+    return fail(B200_EINVAL, "msm_sort: shape mismatch");
+  MsmShape sh = shape;
   sh.n = (uint32_t)n;
-  uint32_t* counts = b->counts.as<uint32_t>();
-  uint32_t* offsets = b->offsets.as<uint32_t>();
-  uint32_t* cursor = b->cursor.as<uint32_t>();
-  uint32_t* entries = b->entries.as<uint32_t>();
-  XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
-  XYZZ<F>* partials = b->partials.as<XYZZ<F>>();
   uint32_t m = sh.nbuckets + 1;  // counts[0] unused (digit 0), buckets 1..B
-  constexpr int LPB = 8;
   // slice cap: twice the mean bucket population (uniform scalars never split), at least 4 per lane
   uint64_t mean = ((uint64_t)sh.nwin * n + sh.nbuckets - 1) / sh.nbuckets;
-  uint32_t cap = (uint32_t)(2 * mean < 4 * LPB ? 4 * LPB : 2 * mean);
-  SliceTables stb{b->slice_off.as<uint32_t>(), b->slice_start.as<uint32_t>(), b->slice_end.as<uint32_t>()};
+  uint32_t cap = (uint32_t)(2 * mean < 4 * kLPB ? 4 * kLPB : 2 * mean);
+  uint32_t* counts = ss.counts.as<uint32_t>();
   CU(cudaMemsetAsync(counts, 0, (m + 1) * sizeof(uint32_t), st));
   if (n) k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
-  k_scan<<<1, 1024, 0, st>>>(counts, m, cap, offsets, cursor, stb);
-  if (n) k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, cursor, entries, g_d_err);
+  k_scan<<<1, 1024, 0, st>>>(counts, m, cap, ss.offsets.as<uint32_t>(), ss.cursor.as<uint32_t>(), ss.tables());
+  if (n) k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, ss.cursor.as<uint32_t>(),
+                                                           ss.entries.as<uint32_t>(), g_d_err);
+  g_launches += n ? 3 : 1;
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+// Back end: bucket accumulation over the sorted entries of `ss`, slice merge, weighted bucket
+// reduction and final tree sum -> one XYZZ record in d_out (4 launches).
+template <class F>
+int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out, cudaStream_t st) {
+  const MsmShape& sh = b->sh;
+  if (ss.sh.c != sh.c || ss.sh.table_stride != sh.table_stride || ss.max_slices != b->sort.max_slices)
+    return fail(B200_EINVAL, "msm_buckets: sort scratch does not match the base set");
+  uint32_t m = sh.nbuckets + 1;
+  XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
+  XYZZ<F>* partials = b->partials.as<XYZZ<F>>();
+  static const int lpb_env = getenv("B200_LPB") ? atoi(getenv("B200_LPB")) : 0;  // tuning knob
+  SliceTables stb = ss.tables();
   // The out-of-line F_q multiply wins here: the fully inlined madd body (~38 KB of SASS) thrashes the
   // instruction caches (measured 5.85 ms vs 4.80 ms at 2^20, profiles/r1_notes.md).
-  unsigned grid = nblocks((size_t)b->max_slices * LPB, 128);
   ProfRec pr{};
   if (g_prof) {
-    pr = ProfRec{prof_event(), prof_event(), b->group, n};
+    pr = ProfRec{prof_event(), prof_event(), b->group, n_terms};
     cudaEventRecord(pr.e0, st);
   }
-  k_accumulate<F, LPB><<<grid, 128, 0, st>>>(b->table.as<Affine<F>>(), entries, stb, m, b->slice_out.as<XYZZ<F>>());
+  uint64_t mean = ((uint64_t)sh.nwin * n_terms + sh.nbuckets - 1) / sh.nbuckets;
+  int lpb = lpb_env ? lpb_env : (mean >= 384 ? 8 : (mean >= 96 ? 4 : 2));
+  launch_accumulate<F>(lpb, b->table.as<Affine<F>>(), ss.entries.as<uint32_t>(), stb, m,
+                       b->slice_out.as<XYZZ<F>>(), ss.max_slices, st);
   if (g_prof) {
     cudaEventRecord(pr.e1, st);
     g_prof_recs.push_back(pr);
   }
-  g_launches += n ? 7 : 5;
   k_merge_slices<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(b->slice_out.as<XYZZ<F>>(), stb, sh.nbuckets, buckets);
   k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
   k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
+  g_launches += 4;
   CU(cudaGetLastError());
   return B200_OK;
+}
+
+template <class F>
+int msm_enqueue(Bases* b, const Fr* d_scalars, size_t n, int mont, XYZZ<F>* d_out, cudaStream_t st) {
+  if (n > b->n) return fail(B200_EINVAL, "msm: n=%zu exceeds base set size %zu", n, b->n);
+  int rc = msm_sort(b->sort, b->sh, d_scalars, n, mont, st);
+  if (rc) return rc;
+  return msm_buckets<F>(b, b->sort, n, d_out, st);
 }
 
 template <class F>
@@ -477,6 +548,7 @@ int b200_shutdown(void) {
   g_poly.reset();
   if (g_d_err) cudaFree(g_d_err);
   if (g_stream) cudaStreamDestroy(g_stream);
+  for (auto& sd : g_side) { if (sd) cudaStreamDestroy(sd); sd = nullptr; }
   g_d_err = nullptr;
   g_stream = nullptr;
   g_init = false;

@@ -11,12 +11,18 @@
 //     piB1 = sum w_i B1_i + Beta1 + s*Delta                       (:244,259-262)
 //     PiB  = sum w_i B2_i + Beta2 + s*Delta2                      (:245,260-264)
 //     PiC  = sum_{i>l} w_i C_i + sum h_i PTD_i + s*PiA + r*piB1 - rs*Delta   (:248-275)
-// become four MSMs:
-//     A-set  = At ++ [Alpha, Delta]      scalars  w ++ [1, r]
-//     B1-set = B1 ++ [Beta1, Delta]      scalars  w ++ [1, s]
-//     B2-set = B2 ++ [Beta2, Delta2]     scalars  w ++ [1, s]
+// become four MSMs, the first three over ONE scalar vector W = w ++ [1, r, s] (O = infinity):
+//     A-set  = At ++ [Alpha, Delta,  O     ]
+//     B1-set = B1 ++ [Beta1, O,      Delta ]
+//     B2-set = B2 ++ [Beta2, O,      Delta2]
 //     CH-set = C[l+1..m) ++ PTD ++ [Delta]   scalars  w[l+1..m) ++ h ++ 0.. ++ [-rs]
-// plus the two variable-base products s*PiA and r*piB1 (k_groth16_finalize).
+// so the digit recode + counting sort of W is done once and shared by A, B1 and B2
+// (the sorted entry list depends only on the scalars).  The two variable-base
+// products s*PiA and r*piB1 run on a side stream while B2 / CH are still accumulating.
+//
+// Streams: the four bucket phases are independent, so they are issued on four streams
+// (caller's + 3 side streams): the latency-bound tails (bucket reduction, tree sum) of
+// one MSM overlap the throughput-bound accumulation of the others.
 
 struct ProvingKey {
   int kind = 0;  // 1 Groth16, 2 Pinocchio
@@ -27,6 +33,8 @@ struct ProvingKey {
   size_t clo = 0;             // slice [clo, hi) of BACDelta (clo >= npublic + 1)
   size_t plo = 0, phi = 0;    // slice of [0, n_h_bases) for PowersTauDelta
   DevBuf h_full;              // full quotient (sharded mode)
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  ~ProvingKey() { for (auto e : ev) if (e) cudaEventDestroy(e); }
   std::unique_ptr<Bases> g[8];  // Groth16: A, B1, B2(G2), CH   Pinocchio: A, Ap, B(G2), Bp, C, Cp, Kp, H
   Divisor Z;
   DevBuf s1, s2, s3;   // scalar vectors
@@ -126,6 +134,7 @@ int pk_common_init(ProvingKey& pk, const uint64_t* z, size_t nz, size_t m) {
   CU(pk.res.alloc(8 * 256));
   CU(pk.out_std.alloc(64 * sizeof(Fq)));
   CU(pk.rs.alloc(8 * sizeof(Fr)));
+  for (auto& e : pk.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return check_err_flag<Fr>("pk_load(Z)");
 }
 
@@ -155,17 +164,17 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   const bool lead = rank == 0;
   {
     PointCat cat(12);
-    cat.add(at + 12 * lo, hi - lo); cat.add(lead ? alpha1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1);
+    cat.add(at + 12 * lo, hi - lo); cat.add(lead ? alpha1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1); cat.add(inf1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0]))) return rc;
   }
   {
     PointCat cat(12);
-    cat.add(b1 + 12 * lo, hi - lo); cat.add(lead ? beta1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1);
+    cat.add(b1 + 12 * lo, hi - lo); cat.add(lead ? beta1 : inf1, 1); cat.add(inf1, 1); cat.add(lead ? delta1 : inf1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1]))) return rc;
   }
   {
     PointCat cat(24);
-    cat.add(b2 + 24 * lo, hi - lo); cat.add(lead ? beta2 : inf2, 1); cat.add(lead ? delta2 : inf2, 1);
+    cat.add(b2 + 24 * lo, hi - lo); cat.add(lead ? beta2 : inf2, 1); cat.add(inf2, 1); cat.add(lead ? delta2 : inf2, 1);
     if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2]))) return rc;
   }
   {
@@ -194,22 +203,42 @@ Fr fr_load_std(const uint64_t* v) {
   return r;
 }
 
-// tails of the scalar vectors: v = [1, r, 1, s, -rs]
-__global__ void k_groth16_tails(const Fr* v, Fr* sA_tail, Fr* sB_tail, Fr* sCH_last) {
+// tails of the scalar vectors: v = [1, r, s, -rs]
+__global__ void k_groth16_tails(const Fr* v, Fr* sW_tail, Fr* sCH_last) {
   if (threadIdx.x | blockIdx.x) return;
-  sA_tail[0] = v[0];
-  sA_tail[1] = v[1];
-  sB_tail[0] = v[2];
-  sB_tail[1] = v[3];
-  sCH_last[0] = v[4];
+  sW_tail[0] = v[0];
+  sW_tail[1] = v[1];
+  sW_tail[2] = v[2];
+  sCH_last[0] = v[3];
 }
 
+// prod[0] = s * A, prod[1] = r * B1  (groth16.go:272-273); res layout as in k_groth16_finalize
+__global__ void k_groth16_products(const uint8_t* res, const Fr* rs, XYZZ<Fq>* prod) {
+  uint32_t t = threadIdx.x;
+  if (t == 0) prod[0] = xyzz_mul_scalar(*reinterpret_cast<const XYZZ<Fq>*>(res), rs[1]);
+  if (t == 32) prod[1] = xyzz_mul_scalar(*reinterpret_cast<const XYZZ<Fq>*>(res + 256), rs[0]);
+}
+__global__ void k_groth16_combine(const uint8_t* res, const XYZZ<Fq>* prod, Fq* out_a, Fq* out_c, Fq2* out_b) {
+  uint32_t t = threadIdx.x;
+  if (t == 0) {
+    XYZZ<Fq> c = *reinterpret_cast<const XYZZ<Fq>*>(res + 768);
+    xyzz_add(c, prod[0]);
+    xyzz_add(c, prod[1]);
+    store_jacobian_std(c, out_c);
+  }
+  if (t == 32) store_jacobian_std(*reinterpret_cast<const XYZZ<Fq>*>(res), out_a);
+  if (t == 64) store_jacobian_std(*reinterpret_cast<const XYZZ<Fq2>*>(res + 512), out_b);
+}
+
+#define EV_REC(e, stream) CU(cudaEventRecord((e), (stream)))
+#define EV_WAIT(stream, e) CU(cudaStreamWaitEvent((stream), (e), 0))
+
 // Enqueue one Groth16 proof on `st` from DEVICE-resident witness / px (standard
-// form).  d_out receives PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2) in standard form.
-// No host synchronisation.
+// form).  d_out receives PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2) in standard form
+// (or, for a sharded key, the 1 KB partial record).  No host synchronisation.
 int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, size_t npx, const uint64_t* r,
                     const uint64_t* s, Fq* d_out, cudaStream_t st) {
-  size_t m = pk->m, l1 = pk->npublic + 1;
+  size_t m = pk->m;
   if (nw != m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, m);
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "groth16_prove: len(px) < len(Z)");
   size_t nq = npx - pk->Z.nb + 1;
@@ -221,40 +250,62 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   Fr neg_rs = (fr_r.to_mont() * fr_s.to_mont()).neg().from_mont();  // -(r*s) mod r  (groth16.go:274)
   Fr one = Fr::zero();
   one.l[0] = 1;
-  Fr* sA = pk->s1.as<Fr>();
-  Fr* sB = pk->s2.as<Fr>();
+  Fr* sW = pk->s1.as<Fr>();
   Fr* sCH = pk->s3.as<Fr>();
-  (void)l1;
   const size_t lo = pk->lo, hi = pk->hi, clo = pk->clo, plo = pk->plo, phi = pk->phi;
   const size_t n_ab = hi - lo, n_c = hi - clo, n_p = phi - plo, n_ch = n_c + n_p + 1;
-  Fr small[7] = {one, fr_r, one, fr_s, neg_rs, fr_r, fr_s};
+  cudaStream_t s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
+  cudaEvent_t e_in = pk->ev[0], e_w = pk->ev[1], e_a = pk->ev[2], e_b1 = pk->ev[3], e_b2 = pk->ev[4],
+              e_ch = pk->ev[5], e_prod = pk->ev[6];
+  Fr small[6] = {one, fr_r, fr_s, neg_rs, fr_r, fr_s};
   CU(cudaMemcpyAsync(pk->rs.p, small, sizeof small, cudaMemcpyHostToDevice, st));
-  k_groth16_tails<<<1, 32, 0, st>>>(pk->rs.as<Fr>(), sA + n_ab, sB + n_ab, sCH + n_ch - 1);
-  if (n_ab) {
-    CU(cudaMemcpyAsync(sA, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(sB, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  }
+  k_groth16_tails<<<1, 32, 0, st>>>(pk->rs.as<Fr>(), sW + n_ab, sCH + n_ch - 1);
+  if (n_ab) CU(cudaMemcpyAsync(sW, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
   if (n_c) CU(cudaMemcpyAsync(sCH, d_w + clo, n_c * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+  EV_REC(e_in, st);
   uint8_t* res = pk->res.as<uint8_t>();
   int rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[0].get(), sA, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[1].get(), sB, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq>*>(res + 256), st))) return rc;
-  if ((rc = msm_enqueue<Fq2>(pk->g[2].get(), sB, n_ab + 2, 0, reinterpret_cast<XYZZ<Fq2>*>(res + 512), st))) return rc;
-  // hx = px / Z  (groth16.go:266).  Single GPU: written straight into the CH scalar vector.  Sharded: every
-  // rank repeats the (cheap) division and keeps its slice h[plo, phi) — no inter-GPU traffic.
+  // --- side stream 3: hx = px / Z (groth16.go:266), then the CH MSM.  Single GPU: h is written straight
+  // into the CH scalar vector.  Sharded: every rank repeats the (cheap) division and keeps its slice
+  // h[plo, phi) — no inter-GPU traffic.
+  EV_WAIT(s3, e_in);
   Fr* h_dst = pk->world == 1 ? sCH + n_c : pk->h_full.as<Fr>();
-  CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, st));
+  CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, s3));
   size_t have = nq > plo ? (nq < phi ? nq - plo : n_p) : 0;   // valid h coefficients inside this rank's slice
   if (pk->world > 1 && have)
-    CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + plo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  if (n_p > have) CU(cudaMemsetAsync(sCH + n_c + have, 0, (n_p - have) * sizeof(Fr), st));
-  if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, n_ch, 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), st))) return rc;
+    CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + plo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
+  if (n_p > have) CU(cudaMemsetAsync(sCH + n_c + have, 0, (n_p - have) * sizeof(Fr), s3));
+  if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, n_ch, 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), s3))) return rc;
+  EV_REC(e_ch, s3);
+  // --- main stream: one sort of W shared by the A, B1, B2 bucket phases
+  SortScratch& sw = pk->g[0]->sort;
+  if ((rc = msm_sort(sw, pk->g[0]->sh, sW, n_ab + 3, 0, st))) return rc;
+  EV_REC(e_w, st);
+  EV_WAIT(s1, e_w);
+  if ((rc = msm_buckets<Fq>(pk->g[1].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
+  EV_REC(e_b1, s1);
+  EV_WAIT(s2, e_w);
+  if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
+  EV_REC(e_b2, s2);
+  if ((rc = msm_buckets<Fq>(pk->g[0].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
+  EV_REC(e_a, st);
   if (pk->world == 1) {
-    k_groth16_finalize<<<1, 128, 0, st>>>(res, 1, pk->rs.as<Fr>() + 5, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
+    // s*A and r*B1 on side stream 1 while B2 / CH are still running
+    XYZZ<Fq>* prod = reinterpret_cast<XYZZ<Fq>*>(res + 1024);
+    EV_WAIT(s1, e_a);
+    k_groth16_products<<<1, 64, 0, s1>>>(res, pk->rs.as<Fr>() + 4, prod);
+    EV_REC(e_prod, s1);
+    EV_WAIT(st, e_prod);
+    EV_WAIT(st, e_b2);
+    EV_WAIT(st, e_ch);
+    k_groth16_combine<<<1, 96, 0, st>>>(res, prod, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
   } else {  // hand the 1 KB partial record to the caller's all-gather
+    EV_WAIT(st, e_b1);
+    EV_WAIT(st, e_b2);
+    EV_WAIT(st, e_ch);
     CU(cudaMemcpyAsync(d_out, res, kPartialBytes, cudaMemcpyDeviceToDevice, st));
   }
-  g_launches += 2;
+  g_launches += 3;
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -264,8 +315,8 @@ int groth16_finalize_enqueue(ProvingKey* pk, const uint8_t* d_parts, int nparts,
                              Fq* d_out, cudaStream_t st) {
   Fr rs_host[2] = {fr_load_std(r), fr_load_std(s)};
   if (rs_host[0].geq_modulus() || rs_host[1].geq_modulus()) return fail(B200_ERANGE, "groth16_finalize: r or s >= field order");
-  CU(cudaMemcpyAsync(pk->rs.as<Fr>() + 5, rs_host, sizeof rs_host, cudaMemcpyHostToDevice, st));
-  k_groth16_finalize<<<1, 128, 0, st>>>(d_parts, nparts, pk->rs.as<Fr>() + 5, d_out, d_out + 3,
+  CU(cudaMemcpyAsync(pk->rs.as<Fr>() + 6, rs_host, sizeof rs_host, cudaMemcpyHostToDevice, st));
+  k_groth16_finalize<<<1, 128, 0, st>>>(d_parts, nparts, pk->rs.as<Fr>() + 6, d_out, d_out + 3,
                                         reinterpret_cast<Fq2*>(d_out + 6));
   g_launches += 1;
   CU(cudaGetLastError());
@@ -341,29 +392,50 @@ int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* p
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "pinocchio_prove: len(px) < len(Z)");
   size_t nq = npx - pk->Z.nb + 1;
   if (nq > pk->n_h_bases) return fail(B200_EINVAL, "pinocchio_prove: len(hx)=%zu exceeds len(G1T)=%zu", nq, pk->n_h_bases);
-  cudaStream_t st = g_stream;
+  cudaStream_t st = g_stream, s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
+  cudaEvent_t e_in = pk->ev[0], e_wp = pk->ev[1], e_w = pk->ev[2], e1 = pk->ev[3], e2 = pk->ev[4], e3 = pk->ev[5];
   Fr* dw = pk->s1.as<Fr>();
   Fr* dh = pk->s3.as<Fr>();
   CU(pk->px.ensure(npx * sizeof(Fr)));
   CU(cudaMemcpyAsync(dw, w, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  EV_REC(e_in, st);
   uint8_t* res = pk->res.as<uint8_t>();
   auto R1 = [&](int k) { return reinterpret_cast<XYZZ<Fq>*>(res + 256 * k); };
   int rc;
   // result slots: 0 PiA, 1 PiAp, 2 PiBp, 3 PiC, 4 PiCp, 5 PiH, 6 PiKp, 7 PiB(G2)
+  // side stream 3: hx = px / Z (snark.go:280) and PiH (snark.go:284-286)
+  EV_WAIT(s3, e_in);
+  CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, s3));
+  if ((rc = msm_enqueue<Fq>(pk->g[7].get(), dh, nq, 0, R1(5), s3))) return rc;
+  // two shared sorts: w[l+1..m) feeds PiA, PiAp (snark.go:265-268); w feeds PiB, PiBp, PiC, PiCp, PiKp (:270-278)
   if (m > l1) {
-    if ((rc = msm_enqueue<Fq>(pk->g[0].get(), dw + l1, m - l1, 0, R1(0), st))) return rc;
-    if ((rc = msm_enqueue<Fq>(pk->g[1].get(), dw + l1, m - l1, 0, R1(1), st))) return rc;
+    SortScratch& swp = pk->g[0]->sort;
+    if ((rc = msm_sort(swp, pk->g[0]->sh, dw + l1, m - l1, 0, st))) return rc;
+    EV_REC(e_wp, st);
+    EV_WAIT(s1, e_wp);
+    if ((rc = msm_buckets<Fq>(pk->g[1].get(), swp, m - l1, R1(1), s1))) return rc;
   } else {
     CU(cudaMemsetAsync(res, 0, 512, st));
   }
-  if ((rc = msm_enqueue<Fq2>(pk->g[2].get(), dw, m, 0, reinterpret_cast<XYZZ<Fq2>*>(res + 256 * 7), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[3].get(), dw, m, 0, R1(2), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[4].get(), dw, m, 0, R1(3), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[5].get(), dw, m, 0, R1(4), st))) return rc;
-  if ((rc = msm_enqueue<Fq>(pk->g[6].get(), dw, m, 0, R1(6), st))) return rc;
-  CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, st));   // snark.go:280
-  if ((rc = msm_enqueue<Fq>(pk->g[7].get(), dh, nq, 0, R1(5), st))) return rc;               // snark.go:284-286
+  SortScratch& sw = pk->g[3]->sort;
+  if ((rc = msm_sort(sw, pk->g[3]->sh, dw, m, 0, st))) return rc;
+  EV_REC(e_w, st);
+  EV_WAIT(s2, e_w);
+  if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, m, reinterpret_cast<XYZZ<Fq2>*>(res + 256 * 7), s2))) return rc;
+  EV_WAIT(s1, e_w);
+  if ((rc = msm_buckets<Fq>(pk->g[4].get(), sw, m, R1(3), s1))) return rc;
+  if ((rc = msm_buckets<Fq>(pk->g[5].get(), sw, m, R1(4), s1))) return rc;
+  EV_WAIT(s3, e_w);
+  if ((rc = msm_buckets<Fq>(pk->g[6].get(), sw, m, R1(6), s3))) return rc;
+  if (m > l1 && (rc = msm_buckets<Fq>(pk->g[0].get(), pk->g[0]->sort, m - l1, R1(0), st))) return rc;
+  if ((rc = msm_buckets<Fq>(pk->g[3].get(), sw, m, R1(2), st))) return rc;
+  EV_REC(e1, s1);
+  EV_REC(e2, s2);
+  EV_REC(e3, s3);
+  EV_WAIT(st, e1);
+  EV_WAIT(st, e2);
+  EV_WAIT(st, e3);
   Fq* o = pk->out_std.as<Fq>();
   k_pinocchio_finalize<<<1, 64, 0, st>>>(res, o, reinterpret_cast<Fq2*>(o + 21));
   CU(cudaGetLastError());
