@@ -55,6 +55,15 @@ _SIGNATURES = {
     "b200_groth16_pk_load_shard": [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _sz, _int,
                                    _int, _int, ctypes.POINTER(_h)],
     "b200_groth16_finalize_device": [_h, _vp, _int, _vp, _vp, _vp, _vp],
+    "b200_poly_add": [_vp, _sz, _vp, _sz, _vp],
+    "b200_poly_sub": [_vp, _sz, _vp, _sz, _vp],
+    "b200_poly_eval": [_vp, _sz, _vp, _vp],
+    "b200_r1cs_to_qap": [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp],
+    "b200_combine_polynomials": [_vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp],
+    "b200_g1_add_batch": [_vp, _vp, _sz, _vp], "b200_g2_add_batch": [_vp, _vp, _sz, _vp],
+    "b200_g1_double_batch": [_vp, _sz, _vp], "b200_g2_double_batch": [_vp, _sz, _vp],
+    "b200_g1_neg_batch": [_vp, _sz, _vp], "b200_g2_neg_batch": [_vp, _sz, _vp],
+    "b200_g1_affine_batch": [_vp, _sz, _vp], "b200_g2_affine_batch": [_vp, _sz, _vp],
     "b200_profile": [_int],
     "b200_profile_read": [ctypes.POINTER(ctypes.c_double)],
 }

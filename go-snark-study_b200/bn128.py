@@ -113,6 +113,50 @@ class _Group:
         identical X,Y,Z whenever |e| < r)."""
         return self.MulScalarBatch([p], [e])[0]
 
+    # element-wise group law with the reference's formulas (X,Y,Z-exact): g1.go:32-170 / g2.go:32-200
+    def _op(self, name, pts, qts=None, out_fe=3):
+        n = len(pts)
+        flat = _flatten_g1 if self._group == 1 else _flatten_g2
+        words = (4 if self._group == 1 else 8) * out_fe
+        out = np.zeros(n * words, dtype=np.uint64)
+        fn = getattr(lib(), f"b200_g{self._group}_{name}_batch")
+        if qts is None:
+            check(fn(ptr(flat(pts)), n, ptr(out)))
+        else:
+            check(fn(ptr(flat(pts)), ptr(flat(qts)), n, ptr(out)))
+        return out
+
+    def Add(self, p1, p2):
+        return (_unflatten_g1 if self._group == 1 else _unflatten_g2)(self._op("add", [p1], [p2]))[0]
+
+    def Double(self, p):
+        return (_unflatten_g1 if self._group == 1 else _unflatten_g2)(self._op("double", [p]))[0]
+
+    def Neg(self, p):
+        return (_unflatten_g1 if self._group == 1 else _unflatten_g2)(self._op("neg", [p]))[0]
+
+    def Sub(self, a, b):                      # g1.go:98-100
+        return self.Add(a, self.Neg(b))
+
+    def IsZero(self, p):                      # g1.go:28-30
+        z = p[2]
+        return z == 0 if self._group == 1 else (z[0] == 0 and z[1] == 0)
+
+    def Affine(self, p):
+        """G1.Affine -> (x, y), infinity (0, 0) (g1.go:157-170); G2.Affine -> (x, y, one), infinity
+        ((0,0),(1,0),(0,0)) (g2.go:183-200)."""
+        v = limbs_to_ints(self._op("affine", [p], out_fe=2))
+        if self._group == 1:
+            return (v[0], v[1])
+        if self.IsZero(p):
+            return ((0, 0), (1, 0), (0, 0))
+        return ((v[0], v[1]), (v[2], v[3]), (1, 0))
+
+    def Equal(self, p1, p2):                  # g1.go:172-193: same point <=> same affine coordinates
+        if self.IsZero(p1) or self.IsZero(p2):
+            return self.IsZero(p1) and self.IsZero(p2)
+        return self.Affine(p1) == self.Affine(p2)
+
     def MSM(self, points, scalars, window_bits=0):
         bs = BaseSet(self._group, points, window_bits=window_bits)
         try:

@@ -16,6 +16,7 @@
 #include "b200snark.h"
 #include "msm.cuh"
 #include "poly_host.cuh"
+#include "qap.cuh"
 
 using namespace b200;
 
@@ -421,6 +422,118 @@ int poly_div_host(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 
 #include "prove_host.cuh"
 
+// ---- dense QAP API (small n) -------------------------------------------------
+int r1cs_to_qap_host(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, size_t m, uint64_t* alphas,
+                     uint64_t* betas, uint64_t* gammas, uint64_t* z) {
+  if (!a || !b || !c || !alphas || !betas || !gammas || !z) return fail(B200_EINVAL, "r1cs_to_qap: null pointer");
+  if (n == 0 || m < 2 || n > 8191 || m > 8193) return fail(B200_EINVAL, "r1cs_to_qap: dense API supports 1 <= n <= 8191");
+  cudaStream_t st = g_stream;
+  DevBuf zn, L, M, out, zz;
+  size_t nz = m - 2;  // Z = prod_{i=1}^{m-2} (x - i)   (r1csqap.go:177-186)
+  size_t zmax = (n > nz ? n : nz) + 1;
+  CU(zn.alloc(zmax * sizeof(Fr)));
+  CU(L.alloc(n * n * sizeof(Fr)));
+  CU(M.alloc(n * m * sizeof(Fr)));
+  CU(out.alloc(m * n * sizeof(Fr)));
+  CU(zz.alloc((nz + 1) * sizeof(Fr)));
+  k_zero_poly<<<1, 1024, 0, st>>>(zn.as<Fr>(), (uint32_t)n);
+  k_lagrange_basis<<<nblk(n, 128), 128, 0, st>>>(zn.as<Fr>(), (uint32_t)n, L.as<Fr>());
+  const uint64_t* in[3] = {a, b, c};
+  uint64_t* outs[3] = {alphas, betas, gammas};
+  for (int k = 0; k < 3; k++) {
+    CU(cudaMemcpyAsync(M.p, in[k], n * m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    dim3 grid(nblk(n, 128), (unsigned)m);
+    k_qap_interpolate<<<grid, 128, 0, st>>>(M.as<Fr>(), (uint32_t)n, (uint32_t)m, L.as<Fr>(), out.as<Fr>(), g_d_err);
+    CU(cudaMemcpyAsync(outs[k], out.p, m * n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  k_zero_poly<<<1, 1024, 0, st>>>(zn.as<Fr>(), (uint32_t)nz);
+  k_poly_store<<<nblk(nz + 1, 256), 256, 0, st>>>(zn.as<Fr>(), (uint32_t)(nz + 1), 0, 1, zz.as<Fr>());
+  CU(cudaMemcpyAsync(z, zz.p, (nz + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  CU(cudaGetLastError());
+  return check_err_flag<Fr>("r1cs_to_qap");
+}
+
+int combine_polynomials_host(const uint64_t* r, size_t m, const uint64_t* ap, const uint64_t* bp, const uint64_t* cp,
+                             size_t n, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px) {
+  if (!r || !ap || !bp || !cp || !ax || !bx || !cx || !px || m == 0 || n == 0)
+    return fail(B200_EINVAL, "combine_polynomials: bad arguments");
+  cudaStream_t st = g_stream;
+  DevBuf dr, dP, mont[3], stdv[3], prod;
+  CU(dr.alloc(m * sizeof(Fr)));
+  CU(dP.alloc(m * n * sizeof(Fr)));
+  CU(prod.alloc((2 * n - 1) * sizeof(Fr)));
+  CU(cudaMemcpyAsync(dr.p, r, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  const uint64_t* in[3] = {ap, bp, cp};
+  uint64_t* outs[3] = {ax, bx, cx};
+  for (int k = 0; k < 3; k++) {
+    CU(mont[k].alloc(n * sizeof(Fr)));
+    CU(stdv[k].alloc(n * sizeof(Fr)));
+    CU(cudaMemcpyAsync(dP.p, in[k], m * n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    k_combine<<<nblk(n, 128), 128, 0, st>>>(dr.as<Fr>(), (uint32_t)m, dP.as<Fr>(), (uint32_t)n, mont[k].as<Fr>(),
+                                            stdv[k].as<Fr>(), g_d_err);
+    CU(cudaMemcpyAsync(outs[k], stdv[k].p, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  // px = ax*bx - cx   (r1csqap.go:208)
+  CU(poly_mul_device(*g_poly, mont[0].as<Fr>(), n, 1, mont[1].as<Fr>(), n, 1, prod.as<Fr>(), g_d_err, st));
+  k_poly_addsub<<<nblk(2 * n - 1, 256), 256, 0, st>>>(prod.as<Fr>(), (uint32_t)(2 * n - 1), stdv[2].as<Fr>(), (uint32_t)n, 1,
+                                                      prod.as<Fr>(), g_d_err);
+  CU(cudaMemcpyAsync(px, prod.p, (2 * n - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  CU(cudaGetLastError());
+  return check_err_flag<Fr>("combine_polynomials");
+}
+
+int poly_addsub_host(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, int sub, uint64_t* out) {
+  size_t n = na > nb ? na : nb;
+  if (n == 0) return B200_OK;
+  if ((na && !a) || (nb && !b) || !out) return fail(B200_EINVAL, "poly_add/sub: null pointer");
+  DevBuf da, db, dout;
+  CU(da.alloc((na ? na : 1) * sizeof(Fr)));
+  CU(db.alloc((nb ? nb : 1) * sizeof(Fr)));
+  CU(dout.alloc(n * sizeof(Fr)));
+  if (na) CU(cudaMemcpyAsync(da.p, a, na * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  if (nb) CU(cudaMemcpyAsync(db.p, b, nb * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  k_poly_addsub<<<nblk(n, 256), 256, 0, g_stream>>>(da.as<Fr>(), (uint32_t)na, db.as<Fr>(), (uint32_t)nb, sub, dout.as<Fr>(), g_d_err);
+  CU(cudaMemcpyAsync(out, dout.p, n * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("poly_add/sub");
+}
+
+int poly_eval_host(const uint64_t* v, size_t n, const uint64_t* x, uint64_t* out) {
+  if (!x || !out || (n && !v)) return fail(B200_EINVAL, "poly_eval: null pointer");
+  DevBuf dv, dout;
+  CU(dv.alloc((n ? n : 1) * sizeof(Fr)));
+  CU(dout.alloc(sizeof(Fr)));
+  if (n) CU(cudaMemcpyAsync(dv.p, v, n * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  Fr xs = fr_load_std(x);
+  if (xs.geq_modulus()) return fail(B200_ERANGE, "poly_eval: x >= r");
+  k_poly_eval<<<1, 256, 0, g_stream>>>(dv.as<Fr>(), (uint32_t)n, xs, dout.as<Fr>(), g_d_err);
+  CU(cudaMemcpyAsync(out, dout.p, sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("poly_eval");
+}
+
+template <class F>
+int group_op_host(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
+  if (!p || !out || (op == 0 && !q)) return fail(B200_EINVAL, "group op: null pointer");
+  if (n == 0) return B200_OK;
+  DevBuf dp, dq, dout;
+  size_t out_fe = op == 3 ? 2 : 3;
+  CU(dp.alloc(n * 3 * sizeof(F)));
+  CU(dout.alloc(n * out_fe * sizeof(F)));
+  CU(cudaMemcpyAsync(dp.p, p, n * 3 * sizeof(F), cudaMemcpyHostToDevice, g_stream));
+  if (op == 0) {
+    CU(dq.alloc(n * 3 * sizeof(F)));
+    CU(cudaMemcpyAsync(dq.p, q, n * 3 * sizeof(F), cudaMemcpyHostToDevice, g_stream));
+  }
+  if (op == 3)
+    k_group_affine<F><<<nblk(n, 128), 128, 0, g_stream>>>(dp.as<F>(), n, dout.as<F>(), g_d_err);
+  else
+    k_group_op<F><<<nblk(n, 128), 128, 0, g_stream>>>(op, dp.as<F>(), dq.as<F>(), n, dout.as<F>(), g_d_err);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, n * out_fe * sizeof(F), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<F>("group op");
+}
+
 }  // namespace
 
 extern "C" {
@@ -517,6 +630,30 @@ int b200_pk_free(b200_pk_t pk) {
   cudaStreamSynchronize(g_stream);
   return g_pks.erase(pk) ? B200_OK : fail(B200_EINVAL, "pk_free: bad handle");
 }
+
+#define B200_API_BODY(expr)              \
+  std::lock_guard<std::mutex> lk(g_mu);  \
+  NEED_INIT();                           \
+  return expr;
+int b200_r1cs_to_qap(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, size_t m, uint64_t* alphas,
+                     uint64_t* betas, uint64_t* gammas, uint64_t* z) {
+  B200_API_BODY(r1cs_to_qap_host(a, b, c, n, m, alphas, betas, gammas, z))
+}
+int b200_combine_polynomials(const uint64_t* r, size_t m, const uint64_t* ap, const uint64_t* bp, const uint64_t* cp,
+                             size_t n, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px) {
+  B200_API_BODY(combine_polynomials_host(r, m, ap, bp, cp, n, ax, bx, cx, px))
+}
+int b200_poly_add(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) { B200_API_BODY(poly_addsub_host(a, na, b, nb, 0, out)) }
+int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) { B200_API_BODY(poly_addsub_host(a, na, b, nb, 1, out)) }
+int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]) { B200_API_BODY(poly_eval_host(v, n, x, out)) }
+int b200_g1_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(0, p, q, n, out)) }
+int b200_g1_double_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(1, p, nullptr, n, out)) }
+int b200_g1_neg_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(2, p, nullptr, n, out)) }
+int b200_g1_affine_batch(const uint64_t* p, size_t n, uint64_t* out_xy) { B200_API_BODY(group_op_host<Fq>(3, p, nullptr, n, out_xy)) }
+int b200_g2_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq2>(0, p, q, n, out)) }
+int b200_g2_double_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq2>(1, p, nullptr, n, out)) }
+int b200_g2_neg_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq2>(2, p, nullptr, n, out)) }
+int b200_g2_affine_batch(const uint64_t* p, size_t n, uint64_t* out_xy) { B200_API_BODY(group_op_host<Fq2>(3, p, nullptr, n, out_xy)) }
 
 int b200_poly_mul(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -165,6 +165,35 @@ int b200_poly_mul(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
  * na < nb: quotient is empty and rem = a (na coefficients), as in the reference. */
 int b200_poly_div(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* q, uint64_t* rem);
 
+int b200_poly_add(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out); /* r1csqap.go:94-103, max(na,nb) out */
+int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out); /* r1csqap.go:106-115 */
+int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]);        /* r1csqap.go:118-126 */
+
+/* ---- dense QAP API upstream of GenerateProofs (small n; the prove path consumes px) ---- */
+/* PolynomialField.R1CSToQAP (r1csqap/r1csqap.go:161-188).  a, b, c: n x m row-major R1CS matrices (coefficients
+ * reduced mod r).  alphas/betas/gammas: m x n (row i = coefficients of signal i's polynomial over the domain {1..n});
+ * z: m-1 coefficients of prod_{i=1}^{m-2}(x-i).  Exact big-integer Lagrange denominators: identical to the reference
+ * for n <= 21, and the mathematically intended result where the reference's native-int factorial overflows
+ * (r1csqap.go:130-136).  1 <= n <= 8191.                                                                   */
+int b200_r1cs_to_qap(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, size_t m, uint64_t* alphas,
+                     uint64_t* betas, uint64_t* gammas, uint64_t* z);
+/* PolynomialField.CombinePolynomials (r1csqap/r1csqap.go:191-210): ax = sum r_i*ap[i] (likewise bx, cx; n coefficients
+ * each, ap/bp/cp m x n row-major) and px = ax*bx - cx (2n-1 coefficients).                                            */
+int b200_combine_polynomials(const uint64_t* r, size_t m, const uint64_t* ap, const uint64_t* bp, const uint64_t* cp,
+                             size_t n, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px);
+
+/* ---- element-wise group operations, reference formulas (X,Y,Z-exact) ------------------- */
+/* bn128.G1.Add / Double / Neg / Affine (bn128/g1.go:32-170) and the G2 twins (bn128/g2.go:32-200), n independent
+ * operations per call.  Affine writes (x, y) per point, infinity as (0, 0) like G1.Affine.                            */
+int b200_g1_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);
+int b200_g1_double_batch(const uint64_t* p, size_t n, uint64_t* out);
+int b200_g1_neg_batch(const uint64_t* p, size_t n, uint64_t* out);
+int b200_g1_affine_batch(const uint64_t* p, size_t n, uint64_t* out_xy);
+int b200_g2_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);
+int b200_g2_double_batch(const uint64_t* p, size_t n, uint64_t* out);
+int b200_g2_neg_batch(const uint64_t* p, size_t n, uint64_t* out);
+int b200_g2_affine_batch(const uint64_t* p, size_t n, uint64_t* out_xy);
+
 #ifdef __cplusplus
 }
 #endif
