@@ -64,7 +64,7 @@ def _parse_go_matrices(stdout):
     for line in stdout.splitlines():
         line = line.strip()
         if line.startswith("[[") and line.endswith("]]"):
-            rows = re.findall(r"\\[([0-9 ]*)\\]", line[1:-1])
+            rows = re.findall(r"\[([0-9 ]*)\]", line[1:-1])
             mats.append([[int(x) for x in r.split()] for r in rows])
     return mats
 
