@@ -15,6 +15,7 @@
 
 #include "b200snark.h"
 #include "msm.cuh"
+#include "bucket_affine.cuh"
 #include "poly_host.cuh"
 #include "qap.cuh"
 
@@ -88,6 +89,12 @@ int init_locked(int device) {
   }
   if (device >= count) return fail(B200_EINVAL, "device %d out of range (%d devices)", device, count);
   CU(cudaSetDevice(device));
+  {
+    // random 64-byte point gathers: ask L2 for <= 64 B fetches (ncu showed 128 B per 64 B point otherwise)
+    const char* g = getenv("B200_L2_GRAN");   // tuning knob (no measurable effect on B200: left at the default)
+    size_t gran = g ? (size_t)atoi(g) : 0;
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+  }
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
   CU(cudaMalloc(&g_d_err, sizeof(int)));
@@ -120,6 +127,7 @@ struct SortScratch {
   MsmShape sh{};            // shape it was allocated for (n = capacity)
   DevBuf counts, offsets, cursor, entries, slice_off, slice_start, slice_end;
   uint32_t max_slices = 0;
+  uint32_t slice_S = 0;     // > 0: fixed-size slices of S slots (batched-affine mode)
   SliceTables tables() const { return SliceTables{slice_off.as<uint32_t>(), slice_start.as<uint32_t>(), slice_end.as<uint32_t>()}; }
 };
 
@@ -133,10 +141,14 @@ struct Bases {
   DevBuf slice_out, buckets, partials, result, out_std;
   SortScratch sort;  // own front-end scratch (stand-alone MSMs)
   uint32_t nseg = 0, seg = 0;
+  // batched-affine accumulation (affine_S > 0): ping-pong node buffers, prefix products, per-thread / per-block products
+  uint32_t affine_S = 0;
+  DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot;
 };
 
-int sort_alloc(SortScratch& ss, const MsmShape& sh) {
+int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
   ss.sh = sh;
+  ss.slice_S = slice_S;
   size_t entries = (size_t)sh.nwin * sh.n;
   CU(ss.counts.alloc((sh.nbuckets + 2) * sizeof(uint32_t)));
   CU(ss.offsets.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
@@ -144,6 +156,7 @@ int sort_alloc(SortScratch& ss, const MsmShape& sh) {
   CU(ss.entries.alloc(entries * sizeof(uint32_t)));
   // slices: every bucket owns >= 1; a bucket above cap = 2*mean entries is cut => at most B + B/2 + 1
   ss.max_slices = sh.nbuckets + sh.nbuckets / 2 + 2;
+  if (slice_S) ss.max_slices = sh.nbuckets + (uint32_t)((entries + slice_S - 1) / slice_S) + 2;
   CU(ss.slice_off.alloc((sh.nbuckets + 3) * sizeof(uint32_t)));
   CU(ss.slice_start.alloc((size_t)ss.max_slices * sizeof(uint32_t)));
   CU(ss.slice_end.alloc((size_t)ss.max_slices * sizeof(uint32_t)));
@@ -186,10 +199,32 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
   CU(b->scalars.alloc(n * sizeof(Fr)));
   CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
   {
-    int rc_ = sort_alloc(b->sort, sh);
+    // accumulation mode: batched affine (default) or XYZZ mixed adds (B200_ACC_MODE=xyzz)
+    static const bool xyzz_mode = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "xyzz");
+    uint32_t S = 0;
+    uint64_t mean = ((uint64_t)sh.nwin * n) / sh.nbuckets;
+    static const int min_mean = getenv("B200_AFF_MIN_MEAN") ? atoi(getenv("B200_AFF_MIN_MEAN")) : 96;  // tuning knob
+    // small bucket populations: the per-round launch + inversion latency is not amortised -> XYZZ path
+    if (!xyzz_mode && mean >= (uint64_t)min_mean) {
+      S = 8;
+      while (S < 128 && (uint64_t)S * 2 * 6 <= mean) S *= 2;   // largest power of two <= mean/6, in [8, 128]
+      static const int s_env = getenv("B200_AFF_S") ? atoi(getenv("B200_AFF_S")) : 0;  // tuning knob
+      if (s_env) S = (uint32_t)s_env;
+    }
+    b->affine_S = S;
+    int rc_ = sort_alloc(b->sort, sh, S);
     if (rc_) return rc_;
+    if (S) {
+      size_t nsl = b->sort.max_slices;
+      CU(b->nodeA.alloc(nsl * (S / 2) * sizeof(Affine<F>)));
+      CU(b->nodeB.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(Affine<F>)));
+      CU(b->aff_pre.alloc(nsl * (S / 2) * sizeof(F)));
+      size_t nblk_max = (nsl * (S / 2) + kAffBlock * 16 - 1) / (kAffBlock * 16);
+      CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
+      CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
+    }
   }
-  CU(b->slice_out.alloc((size_t)b->sort.max_slices * sizeof(XYZZ<F>)));
+  CU(b->slice_out.alloc((size_t)(b->affine_S ? 1 : b->sort.max_slices) * sizeof(XYZZ<F>)));
   b->seg = sh.nbuckets >= 4096 ? 16 : (sh.nbuckets >= 256 ? 4 : 1);
   b->nseg = (sh.nbuckets + b->seg - 1) / b->seg;
   CU(b->partials.alloc((size_t)b->nseg * sizeof(XYZZ<F>)));
@@ -274,13 +309,19 @@ int msm_sort(SortScratch& ss, const MsmShape& shape, const Fr* d_scalars, size_t
   // slice cap: twice the mean bucket population (uniform scalars never split), at least 4 per lane
   uint64_t mean = ((uint64_t)sh.nwin * n + sh.nbuckets - 1) / sh.nbuckets;
   uint32_t cap = (uint32_t)(2 * mean < 4 * kLPB ? 4 * kLPB : 2 * mean);
+  int fixed = 0;
+  if (ss.slice_S) {
+    cap = ss.slice_S;
+    fixed = 1;
+  }
   uint32_t* counts = ss.counts.as<uint32_t>();
   CU(cudaMemsetAsync(counts, 0, (m + 1) * sizeof(uint32_t), st));
   if (n) k_digits_count<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, counts, g_d_err);
-  k_scan<<<1, 1024, 0, st>>>(counts, m, cap, ss.offsets.as<uint32_t>(), ss.cursor.as<uint32_t>(), ss.tables());
+  k_scan<<<1, 1024, 0, st>>>(counts, m, cap, fixed, ss.offsets.as<uint32_t>(), ss.cursor.as<uint32_t>(), ss.tables());
+  k_fill_slices<<<nblocks(m, 256), 256, 0, st>>>(counts, ss.offsets.as<uint32_t>(), m, cap, fixed, ss.tables());
   if (n) k_digits_scatter<<<nblocks(n, 256), 256, 0, st>>>(d_scalars, sh, mont, ss.cursor.as<uint32_t>(),
                                                            ss.entries.as<uint32_t>(), g_d_err);
-  g_launches += n ? 3 : 1;
+  g_launches += n ? 4 : 2;
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -290,7 +331,8 @@ int msm_sort(SortScratch& ss, const MsmShape& shape, const Fr* d_scalars, size_t
 template <class F>
 int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out, cudaStream_t st) {
   const MsmShape& sh = b->sh;
-  if (ss.sh.c != sh.c || ss.sh.table_stride != sh.table_stride || ss.max_slices != b->sort.max_slices)
+  if (ss.sh.c != sh.c || ss.sh.table_stride != sh.table_stride || ss.max_slices != b->sort.max_slices ||
+      ss.slice_S != b->sort.slice_S)
     return fail(B200_EINVAL, "msm_buckets: sort scratch does not match the base set");
   uint32_t m = sh.nbuckets + 1;
   XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
@@ -303,6 +345,60 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
   if (g_prof) {
     pr = ProfRec{prof_event(), prof_event(), b->group, n_terms};
     cudaEventRecord(pr.e0, st);
+  }
+  if (b->affine_S) {
+    if (ss.slice_S != b->affine_S) return fail(B200_EINVAL, "msm_buckets: slice size mismatch");
+    const uint32_t S = b->affine_S;
+    uint32_t R = 0;
+    while ((1u << R) < S) R++;
+    // host-side bound on the live slice count for this call (the exact count lives on the device)
+    uint64_t total = (uint64_t)sh.nwin * n_terms;
+    uint64_t nsl_bound = (uint64_t)sh.nbuckets + (total + S - 1) / S + 2;
+    if (nsl_bound > ss.max_slices) nsl_bound = ss.max_slices;
+    AffineRound<F> ar{};
+    ar.table = b->table.as<Affine<F>>();
+    ar.entries = ss.entries.as<uint32_t>();
+    ar.slice_start = stb.slice_start;
+    ar.slice_end = stb.slice_end;
+    ar.nslices_ptr = stb.slice_off + m;
+    ar.pre = b->aff_pre.as<F>();
+    ar.others = b->aff_others.as<F>();
+    ar.btot = b->aff_btot.as<F>();
+    Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
+    const Affine<F>* prev = nullptr;
+    static const int rounds_env = getenv("B200_AFF_ROUNDS") ? atoi(getenv("B200_AFF_ROUNDS")) : 0;  // tuning knob
+    // all rounds affine by default: inside a proof the per-round inversion latency is hidden by the other
+    // MSMs' streams (22.3 ms vs 25.5 ms with an XYZZ tail after round 3 at 2^20, profiles/r1_notes.md)
+    uint32_t R_aff = rounds_env ? (uint32_t)rounds_env : R;
+    if (R_aff > R) R_aff = R;
+    for (uint32_t r = 1; r <= R_aff; r++) {
+      ar.round = r;
+      ar.q_log = R - r;
+      ar.prev = prev;
+      ar.out = bufs[(r - 1) & 1];
+      uint64_t npairs_max = nsl_bound << ar.q_log;
+      static const int t_env = getenv("B200_AFF_T") ? atoi(getenv("B200_AFF_T")) : 32;  // tuning knob
+      const unsigned T = t_env == 16 ? 16 : 32;
+      unsigned nb = (unsigned)((npairs_max + kAffBlock * T - 1) / (kAffBlock * T));
+      if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar); else k_affine_forward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      k_affine_invert<F><<<nblocks(nb, 64), 64, 0, st>>>(ar.btot, nb);
+      if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar); else k_affine_backward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      prev = ar.out;
+      g_launches += 3;
+    }
+    if (g_prof) {
+      cudaEventRecord(pr.e1, st);
+      g_prof_recs.push_back(pr);
+    }
+    if (R_aff == R)
+      k_merge_slices_affine<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, buckets);
+    else
+      k_accumulate_nodes<F, 8><<<nblocks((size_t)sh.nbuckets * 8, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, R - R_aff, buckets);
+    k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
+    k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
+    g_launches += 3;
+    CU(cudaGetLastError());
+    return B200_OK;
   }
   uint64_t mean = ((uint64_t)sh.nwin * n_terms + sh.nbuckets - 1) / sh.nbuckets;
   int lpb = lpb_env ? lpb_env : (mean >= 384 ? 8 : (mean >= 96 ? 4 : 2));
