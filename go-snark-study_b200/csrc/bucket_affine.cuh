@@ -124,8 +124,8 @@ __device__ __forceinline__ F shfl_idx_fe(const F& v, int lane) {
   return r;
 }
 
-template <class F, int kAffT>
-__global__ void __launch_bounds__(kAffBlock) k_affine_forward(AffineRound<F> a) {
+template <class F, int kAffT, int MINB = 1>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_forward(AffineRound<F> a) {
   __shared__ F wtot[kAffBlock / 32];
   const uint32_t nslices = *a.nslices_ptr;
   const uint32_t npairs = nslices << a.q_log;
@@ -182,8 +182,8 @@ __global__ void k_affine_invert(F* btot, uint32_t nblocks_live) {
   btot[i] = btot[i].inverse();
 }
 
-template <class F, int kAffT>
-__global__ void __launch_bounds__(kAffBlock) k_affine_backward(AffineRound<F> a) {
+template <class F, int kAffT, int MINB = 1>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound<F> a) {
   const uint32_t nslices = *a.nslices_ptr;
   const uint32_t npairs = nslices << a.q_log;
   const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);

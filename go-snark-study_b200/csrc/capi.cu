@@ -36,6 +36,7 @@ std::unique_ptr<PolyCtx> g_poly;
 // timing of the dominant kernel (k_accumulate), per group.
 unsigned long long g_launches = 0;
 bool g_prof = false;
+bool g_serial = false;  // measurement mode: issue every MSM of a proof on the caller's stream (exclusive kernel timings)
 struct ProfRec { cudaEvent_t e0, e1; int group; size_t terms; };
 std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_event_pool;
@@ -179,8 +180,12 @@ int check_err_flag(const char* what) {
   return B200_OK;
 }
 
+// in_pipeline: the base set belongs to a proving key, whose MSMs run concurrently on several streams —
+// there the batched-affine accumulation wins (its per-round inversion latency is covered by the other
+// streams: 21.5 vs 26.3 ms per 2^20 proof).  A stand-alone MSM has nothing to overlap with and is faster
+// with the XYZZ kernel (4.7 vs 5.3 ms at 2^20), so it keeps that unless B200_ACC_MODE=affine forces it.
 template <class F>
-int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_ptr<Bases>& out_b) {
+int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_ptr<Bases>& out_b, bool in_pipeline = false) {
   if (!pts || n == 0 || n > (1u << 26)) return fail(B200_EINVAL, "bases_load: bad arguments");
   if (c == 0) c = pick_window_bits(n);
   if (c < 2 || c > 24) return fail(B200_EINVAL, "window_bits must be in [2,24]");
@@ -200,7 +205,9 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
   CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
   {
     // accumulation mode: batched affine (default) or XYZZ mixed adds (B200_ACC_MODE=xyzz)
-    static const bool xyzz_mode = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "xyzz");
+    static const bool force_xyzz = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "xyzz");
+    static const bool force_affine = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "affine");
+    const bool xyzz_mode = force_xyzz || (!in_pipeline && !force_affine);
     uint32_t S = 0;
     uint64_t mean = ((uint64_t)sh.nwin * n) / sh.nbuckets;
     static const int min_mean = getenv("B200_AFF_MIN_MEAN") ? atoi(getenv("B200_AFF_MIN_MEAN")) : 96;  // tuning knob
@@ -380,9 +387,15 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       static const int t_env = getenv("B200_AFF_T") ? atoi(getenv("B200_AFF_T")) : 32;  // tuning knob
       const unsigned T = t_env == 16 ? 16 : 32;
       unsigned nb = (unsigned)((npairs_max + kAffBlock * T - 1) / (kAffBlock * T));
-      if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar); else k_affine_forward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      static const int mb_env = getenv("B200_AFF_MINB") ? atoi(getenv("B200_AFF_MINB")) : 4;  // tuning knob (4: -3 % at 2^20)
+      if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (mb_env >= 3) k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
+      else k_affine_forward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
       k_affine_invert<F><<<nblocks(nb, 64), 64, 0, st>>>(ar.btot, nb);
-      if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar); else k_affine_backward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (mb_env >= 4) k_affine_backward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (mb_env >= 3) k_affine_backward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
+      else k_affine_backward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
       prev = ar.out;
       g_launches += 3;
     }
@@ -695,7 +708,8 @@ int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const vo
 }
 int b200_profile(int enable) {
   std::lock_guard<std::mutex> lk(g_mu);
-  g_prof = enable != 0;
+  g_prof = (enable & 1) != 0;
+  g_serial = (enable & 2) != 0;
   return B200_OK;
 }
 int b200_profile_read(double out[8]) {

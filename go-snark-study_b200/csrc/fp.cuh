@@ -174,6 +174,107 @@ struct alignas(32) Fp {
   }
   HD Fp sqr() const { return (*this) * (*this); }
 
+  // ---- split multiply for lazy reduction (used by the F_q^2 tower) ---------------------------
+  // w[0..16) = a * b as a plain 512-bit integer (operands may be unreduced, < 2^256).
+  // Row i adds a * b[i] at column i; the partial products of even and odd columns are kept in two
+  // accumulators E (pairs aligned at even columns) and O (aligned at odd columns) so every row is two
+  // independent carry chains of fused IMAD.WIDE.U32.X, exactly as in mul_impl.
+  static HD void mul_full(uint32_t* w, const uint32_t* a, const uint32_t* b) {
+    using namespace cc;
+    uint32_t E[16], O[16];  // O[k] sits at column k + 1
+#pragma unroll
+    for (int k = 0; k < 16; k++) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t bi = b[i];
+      if ((i & 1) == 0) {
+        // a[even] * bi -> columns i + j (even)  : E ;  a[odd] * bi -> columns i + j (odd) : O at index i + j - 1
+        E[i] = mad_lo_cc(a[0], bi, E[i]);
+        E[i + 1] = madc_hi_cc(a[0], bi, E[i + 1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+          E[i + j] = madc_lo_cc(a[j], bi, E[i + j]);
+          E[i + j + 1] = madc_hi_cc(a[j], bi, E[i + j + 1]);
+        }
+        if (i + 8 < 16) E[i + 8] = addc(E[i + 8], 0u);
+        O[i] = mad_lo_cc(a[1], bi, O[i]);
+        O[i + 1] = madc_hi_cc(a[1], bi, O[i + 1]);
+#pragma unroll
+        for (int j = 3; j < 8; j += 2) {
+          O[i + j - 1] = madc_lo_cc(a[j], bi, O[i + j - 1]);
+          O[i + j] = madc_hi_cc(a[j], bi, O[i + j]);
+        }
+        if (i + 8 < 16) O[i + 8] = addc(O[i + 8], 0u);
+      } else {
+        // i odd: a[even] * bi -> odd columns : O at index i + j - 1 ; a[odd] * bi -> even columns : E
+        O[i - 1] = mad_lo_cc(a[0], bi, O[i - 1]);
+        O[i] = madc_hi_cc(a[0], bi, O[i]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+          O[i + j - 1] = madc_lo_cc(a[j], bi, O[i + j - 1]);
+          O[i + j] = madc_hi_cc(a[j], bi, O[i + j]);
+        }
+        if (i + 7 < 16) O[i + 7] = addc(O[i + 7], 0u);
+        E[i + 1] = mad_lo_cc(a[1], bi, E[i + 1]);
+        E[i + 2] = madc_hi_cc(a[1], bi, E[i + 2]);
+#pragma unroll
+        for (int j = 3; j < 8; j += 2) {
+          E[i + j] = madc_lo_cc(a[j], bi, E[i + j]);
+          E[i + j + 1] = madc_hi_cc(a[j], bi, E[i + j + 1]);
+        }
+        if (i + 9 < 16) E[i + 9] = addc(E[i + 9], 0u);
+      }
+    }
+    // w = E + (O << 32)
+    w[0] = E[0];
+    w[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 15; k++) w[k] = addc_cc(E[k], O[k - 1]);
+    w[15] = addc(E[15], O[14]);
+  }
+
+  // Montgomery reduction of a 512-bit value t < p * 2^256:  returns t / 2^256 mod p, canonical.
+  static HD Fp redc_wide(const uint32_t* t_in) {
+    using namespace cc;
+    uint32_t t[17];
+#pragma unroll
+    for (int k = 0; k < 16; k++) t[k] = t_in[k];
+    t[16] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t m = mul_lo(t[i], P::INV);
+      // t += m * p << (32 i): even limbs of p in one chain, odd limbs in another, then fold the carries up
+      uint32_t lo_c, hi_c;
+      t[i] = mad_lo_cc(P::MOD(0), m, t[i]);
+      t[i + 1] = madc_hi_cc(P::MOD(0), m, t[i + 1]);
+#pragma unroll
+      for (int j = 2; j < 8; j += 2) {
+        t[i + j] = madc_lo_cc(P::MOD(j), m, t[i + j]);
+        t[i + j + 1] = madc_hi_cc(P::MOD(j), m, t[i + j + 1]);
+      }
+      lo_c = addc(0u, 0u);
+      t[i + 1] = mad_lo_cc(P::MOD(1), m, t[i + 1]);
+      t[i + 2] = madc_hi_cc(P::MOD(1), m, t[i + 2]);
+#pragma unroll
+      for (int j = 3; j < 8; j += 2) {
+        t[i + j] = madc_lo_cc(P::MOD(j), m, t[i + j]);
+        t[i + j + 1] = madc_hi_cc(P::MOD(j), m, t[i + j + 1]);
+      }
+      hi_c = addc(0u, 0u);
+      // carries: lo_c belongs to column i + 8, hi_c to column i + 9; ripple through the remaining limbs
+      t[i + 8] = add_cc(t[i + 8], lo_c);
+      if (i + 9 <= 16) t[i + 9] = addc_cc(t[i + 9], hi_c);
+#pragma unroll
+      for (int k = i + 10; k <= 16; k++) t[k] = addc_cc(t[k], 0u);
+    }
+    Fp r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.l[k] = t[8 + k];
+    // t < p*2^256 + p*2^256  =>  result < 2p (t[16] is then 0 because 2p < 2^256)
+    final_sub(r.l);
+    return r;
+  }
+
   HD Fp to_mont() const { return (*this) * r2(); }
   HD Fp from_mont() const {
     Fp o = zero();

@@ -37,11 +37,44 @@ struct alignas(32) Fq2T {
   HD Fq2T dbl() const { return Fq2T{c0.dbl(), c1.dbl()}; }
 
   // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u
+  // Lazy reduction: the three Karatsuba products are kept as 512-bit integers and each output
+  // component is reduced ONCE (3*64 + 2*64 = 320 wide multiplies instead of 3*128).  Bounds, with
+  // p < 2^254: v0, v1 < p^2;  s = (a0+a1)(b0+b1) < 4p^2 < 2^510;  c1 = s - v0 - v1 = a0b1 + a1b0 in
+  // [0, 2p^2);  c0 = v0 - v1 + p^2 in (0, 2p^2);  2p^2 < p*2^256, the Montgomery-reduction bound.
   static HD Fq2T mul_impl(const Fq2T& a, const Fq2T& b) {
-    B v0 = a.c0 * b.c0;
-    B v1 = a.c1 * b.c1;
-    B s = (a.c0 + a.c1) * (b.c0 + b.c1);
-    return Fq2T{v0 - v1, s - v0 - v1};
+    using namespace cc;
+    uint32_t v0[16], v1[16], s[16], sa[8], sb[8];
+    B::mul_full(v0, a.c0.l, b.c0.l);
+    B::mul_full(v1, a.c1.l, b.c1.l);
+    sa[0] = add_cc(a.c0.l[0], a.c1.l[0]);
+    sb[0] = 0;
+#pragma unroll
+    for (int i = 1; i < 7; i++) sa[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
+    sa[7] = addc(a.c0.l[7], a.c1.l[7]);
+    sb[0] = add_cc(b.c0.l[0], b.c1.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sb[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+    sb[7] = addc(b.c0.l[7], b.c1.l[7]);
+    B::mul_full(s, sa, sb);
+    // s <- s - v0 - v1
+    s[0] = sub_cc(s[0], v0[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) s[i] = subc_cc(s[i], v0[i]);
+    s[15] = subc(s[15], v0[15]);
+    s[0] = sub_cc(s[0], v1[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) s[i] = subc_cc(s[i], v1[i]);
+    s[15] = subc(s[15], v1[15]);
+    // v0 <- v0 - v1 + p^2
+    v0[0] = sub_cc(v0[0], v1[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) v0[i] = subc_cc(v0[i], v1[i]);
+    v0[15] = subc(v0[15], v1[15]);
+    v0[0] = add_cc(v0[0], FqP2(0));
+#pragma unroll
+    for (int i = 1; i < 15; i++) v0[i] = addc_cc(v0[i], FqP2(i));
+    v0[15] = addc(v0[15], FqP2(15));
+    return Fq2T{B::redc_wide(v0), B::redc_wide(s)};
   }
   // (a0 + a1 u)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 u
   static HD Fq2T sqr_impl(const Fq2T& a) {

@@ -165,22 +165,22 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   {
     PointCat cat(12);
     cat.add(at + 12 * lo, hi - lo); cat.add(lead ? alpha1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1); cat.add(inf1, 1);
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0]))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], true))) return rc;
   }
   {
     PointCat cat(12);
     cat.add(b1 + 12 * lo, hi - lo); cat.add(lead ? beta1 : inf1, 1); cat.add(inf1, 1); cat.add(lead ? delta1 : inf1, 1);
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1]))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], true))) return rc;
   }
   {
     PointCat cat(24);
     cat.add(b2 + 24 * lo, hi - lo); cat.add(lead ? beta2 : inf2, 1); cat.add(inf2, 1); cat.add(lead ? delta2 : inf2, 1);
-    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2]))) return rc;
+    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], true))) return rc;
   }
   {
     PointCat cat(12);
     cat.add(bacdelta + 12 * clo, hi - clo); cat.add(ptd + 12 * plo, phi - plo); cat.add(lead ? delta1 : inf1, 1);
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3]))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], true))) return rc;
   }
   CU(pk->s3.alloc((m + n_ptd + 4) * sizeof(Fr)));
   if (world > 1) CU(pk->h_full.alloc((m + n_ptd + 4) * sizeof(Fr)));
@@ -255,6 +255,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   const size_t lo = pk->lo, hi = pk->hi, clo = pk->clo, plo = pk->plo, phi = pk->phi;
   const size_t n_ab = hi - lo, n_c = hi - clo, n_p = phi - plo, n_ch = n_c + n_p + 1;
   cudaStream_t s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
+  if (g_serial) s1 = s2 = s3 = st;  // measurement mode (b200_profile bit 1): no overlap, exclusive kernel timings
   cudaEvent_t e_in = pk->ev[0], e_w = pk->ev[1], e_a = pk->ev[2], e_b1 = pk->ev[3], e_b2 = pk->ev[4],
               e_ch = pk->ev[5], e_prod = pk->ev[6];
   Fr small[6] = {one, fr_r, fr_s, neg_rs, fr_r, fr_s};
@@ -368,15 +369,15 @@ int pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2,
   size_t l1 = npublic + 1;
   // snark.go:265-268: PiA, PiAp run over i in [NPublic+1, NVars)
   if (m > l1) {
-    if ((rc = bases_create<Fq>(a + 12 * l1, m - l1, wb, 1, pk->g[0]))) return rc;
-    if ((rc = bases_create<Fq>(ap + 12 * l1, m - l1, wb, 1, pk->g[1]))) return rc;
+    if ((rc = bases_create<Fq>(a + 12 * l1, m - l1, wb, 1, pk->g[0], true))) return rc;
+    if ((rc = bases_create<Fq>(ap + 12 * l1, m - l1, wb, 1, pk->g[1], true))) return rc;
   }
-  if ((rc = bases_create<Fq2>(b2, m, wb, 2, pk->g[2]))) return rc;
-  if ((rc = bases_create<Fq>(bp, m, wb, 1, pk->g[3]))) return rc;
-  if ((rc = bases_create<Fq>(c, m, wb, 1, pk->g[4]))) return rc;
-  if ((rc = bases_create<Fq>(cp, m, wb, 1, pk->g[5]))) return rc;
-  if ((rc = bases_create<Fq>(kp, m, wb, 1, pk->g[6]))) return rc;
-  if ((rc = bases_create<Fq>(g1t, n_g1t, wb, 1, pk->g[7]))) return rc;
+  if ((rc = bases_create<Fq2>(b2, m, wb, 2, pk->g[2], true))) return rc;
+  if ((rc = bases_create<Fq>(bp, m, wb, 1, pk->g[3], true))) return rc;
+  if ((rc = bases_create<Fq>(c, m, wb, 1, pk->g[4], true))) return rc;
+  if ((rc = bases_create<Fq>(cp, m, wb, 1, pk->g[5], true))) return rc;
+  if ((rc = bases_create<Fq>(kp, m, wb, 1, pk->g[6], true))) return rc;
+  if ((rc = bases_create<Fq>(g1t, n_g1t, wb, 1, pk->g[7], true))) return rc;
   CU(pk->s3.alloc((n_g1t + 4) * sizeof(Fr)));
   uint64_t h = g_next_pk++;
   g_pks[h] = std::move(pk);

@@ -149,8 +149,10 @@ int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint6
 int b200_pk_free(b200_pk_t pk);
 
 /* ---- instrumentation (bench.py) -------------------------------------------- */
-/* b200_profile(1) brackets every bucket-accumulation launch (the dominant kernel)
- * with CUDA events on its stream.  b200_profile_read synchronises and returns
+/* b200_profile(flags): bit 0 brackets every bucket-accumulation phase (the dominant
+ * kernels) with CUDA events on its stream; bit 1 additionally issues all MSMs of a
+ * proof on the caller's stream instead of overlapping them on side streams, so that
+ * those event times are exclusive (measurement mode, slower).  b200_profile_read synchronises and returns
  * out = { G1 ms total, G1 launches, G1 terms total, G2 ms total, G2 launches,
  *         G2 terms total, kernel launches since the last read, 0 } and resets.      */
 int b200_profile(int enable);

@@ -88,6 +88,18 @@ def test_fq2_ops(lib):
             assert tuple(call(lib.t_fq2_op, 3, ptr(A), ptr(B), nout=2)) == F2.inverse(a)  # fq2.go:99-108
 
 
+def test_fq2_lazy_reduction_extremes(lib):
+    """The lazily reduced product keeps 512-bit intermediates: exercise the bound cases
+    (all components p-1, zero, v0 < v1, v0 > v1)."""
+    F2 = o.BN.Fq2
+    ext = [0, 1, Q - 1, Q - 2, (Q - 1) // 2, 2]
+    for a0 in ext:
+        for a1 in ext:
+            for b0, b1 in ((Q - 1, Q - 1), (0, Q - 1), (Q - 1, 0), (1, 1), (Q - 2, 3)):
+                a, b = (a0, a1), (b0, b1)
+                assert tuple(call(lib.t_fq2_op, 2, ptr(to_u32(a)), ptr(to_u32(b)), nout=2)) == F2.mul(a, b)
+
+
 def _flat(pt):
     out = []
     for c in pt:
