@@ -27,11 +27,16 @@
 struct ProvingKey {
   int kind = 0;  // 1 Groth16, 2 Pinocchio
   size_t m = 0, npublic = 0, n_h_bases = 0;
-  // index-range shard of this rank (world == 1: everything)
+  // Work shard of this rank (world == 1: everything).  The four MSMs are laid end to end on a line weighted
+  // by cost (a G2 term ~2.8 G1 terms) and rank g takes the g-th of `world` equal pieces, so a rank holds
+  // whole MSMs where it can and index ranges where it must: fewer sorts / reduction tails per rank than
+  // slicing every MSM `world` ways.  set k: 0 A, 1 B1, 2 B2, 3 C||PTD.
   int rank = 0, world = 1;
-  size_t lo = 0, hi = 0;      // slice of [0, m) for the A / B1 / B2 sets
-  size_t clo = 0;             // slice [clo, hi) of BACDelta (clo >= npublic + 1)
-  size_t plo = 0, phi = 0;    // slice of [0, n_h_bases) for PowersTauDelta
+  size_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};  // index range inside set k
+  bool tail[4] = {false, false, false, false};        // this rank also holds set k's blinding points
+  size_t n_c_full = 0;                                // length of the C part of the C||PTD set (m - npublic - 1)
+  bool shared_w = false;                              // sets 0..2 cover identical ranges -> one shared digit sort
+  DevBuf s4;                                          // extra scalar vector (non-shared case)
   DevBuf h_full;              // full quotient (sharded mode)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ~ProvingKey() { for (auto e : ev) if (e) cudaEventDestroy(e); }
@@ -153,36 +158,63 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   pk->n_h_bases = n_ptd;
   int rc = pk_common_init(*pk, z, nz, m);
   if (rc) return rc;
-  // contiguous index-range shard; the blinding points ride on rank 0 only
   pk->rank = rank;
   pk->world = world;
-  size_t lo = pk->lo = m * (size_t)rank / world, hi = pk->hi = m * (size_t)(rank + 1) / world;
-  size_t clo = pk->clo = lo > npublic + 1 ? lo : npublic + 1;
-  if (clo > hi) clo = pk->clo = hi;
-  size_t plo = pk->plo = n_ptd * (size_t)rank / world, phi = pk->phi = n_ptd * (size_t)(rank + 1) / world;
+  const size_t l1 = npublic + 1;
+  const size_t n_c_full = pk->n_c_full = m - l1;
+  const size_t len[4] = {m, m, m, n_c_full + n_ptd};
+  const double wgt[4] = {1.0, 1.0, 2.8, 1.0};
+  double off[5] = {0, 0, 0, 0, 0};
+  for (int k = 0; k < 4; k++) off[k + 1] = off[k] + wgt[k] * (double)len[k];
+  auto cut = [&](int g, int k) -> size_t {   // first index of set k at or after the g-th cut of the line
+    double pos = off[4] * (double)g / (double)world;
+    double x = (pos - off[k]) / wgt[k];
+    if (g >= world) return len[k];
+    if (x <= 0) return 0;
+    if (x >= (double)len[k]) return len[k];
+    return (size_t)x;
+  };
+  for (int k = 0; k < 4; k++) {
+    pk->lo[k] = cut(rank, k);
+    pk->hi[k] = cut(rank + 1, k);
+    pk->tail[k] = pk->hi[k] == len[k] && (pk->lo[k] < pk->hi[k] || (rank == world - 1 && len[k] == 0));
+  }
+  // a set whose end falls exactly on a cut: the rank holding its last element owns the tail (checked above);
+  // if no rank holds elements of it (len == 0) the last rank does.
+  pk->shared_w = pk->lo[0] == pk->lo[1] && pk->lo[1] == pk->lo[2] && pk->hi[0] == pk->hi[1] && pk->hi[1] == pk->hi[2] &&
+                 pk->tail[0] && pk->tail[1] && pk->tail[2];
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
-  const bool lead = rank == 0;
-  {
+  auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
+  if (has(0)) {
     PointCat cat(12);
-    cat.add(at + 12 * lo, hi - lo); cat.add(lead ? alpha1 : inf1, 1); cat.add(lead ? delta1 : inf1, 1); cat.add(inf1, 1);
+    cat.add(at + 12 * pk->lo[0], pk->hi[0] - pk->lo[0]);
+    if (pk->tail[0]) { cat.add(alpha1, 1); cat.add(delta1, 1); cat.add(inf1, 1); }
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], true))) return rc;
   }
-  {
+  if (has(1)) {
     PointCat cat(12);
-    cat.add(b1 + 12 * lo, hi - lo); cat.add(lead ? beta1 : inf1, 1); cat.add(inf1, 1); cat.add(lead ? delta1 : inf1, 1);
+    cat.add(b1 + 12 * pk->lo[1], pk->hi[1] - pk->lo[1]);
+    if (pk->tail[1]) { cat.add(beta1, 1); cat.add(inf1, 1); cat.add(delta1, 1); }
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], true))) return rc;
   }
-  {
+  if (has(2)) {
     PointCat cat(24);
-    cat.add(b2 + 24 * lo, hi - lo); cat.add(lead ? beta2 : inf2, 1); cat.add(inf2, 1); cat.add(lead ? delta2 : inf2, 1);
+    cat.add(b2 + 24 * pk->lo[2], pk->hi[2] - pk->lo[2]);
+    if (pk->tail[2]) { cat.add(beta2, 1); cat.add(inf2, 1); cat.add(delta2, 1); }
     if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], true))) return rc;
   }
-  {
+  if (has(3)) {
     PointCat cat(12);
-    cat.add(bacdelta + 12 * clo, hi - clo); cat.add(ptd + 12 * plo, phi - plo); cat.add(lead ? delta1 : inf1, 1);
+    size_t lo3 = pk->lo[3], hi3 = pk->hi[3];
+    size_t c_lo = lo3 < n_c_full ? lo3 : n_c_full, c_hi = hi3 < n_c_full ? hi3 : n_c_full;
+    size_t p_lo = lo3 > n_c_full ? lo3 - n_c_full : 0, p_hi = hi3 > n_c_full ? hi3 - n_c_full : 0;
+    cat.add(bacdelta + 12 * (l1 + c_lo), c_hi - c_lo);
+    cat.add(ptd + 12 * p_lo, p_hi - p_lo);
+    if (pk->tail[3]) cat.add(delta1, 1);
     if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], true))) return rc;
   }
   CU(pk->s3.alloc((m + n_ptd + 4) * sizeof(Fr)));
+  CU(pk->s4.alloc((m + 4) * sizeof(Fr)));
   if (world > 1) CU(pk->h_full.alloc((m + n_ptd + 4) * sizeof(Fr)));
   uint64_t h = g_next_pk++;
   g_pks[h] = std::move(pk);
@@ -201,15 +233,6 @@ Fr fr_load_std(const uint64_t* v) {
   Fr r;
   memcpy(&r, v, sizeof(Fr));
   return r;
-}
-
-// tails of the scalar vectors: v = [1, r, s, -rs]
-__global__ void k_groth16_tails(const Fr* v, Fr* sW_tail, Fr* sCH_last) {
-  if (threadIdx.x | blockIdx.x) return;
-  sW_tail[0] = v[0];
-  sW_tail[1] = v[1];
-  sW_tail[2] = v[2];
-  sCH_last[0] = v[3];
 }
 
 // prod[0] = s * A, prod[1] = r * B1  (groth16.go:272-273); res layout as in k_groth16_finalize
@@ -250,48 +273,83 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   Fr neg_rs = (fr_r.to_mont() * fr_s.to_mont()).neg().from_mont();  // -(r*s) mod r  (groth16.go:274)
   Fr one = Fr::zero();
   one.l[0] = 1;
-  Fr* sW = pk->s1.as<Fr>();
-  Fr* sCH = pk->s3.as<Fr>();
-  const size_t lo = pk->lo, hi = pk->hi, clo = pk->clo, plo = pk->plo, phi = pk->phi;
-  const size_t n_ab = hi - lo, n_c = hi - clo, n_p = phi - plo, n_ch = n_c + n_p + 1;
   cudaStream_t s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
   if (g_serial) s1 = s2 = s3 = st;  // measurement mode (b200_profile bit 1): no overlap, exclusive kernel timings
   cudaEvent_t e_in = pk->ev[0], e_w = pk->ev[1], e_a = pk->ev[2], e_b1 = pk->ev[3], e_b2 = pk->ev[4],
               e_ch = pk->ev[5], e_prod = pk->ev[6];
-  Fr small[6] = {one, fr_r, fr_s, neg_rs, fr_r, fr_s};
-  CU(cudaMemcpyAsync(pk->rs.p, small, sizeof small, cudaMemcpyHostToDevice, st));
-  k_groth16_tails<<<1, 32, 0, st>>>(pk->rs.as<Fr>(), sW + n_ab, sCH + n_ch - 1);
-  if (n_ab) CU(cudaMemcpyAsync(sW, d_w + lo, n_ab * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  if (n_c) CU(cudaMemcpyAsync(sCH, d_w + clo, n_c * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-  EV_REC(e_in, st);
+  const size_t l1 = pk->npublic + 1, n_c_full = pk->n_c_full;
   uint8_t* res = pk->res.as<uint8_t>();
   int rc;
-  // --- side stream 3: hx = px / Z (groth16.go:266), then the CH MSM.  Single GPU: h is written straight
-  // into the CH scalar vector.  Sharded: every rank repeats the (cheap) division and keeps its slice
-  // h[plo, phi) — no inter-GPU traffic.
+  Fr small[6] = {one, fr_r, fr_s, neg_rs, fr_r, fr_s};
+  CU(cudaMemcpyAsync(pk->rs.p, small, sizeof small, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(res, 0, kPartialBytes, st));      // sets this rank does not hold contribute infinity
+  // scalar vectors: set k in {A, B1, B2} uses w[lo_k, hi_k) (+ [1, r, s] when it owns the blinding points)
+  Fr* sv[3] = {pk->s1.as<Fr>(), pk->s2.as<Fr>(), pk->s4.as<Fr>()};
+  size_t nterm[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 3; k++) {
+    if (!pk->g[k]) continue;
+    if (pk->shared_w && k > 0) { nterm[k] = nterm[0]; continue; }
+    size_t cnt = pk->hi[k] - pk->lo[k];
+    if (cnt) CU(cudaMemcpyAsync(sv[k], d_w + pk->lo[k], cnt * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    if (pk->tail[k]) CU(cudaMemcpyAsync(sv[k] + cnt, pk->rs.as<Fr>(), 3 * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    nterm[k] = cnt + (pk->tail[k] ? 3 : 0);
+  }
+  // C || PTD set
+  Fr* sCH = pk->s3.as<Fr>();
+  size_t lo3 = pk->lo[3], hi3 = pk->hi[3];
+  size_t c_lo = lo3 < n_c_full ? lo3 : n_c_full, c_hi = hi3 < n_c_full ? hi3 : n_c_full;
+  size_t p_lo = lo3 > n_c_full ? lo3 - n_c_full : 0, p_hi = hi3 > n_c_full ? hi3 - n_c_full : 0;
+  size_t n_c = c_hi - c_lo, n_p = p_hi - p_lo;
+  if (pk->g[3]) {
+    if (n_c) CU(cudaMemcpyAsync(sCH, d_w + l1 + c_lo, n_c * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    if (pk->tail[3]) CU(cudaMemcpyAsync(sCH + n_c + n_p, pk->rs.as<Fr>() + 3, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    nterm[3] = n_c + n_p + (pk->tail[3] ? 1 : 0);
+  }
+  EV_REC(e_in, st);
+  // --- side stream 3: hx = px / Z (groth16.go:266) when this rank holds PowersTauDelta points, then C||PTD.
+  // Single GPU: h is written straight into the scalar vector.  Sharded: the rank(s) holding PTD indices repeat
+  // the (cheap) division and keep h[p_lo, p_hi) — no inter-GPU traffic.
   EV_WAIT(s3, e_in);
-  Fr* h_dst = pk->world == 1 ? sCH + n_c : pk->h_full.as<Fr>();
-  CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, s3));
-  size_t have = nq > plo ? (nq < phi ? nq - plo : n_p) : 0;   // valid h coefficients inside this rank's slice
-  if (pk->world > 1 && have)
-    CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + plo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
-  if (n_p > have) CU(cudaMemsetAsync(sCH + n_c + have, 0, (n_p - have) * sizeof(Fr), s3));
-  if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, n_ch, 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), s3))) return rc;
+  if (pk->g[3]) {
+    if (n_p) {
+      bool direct = p_lo == 0 && nq <= n_p;
+      Fr* h_dst = direct ? sCH + n_c : pk->h_full.as<Fr>();
+      if (!direct && !pk->h_full.p) CU(pk->h_full.alloc((pk->m + pk->n_h_bases + 4) * sizeof(Fr)));
+      CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, s3));
+      size_t have = nq > p_lo ? (nq < p_hi ? nq - p_lo : n_p) : 0;   // valid h coefficients inside [p_lo, p_hi)
+      if (!direct && have)
+        CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + p_lo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
+      if (n_p > have) CU(cudaMemsetAsync(sCH + n_c + have, 0, (n_p - have) * sizeof(Fr), s3));
+    }
+    if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, nterm[3], 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), s3))) return rc;
+  }
   EV_REC(e_ch, s3);
-  // --- main stream: one sort of W shared by the A, B1, B2 bucket phases
-  SortScratch& sw = pk->g[0]->sort;
-  if ((rc = msm_sort(sw, pk->g[0]->sh, sW, n_ab + 3, 0, st))) return rc;
-  EV_REC(e_w, st);
-  EV_WAIT(s1, e_w);
-  if ((rc = msm_buckets<Fq>(pk->g[1].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
-  EV_REC(e_b1, s1);
-  EV_WAIT(s2, e_w);
-  if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
-  EV_REC(e_b2, s2);
-  if ((rc = msm_buckets<Fq>(pk->g[0].get(), sw, n_ab + 3, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
-  EV_REC(e_a, st);
+  // --- A, B1, B2.  One GPU (or identical ranges): one digit sort of W = w || [1, r, s] shared by the three
+  // bucket phases; otherwise each set sorts its own slice.
+  if (pk->shared_w) {
+    SortScratch& sw = pk->g[0]->sort;
+    if ((rc = msm_sort(sw, pk->g[0]->sh, sv[0], nterm[0], 0, st))) return rc;
+    EV_REC(e_w, st);
+    EV_WAIT(s1, e_w);
+    if ((rc = msm_buckets<Fq>(pk->g[1].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
+    EV_REC(e_b1, s1);
+    EV_WAIT(s2, e_w);
+    if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
+    EV_REC(e_b2, s2);
+    if ((rc = msm_buckets<Fq>(pk->g[0].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
+    EV_REC(e_a, st);
+  } else {
+    EV_WAIT(s1, e_in);
+    if (pk->g[1] && (rc = msm_enqueue<Fq>(pk->g[1].get(), sv[1], nterm[1], 0, reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
+    EV_REC(e_b1, s1);
+    EV_WAIT(s2, e_in);
+    if (pk->g[2] && (rc = msm_enqueue<Fq2>(pk->g[2].get(), sv[2], nterm[2], 0, reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
+    EV_REC(e_b2, s2);
+    if (pk->g[0] && (rc = msm_enqueue<Fq>(pk->g[0].get(), sv[0], nterm[0], 0, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
+    EV_REC(e_a, st);
+  }
   if (pk->world == 1) {
-    // s*A and r*B1 on side stream 1 while B2 / CH are still running
+    // s*A and r*B1 on side stream 1 while B2 / C||PTD are still running
     XYZZ<Fq>* prod = reinterpret_cast<XYZZ<Fq>*>(res + 1024);
     EV_WAIT(s1, e_a);
     k_groth16_products<<<1, 64, 0, s1>>>(res, pk->rs.as<Fr>() + 4, prod);

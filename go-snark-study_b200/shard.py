@@ -1,12 +1,37 @@
-"""Index-range sharding of a Groth16 proving key across ranks — the same
-arithmetic as groth16_pk_load in csrc/prove_host.cuh: rank g of P owns
-[m*g/P, m*(g+1)/P) of At / B1 / B2, the part of it above NPublic of BACDelta, and the
-same fraction of PowersTauDelta; the blinding points ride on rank 0."""
+"""Work sharding of a Groth16 proving key across ranks — the same arithmetic as
+groth16_pk_load in csrc/prove_host.cuh.
+
+The four MSMs (A, B1, B2, C||PTD) are laid end to end on a line weighted by cost (a G2
+term ~ 2.8 G1 terms); rank g takes the g-th of `world` equal pieces.  A rank therefore
+holds whole MSMs where it can and index ranges where it must.  A set's blinding points
+(alpha/beta/delta tails) belong to the rank that holds the set's last element.
+"""
+
+WEIGHTS = (1.0, 1.0, 2.8, 1.0)     # A, B1, B2 (G2), C||PTD
 
 
 def shard_ranges(m, npublic, n_ptd, rank, world):
     assert world >= 1 and 0 <= rank < world
-    lo, hi = m * rank // world, m * (rank + 1) // world
-    clo = min(max(lo, npublic + 1), hi)
-    plo, phi = n_ptd * rank // world, n_ptd * (rank + 1) // world
-    return {"lo": lo, "hi": hi, "clo": clo, "plo": plo, "phi": phi, "lead": rank == 0}
+    n_c_full = m - npublic - 1
+    lens = (m, m, m, n_c_full + n_ptd)
+    off = [0.0]
+    for w, ln in zip(WEIGHTS, lens):
+        off.append(off[-1] + w * float(ln))
+
+    def cut(g, k):
+        if g >= world:
+            return lens[k]
+        pos = off[4] * float(g) / float(world)
+        x = (pos - off[k]) / WEIGHTS[k]
+        if x <= 0:
+            return 0
+        if x >= float(lens[k]):
+            return lens[k]
+        return int(x)
+
+    out = {"n_c_full": n_c_full, "sets": []}
+    for k in range(4):
+        lo, hi = cut(rank, k), cut(rank + 1, k)
+        tail = hi == lens[k] and (lo < hi or (rank == world - 1 and lens[k] == 0))
+        out["sets"].append({"lo": lo, "hi": hi, "tail": tail})
+    return out
