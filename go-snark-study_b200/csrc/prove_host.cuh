@@ -36,6 +36,7 @@ struct ProvingKey {
   bool tail[4] = {false, false, false, false};        // this rank also holds set k's blinding points
   size_t n_c_full = 0;                                // length of the C part of the C||PTD set (m - npublic - 1)
   bool shared_w = false;                              // sets 0..2 cover identical ranges -> one shared digit sort
+  int sort_src[3] = {0, 1, 2};                        // set k reuses the digit sort of set sort_src[k] (same scalars)
   DevBuf s4;                                          // extra scalar vector (non-shared case)
   DevBuf h_full;              // full quotient (sharded mode)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -83,35 +84,30 @@ __device__ void store_jacobian_std(const XYZZ<F>& p, F* out) {
 // world_size after the NCCL all-gather).  rs = {r, s} standard form.
 // out: PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2), Jacobian, standard form.
 constexpr size_t kPartialBytes = 1024;
-__global__ void k_groth16_finalize(const uint8_t* parts, int nparts, const Fr* rs, Fq* out_a, Fq* out_c, Fq2* out_b) {
-  __shared__ XYZZ<Fq> sh[4];  // A, B1, CH, then products reuse [0],[1]
+// Sharded mode.  Each rank has already folded s*A_part + r*B1_part into its C part (linear in the partial
+// sums, so this is done per rank, overlapped with its other MSMs); what remains after the all-gather is
+// three point sums: A (slot @+0), B2 (@+512), C (@+768).
+__global__ void k_groth16_finalize(const uint8_t* parts, int nparts, Fq* out_a, Fq* out_c, Fq2* out_b) {
   uint32_t t = threadIdx.x;
-  auto g1_at = [&](int p, int off) { return *reinterpret_cast<const XYZZ<Fq>*>(parts + kPartialBytes * p + off); };
-  if (t == 0 || t == 32 || t == 96) {
-    int off = t == 0 ? 0 : (t == 32 ? 256 : 768);
-    XYZZ<Fq> acc = g1_at(0, off);
-    for (int p = 1; p < nparts; p++) xyzz_add(acc, g1_at(p, off));
-    sh[t == 0 ? 0 : (t == 32 ? 1 : 2)] = acc;
+  if (t == 0 || t == 32) {
+    int off = t == 0 ? 0 : 768;
+    XYZZ<Fq> acc = *reinterpret_cast<const XYZZ<Fq>*>(parts + off);
+    for (int p = 1; p < nparts; p++) xyzz_add(acc, *reinterpret_cast<const XYZZ<Fq>*>(parts + kPartialBytes * p + off));
+    store_jacobian_std(acc, t == 0 ? out_a : out_c);
   }
   if (t == 64) {
     XYZZ<Fq2> acc = *reinterpret_cast<const XYZZ<Fq2>*>(parts + 512);
     for (int p = 1; p < nparts; p++) xyzz_add(acc, *reinterpret_cast<const XYZZ<Fq2>*>(parts + kPartialBytes * p + 512));
     store_jacobian_std(acc, out_b);
   }
-  __syncthreads();
-  XYZZ<Fq> prod;
-  if (t == 0) prod = xyzz_mul_scalar(sh[0], rs[1]);   // s * PiA     (groth16.go:272)
-  if (t == 32) prod = xyzz_mul_scalar(sh[1], rs[0]);  // r * piBG1   (groth16.go:273)
-  if (t == 64) store_jacobian_std(sh[0], out_a);
-  __syncthreads();
-  if (t == 32) sh[3] = prod;
-  __syncthreads();
-  if (t == 0) {
-    XYZZ<Fq> c = sh[2];
-    xyzz_add(c, prod);
-    xyzz_add(c, sh[3]);
-    store_jacobian_std(c, out_c);
-  }
+}
+// in place: CH part (@+768) += prod[0] + prod[1]
+__global__ void k_groth16_fold_products(uint8_t* res, const XYZZ<Fq>* prod) {
+  if (threadIdx.x | blockIdx.x) return;
+  XYZZ<Fq> c = *reinterpret_cast<const XYZZ<Fq>*>(res + 768);
+  xyzz_add(c, prod[0]);
+  xyzz_add(c, prod[1]);
+  *reinterpret_cast<XYZZ<Fq>*>(res + 768) = c;
 }
 
 // out[k] = Jacobian(res[k]) for the 7 G1 results and the G2 result of Pinocchio
@@ -183,6 +179,11 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   // if no rank holds elements of it (len == 0) the last rank does.
   pk->shared_w = pk->lo[0] == pk->lo[1] && pk->lo[1] == pk->lo[2] && pk->hi[0] == pk->hi[1] && pk->hi[1] == pk->hi[2] &&
                  pk->tail[0] && pk->tail[1] && pk->tail[2];
+  for (int k = 1; k < 3; k++)
+    for (int j = 0; j < k; j++)
+      if (pk->sort_src[k] == k && pk->lo[k] == pk->lo[j] && pk->hi[k] == pk->hi[j] && pk->tail[k] == pk->tail[j] &&
+          (pk->lo[k] < pk->hi[k] || pk->tail[k]))
+        pk->sort_src[k] = pk->sort_src[j];
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
   if (has(0)) {
@@ -324,44 +325,44 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
     if ((rc = msm_enqueue<Fq>(pk->g[3].get(), sCH, nterm[3], 0, reinterpret_cast<XYZZ<Fq>*>(res + 768), s3))) return rc;
   }
   EV_REC(e_ch, s3);
-  // --- A, B1, B2.  One GPU (or identical ranges): one digit sort of W = w || [1, r, s] shared by the three
-  // bucket phases; otherwise each set sorts its own slice.
-  if (pk->shared_w) {
-    SortScratch& sw = pk->g[0]->sort;
-    if ((rc = msm_sort(sw, pk->g[0]->sh, sv[0], nterm[0], 0, st))) return rc;
-    EV_REC(e_w, st);
-    EV_WAIT(s1, e_w);
-    if ((rc = msm_buckets<Fq>(pk->g[1].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
-    EV_REC(e_b1, s1);
-    EV_WAIT(s2, e_w);
-    if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
-    EV_REC(e_b2, s2);
-    if ((rc = msm_buckets<Fq>(pk->g[0].get(), sw, nterm[0], reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
-    EV_REC(e_a, st);
-  } else {
-    EV_WAIT(s1, e_in);
-    if (pk->g[1] && (rc = msm_enqueue<Fq>(pk->g[1].get(), sv[1], nterm[1], 0, reinterpret_cast<XYZZ<Fq>*>(res + 256), s1))) return rc;
-    EV_REC(e_b1, s1);
-    EV_WAIT(s2, e_in);
-    if (pk->g[2] && (rc = msm_enqueue<Fq2>(pk->g[2].get(), sv[2], nterm[2], 0, reinterpret_cast<XYZZ<Fq2>*>(res + 512), s2))) return rc;
-    EV_REC(e_b2, s2);
-    if (pk->g[0] && (rc = msm_enqueue<Fq>(pk->g[0].get(), sv[0], nterm[0], 0, reinterpret_cast<XYZZ<Fq>*>(res), st))) return rc;
-    EV_REC(e_a, st);
+  // --- A, B1, B2.  Sets that consume identical scalar slices (all three on one GPU; A and B1 on a rank that
+  // holds both whole) share ONE digit sort; the sort runs on the main stream, the bucket phases fan out.
+  XYZZ<Fq>* rA = reinterpret_cast<XYZZ<Fq>*>(res);
+  XYZZ<Fq>* rB1 = reinterpret_cast<XYZZ<Fq>*>(res + 256);
+  XYZZ<Fq2>* rB2 = reinterpret_cast<XYZZ<Fq2>*>(res + 512);
+  cudaStream_t sk[3] = {st, s1, s2};
+  cudaEvent_t e_sorted[3] = {e_w, pk->ev[7], e_prod};   // e_prod is re-recorded later; safe: waits are enqueued first
+  for (int k = 0; k < 3; k++) {
+    if (!pk->g[k] || pk->sort_src[k] != k) continue;
+    if ((rc = msm_sort(pk->g[k]->sort, pk->g[k]->sh, sv[k], nterm[k], 0, st))) return rc;
+    EV_REC(e_sorted[k], st);
   }
+  for (int k = 2; k >= 0; k--) {   // B2 first: it is the longest
+    if (!pk->g[k]) continue;
+    int src = pk->sort_src[k];
+    if (sk[k] != st) EV_WAIT(sk[k], e_sorted[src]);
+    size_t nt = nterm[src];
+    if (k == 0) rc = msm_buckets<Fq>(pk->g[0].get(), pk->g[src]->sort, nt, rA, sk[0]);
+    else if (k == 1) rc = msm_buckets<Fq>(pk->g[1].get(), pk->g[src]->sort, nt, rB1, sk[1]);
+    else rc = msm_buckets<Fq2>(pk->g[2].get(), pk->g[src]->sort, nt, rB2, sk[2]);
+    if (rc) return rc;
+  }
+  EV_REC(e_a, st);
+  EV_REC(e_b1, s1);
+  EV_REC(e_b2, s2);
+  // s*A_part and r*B1_part (groth16.go:272-273; linear, so each rank does its own parts) on side stream 1
+  // while B2 / C||PTD are still running
+  XYZZ<Fq>* prod = reinterpret_cast<XYZZ<Fq>*>(res + 1024);
+  EV_WAIT(s1, e_a);
+  k_groth16_products<<<1, 64, 0, s1>>>(res, pk->rs.as<Fr>() + 4, prod);
+  EV_REC(e_prod, s1);
+  EV_WAIT(st, e_prod);
+  EV_WAIT(st, e_b2);
+  EV_WAIT(st, e_ch);
   if (pk->world == 1) {
-    // s*A and r*B1 on side stream 1 while B2 / C||PTD are still running
-    XYZZ<Fq>* prod = reinterpret_cast<XYZZ<Fq>*>(res + 1024);
-    EV_WAIT(s1, e_a);
-    k_groth16_products<<<1, 64, 0, s1>>>(res, pk->rs.as<Fr>() + 4, prod);
-    EV_REC(e_prod, s1);
-    EV_WAIT(st, e_prod);
-    EV_WAIT(st, e_b2);
-    EV_WAIT(st, e_ch);
     k_groth16_combine<<<1, 96, 0, st>>>(res, prod, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
-  } else {  // hand the 1 KB partial record to the caller's all-gather
-    EV_WAIT(st, e_b1);
-    EV_WAIT(st, e_b2);
-    EV_WAIT(st, e_ch);
+  } else {  // fold the products into this rank's C part and hand the 1 KB partial record to the all-gather
+    k_groth16_fold_products<<<1, 32, 0, st>>>(res, prod);
     CU(cudaMemcpyAsync(d_out, res, kPartialBytes, cudaMemcpyDeviceToDevice, st));
   }
   g_launches += 3;
@@ -372,11 +373,8 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
 // Sharded mode, after the all-gather: sum the `world` partial records and finish the proof.
 int groth16_finalize_enqueue(ProvingKey* pk, const uint8_t* d_parts, int nparts, const uint64_t* r, const uint64_t* s,
                              Fq* d_out, cudaStream_t st) {
-  Fr rs_host[2] = {fr_load_std(r), fr_load_std(s)};
-  if (rs_host[0].geq_modulus() || rs_host[1].geq_modulus()) return fail(B200_ERANGE, "groth16_finalize: r or s >= field order");
-  CU(cudaMemcpyAsync(pk->rs.as<Fr>() + 6, rs_host, sizeof rs_host, cudaMemcpyHostToDevice, st));
-  k_groth16_finalize<<<1, 128, 0, st>>>(d_parts, nparts, pk->rs.as<Fr>() + 6, d_out, d_out + 3,
-                                        reinterpret_cast<Fq2*>(d_out + 6));
+  (void)pk; (void)r; (void)s;  // r, s were consumed per rank (their products are already inside the C parts)
+  k_groth16_finalize<<<1, 96, 0, st>>>(d_parts, nparts, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
   g_launches += 1;
   CU(cudaGetLastError());
   return B200_OK;
