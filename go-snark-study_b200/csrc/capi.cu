@@ -97,7 +97,7 @@ int init_locked(int device) {
     if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
   }
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));  // (stream priorities: no measurable effect)
   CU(cudaMalloc(&g_d_err, sizeof(int)));
   CU(cudaMemset(g_d_err, 0, sizeof(int)));
   g_poly = std::make_unique<PolyCtx>();
@@ -232,9 +232,10 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
     }
   }
   CU(b->slice_out.alloc((size_t)(b->affine_S ? 1 : b->sort.max_slices) * sizeof(XYZZ<F>)));
-  b->seg = sh.nbuckets >= 4096 ? 16 : (sh.nbuckets >= 256 ? 4 : 1);
+  // short latency chain: 4-bucket segments (8 adds + one small scalar mul per thread), then a two-level tree sum
+  b->seg = sh.nbuckets >= 256 ? 4 : 1;
   b->nseg = (sh.nbuckets + b->seg - 1) / b->seg;
-  CU(b->partials.alloc((size_t)b->nseg * sizeof(XYZZ<F>)));
+  CU(b->partials.alloc(((size_t)b->nseg + 1024) * sizeof(XYZZ<F>)));
   CU(b->result.alloc(sizeof(XYZZ<F>)));
   CU(b->out_std.alloc(3 * sizeof(F)));
 
@@ -305,6 +306,21 @@ void launch_accumulate(int lpb, const Affine<F>* table, const uint32_t* entries,
 }
 
 constexpr int kLPB = 8;
+
+// d_out[0] = sum of partials[0..n): one block if small, else 512 inputs per first-level block + a final block.
+// `partials` must have room for n + ceil(n/512) records.
+template <class F>
+void launch_tree_sum(XYZZ<F>* partials, uint32_t n, XYZZ<F>* d_out, cudaStream_t st) {
+  if (n <= 1024) {
+    k_sum_points<F><<<1, 256, 0, st>>>(partials, n, n, d_out);
+    g_launches += 1;
+    return;
+  }
+  uint32_t nb = (n + 511) / 512;
+  k_sum_points<F><<<nb, 256, 0, st>>>(partials, n, 512, partials + n);
+  k_sum_points<F><<<1, 256, 0, st>>>(partials + n, nb, nb, d_out);
+  g_launches += 2;
+}
 
 // Front end: signed-digit recode + counting sort of n scalars into bucket order (3 launches).
 int msm_sort(SortScratch& ss, const MsmShape& shape, const Fr* d_scalars, size_t n, int mont, cudaStream_t st) {
@@ -408,8 +424,8 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     else
       k_accumulate_nodes<F, 8><<<nblocks((size_t)sh.nbuckets * 8, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, R - R_aff, buckets);
     k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
-    k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
-    g_launches += 3;
+    launch_tree_sum<F>(partials, b->nseg, d_out, st);
+    g_launches += 2;
     CU(cudaGetLastError());
     return B200_OK;
   }
@@ -423,8 +439,8 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
   }
   k_merge_slices<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(b->slice_out.as<XYZZ<F>>(), stb, sh.nbuckets, buckets);
   k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
-  k_sum_points<F><<<1, 256, 0, st>>>(partials, b->nseg, d_out);
-  g_launches += 4;
+  launch_tree_sum<F>(partials, b->nseg, d_out, st);
+  g_launches += 3;
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -457,7 +473,7 @@ int sum_partials(const void* d_xyzz, size_t count, uint64_t* out, cudaStream_t s
   DevBuf res, std_out;
   CU(res.alloc(sizeof(XYZZ<F>)));
   CU(std_out.alloc(3 * sizeof(F)));
-  k_sum_points<F><<<1, 256, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_xyzz), (uint32_t)count, res.as<XYZZ<F>>());
+  k_sum_points<F><<<1, 256, 0, st>>>(reinterpret_cast<const XYZZ<F>*>(d_xyzz), (uint32_t)count, (uint32_t)count, res.as<XYZZ<F>>());
   k_finalize<F><<<1, 32, 0, st>>>(res.as<XYZZ<F>>(), std_out.as<F>());
   CU(cudaMemcpyAsync(out, std_out.p, 3 * sizeof(F), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -386,14 +386,18 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t nbuckets, uint32_t
   out[t] = sum;
 }
 
-// out[0] = sum of in[0..count): one block, strided accumulate + shuffle/smem tree.
+// out[blockIdx.x] = sum of this block's contiguous chunk of `per_block` inputs (strided accumulate, warp
+// shuffle tree, then warp 0 folds the 8 warp sums with a second shuffle tree).  Launched with one block it is
+// the final tree sum; with several blocks it is the first level of a two-level sum (shorter latency chain).
 template <class F>
 __global__ void __launch_bounds__(256)
-k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t count, XYZZ<F>* __restrict__ out) {
+k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t per_block, XYZZ<F>* __restrict__ out) {
   __shared__ XYZZ<F> warp_sums[8];
   uint32_t t = threadIdx.x;
+  uint32_t lo = blockIdx.x * per_block;
+  uint32_t hi = lo + per_block < count ? lo + per_block : count;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t k = t; k < count; k += blockDim.x) xyzz_add(acc, in[k]);
+  for (uint32_t k = lo + t; k < hi; k += blockDim.x) xyzz_add(acc, in[k]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     XYZZ<F> other = shfl_down_struct(acc, off, 32);
@@ -401,10 +405,14 @@ k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t count, XYZZ<F>* __restrict
   }
   if ((t & 31) == 0) warp_sums[t >> 5] = acc;
   __syncthreads();
-  if (t == 0) {
-    XYZZ<F> r = warp_sums[0];
-    for (uint32_t w = 1; w < (blockDim.x >> 5); w++) xyzz_add(r, warp_sums[w]);
-    out[0] = r;
+  if (t < 32) {
+    XYZZ<F> r = t < (blockDim.x >> 5) ? warp_sums[t] : XYZZ<F>::inf();
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      XYZZ<F> other = shfl_down_struct(r, off, 8);
+      xyzz_add(r, other);
+    }
+    if (t == 0) out[blockIdx.x] = r;
   }
 }
 

@@ -236,11 +236,73 @@ Fr fr_load_std(const uint64_t* v) {
   return r;
 }
 
-// prod[0] = s * A, prod[1] = r * B1  (groth16.go:272-273); res layout as in k_groth16_finalize
-__global__ void k_groth16_products(const uint8_t* res, const Fr* rs, XYZZ<Fq>* prod) {
+// ---- blinding products s*A and r*B1 (groth16.go:272-273) ---------------------------------------
+// They sit on the critical path of small proofs (a single-thread 254-bit double-and-add is ~2 ms), so each is
+// computed by FOUR lanes with the GLV endomorphism of BN254: phi(x, y) = (beta*x, y) = lambda*(x, y), and
+// k = k1 + k2*lambda with |k1|, |k2| < 2^128 (decomposed on the host with the lattice basis below).  Lane 0/1
+// take the low/high 64 bits of |k1| on P, lanes 2/3 those of |k2| on phi(P); the high lanes shift by 64
+// doublings, then two additions.  Depth: 128 Jacobian doublings (7 multiplies each) + ~35 additions instead of
+// 254 XYZZ doublings + ~120 additions.  Constants derived and checked against the oracle (tools/glv_constants.py).
+struct GlvScalars {
+  uint64_t k[2][4];   // product p: |k1| lo, |k1| hi, |k2| lo, |k2| hi
+  uint32_t neg[2][2]; // product p: k1 < 0, k2 < 0
+};
+
+__device__ __forceinline__ Jacobian<Fq> shfl_jac(const Jacobian<Fq>& v, int lane) {
+  Jacobian<Fq> r;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int w = 0; w < (int)(sizeof(Jacobian<Fq>) / 4); w++) dst[w] = __shfl_sync(0xffffffffu, src[w], lane);
+  return r;
+}
+// complete addition on top of the reference formula (which has no doubling branch)
+__device__ Jacobian<Fq> jac_add_complete(const Jacobian<Fq>& a, const Jacobian<Fq>& b) {
+  if (a.is_inf()) return b;
+  if (b.is_inf()) return a;
+  Jacobian<Fq> r = jac_add_ref(a, b);
+  if (r.Z.is_zero()) {  // same x: either a == b (double) or a == -b (infinity)
+    Fq z1z1 = a.Z.sqr(), z2z2 = b.Z.sqr();
+    if (a.Y * (b.Z * z2z2) == b.Y * (a.Z * z1z1)) return jac_double_ref(a);
+    return Jacobian<Fq>::inf();
+  }
+  return r;
+}
+
+// One warp: lanes 0..3 -> prod[0] = s*A, lanes 4..7 -> prod[1] = r*B1; res layout as in k_groth16_finalize.
+__global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* prod) {
   uint32_t t = threadIdx.x;
-  if (t == 0) prod[0] = xyzz_mul_scalar(*reinterpret_cast<const XYZZ<Fq>*>(res), rs[1]);
-  if (t == 32) prod[1] = xyzz_mul_scalar(*reinterpret_cast<const XYZZ<Fq>*>(res + 256), rs[0]);
+  if (t >= 32) return;
+  uint32_t grp = (t >> 2) & 1, lane4 = t & 3, base_lane = t & ~3u;
+  bool active = t < 8;
+  Jacobian<Fq> p = xyzz_to_jacobian(*reinterpret_cast<const XYZZ<Fq>*>(res + (grp ? 256 : 0)));
+  if (lane4 >= 2) {  // phi(P): x -> beta * x
+    Fq beta;
+    const uint32_t bm[8] = {0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu, 0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du};
+#pragma unroll
+    for (int i = 0; i < 8; i++) beta.l[i] = bm[i];
+    p.X = p.X * beta;
+  }
+  if (g.neg[grp][lane4 >> 1]) p.Y = p.Y.neg();
+  uint64_t chunk = active ? g.k[grp][lane4] : 0;
+  Jacobian<Fq> r = Jacobian<Fq>::inf();
+  bool started = false;
+  for (int b = 63; b >= 0; b--) {
+    uint32_t bit = (uint32_t)(chunk >> b) & 1;
+    if (!started && !bit) continue;
+    started = true;
+    r = jac_double_ref(r);
+    if (bit) r = jac_add_ref(r, p);   // r = m*p with m >= 2 or infinity: never equal to +-p
+  }
+  if (lane4 & 1)
+    for (int d = 0; d < 64; d++) r = jac_double_ref(r);   // high chunks: * 2^64
+  Jacobian<Fq> hi = shfl_jac(r, base_lane + (lane4 | 1));
+  if ((lane4 & 1) == 0) r = jac_add_complete(r, hi);      // lanes 0, 2: |k1|*P , |k2|*phi(P)
+  Jacobian<Fq> other = shfl_jac(r, base_lane + 2);
+  if (lane4 == 0) {
+    r = jac_add_complete(r, other);
+    if (active) prod[grp] = jacobian_to_xyzz(r);
+  }
 }
 __global__ void k_groth16_combine(const uint8_t* res, const XYZZ<Fq>* prod, Fq* out_a, Fq* out_c, Fq2* out_b) {
   uint32_t t = threadIdx.x;
@@ -252,6 +314,86 @@ __global__ void k_groth16_combine(const uint8_t* res, const XYZZ<Fq>* prod, Fq* 
   }
   if (t == 32) store_jacobian_std(*reinterpret_cast<const XYZZ<Fq>*>(res), out_a);
   if (t == 64) store_jacobian_std(*reinterpret_cast<const XYZZ<Fq2>*>(res + 512), out_b);
+}
+
+// k = k1 + k2*lambda (mod r), |k1|, |k2| < 2^128.  Lattice basis of BN254's GLV endomorphism:
+//   a1 = 0x89d3256894d213e3, b1 = -0x6f4d8248eeb859fc8211bbeb7d4f1128, a2 = 0x6f4d8248eeb859fd0be4e1541221250b, b2 = a1
+// c1 = round(b2*k/r), c2 = round(-b1*k/r) through g_i = round(2^256 * |.| / r);  k1 = k - c1*a1 - c2*a2,  k2 = c1*|b1| - c2*b2.
+// Any rounding error only lengthens k1, k2 by a bit; k1 + k2*lambda == k holds by construction.
+struct U5 { uint64_t l[5]; };
+inline U5 u5_mul(const uint64_t* a, int na, const uint64_t* b, int nb) {  // (na + nb <= 5 significant limbs)
+  uint64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < na; i++) {
+    unsigned __int128 c = 0;
+    for (int j = 0; j < nb; j++) {
+      c += (unsigned __int128)a[i] * b[j] + t[i + j];
+      t[i + j] = (uint64_t)c;
+      c >>= 64;
+    }
+    t[i + nb] += (uint64_t)c;
+  }
+  U5 r;
+  for (int i = 0; i < 5; i++) r.l[i] = t[i];
+  return r;
+}
+inline U5 u5_sub(const U5& a, const U5& b) {
+  U5 r;
+  unsigned __int128 br = 0;
+  for (int i = 0; i < 5; i++) {
+    unsigned __int128 d = (unsigned __int128)a.l[i] - b.l[i] - (uint64_t)br;
+    r.l[i] = (uint64_t)d;
+    br = (d >> 64) & 1;
+  }
+  return r;
+}
+inline bool u5_abs(U5& a) {  // two's complement -> magnitude; returns the sign
+  bool neg = (a.l[4] >> 63) != 0;
+  if (neg) {
+    unsigned __int128 c = 1;
+    for (int i = 0; i < 5; i++) {
+      c += (uint64_t)~a.l[i];
+      a.l[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  return neg;
+}
+inline int glv_decompose(const Fr& k_std, uint64_t out[4], uint32_t neg[2]) {
+  static const uint64_t A1[2] = {0x89d3256894d213e3ULL, 0}, B1m[2] = {0x8211bbeb7d4f1128ULL, 0x6f4d8248eeb859fcULL};
+  static const uint64_t A2[2] = {0x0be4e1541221250bULL, 0x6f4d8248eeb859fdULL}, B2[2] = {0x89d3256894d213e3ULL, 0};
+  static const uint64_t G1c[3] = {0xd91d232ec7e0b3d7ULL, 0x2ULL, 0}, G2c[3] = {0x7a7bd9d4391eb18eULL, 0x4ccef014a773d2cfULL, 0x2ULL};
+  uint64_t k[4];
+  memcpy(k, &k_std, 32);
+  auto round_shift = [&](const uint64_t* g, uint64_t c[3]) {  // (k * g + 2^255) >> 256
+    uint64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+      unsigned __int128 cy = 0;
+      for (int j = 0; j < 3; j++) {
+        cy += (unsigned __int128)k[i] * g[j] + t[i + j];
+        t[i + j] = (uint64_t)cy;
+        cy >>= 64;
+      }
+      t[i + 3] += (uint64_t)cy;
+    }
+    unsigned __int128 cy = (unsigned __int128)t[3] + 0x8000000000000000ULL;
+    cy >>= 64;
+    for (int i = 4; i < 7; i++) {
+      cy += t[i];
+      c[i - 4] = (uint64_t)cy;
+      cy >>= 64;
+    }
+  };
+  uint64_t c1[3], c2[3];
+  round_shift(G1c, c1);
+  round_shift(G2c, c2);
+  U5 kk{{k[0], k[1], k[2], k[3], 0}};
+  U5 k1 = u5_sub(u5_sub(kk, u5_mul(c1, 3, A1, 1)), u5_mul(c2, 3, A2, 2));
+  U5 k2 = u5_sub(u5_mul(c1, 3, B1m, 2), u5_mul(c2, 3, B2, 1));
+  neg[0] = u5_abs(k1);
+  neg[1] = u5_abs(k2);
+  if (k1.l[2] | k1.l[3] | k1.l[4] | k2.l[2] | k2.l[3] | k2.l[4]) return -1;  // cannot happen (|k_i| < 2^128)
+  out[0] = k1.l[0]; out[1] = k1.l[1]; out[2] = k2.l[0]; out[3] = k2.l[1];
+  return 0;
 }
 
 #define EV_REC(e, stream) CU(cudaEventRecord((e), (stream)))
@@ -354,7 +496,10 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   // while B2 / C||PTD are still running
   XYZZ<Fq>* prod = reinterpret_cast<XYZZ<Fq>*>(res + 1024);
   EV_WAIT(s1, e_a);
-  k_groth16_products<<<1, 64, 0, s1>>>(res, pk->rs.as<Fr>() + 4, prod);
+  GlvScalars glv;
+  if (glv_decompose(fr_s, glv.k[0], glv.neg[0]) || glv_decompose(fr_r, glv.k[1], glv.neg[1]))
+    return fail(B200_EINVAL, "groth16_prove: GLV decomposition out of range");
+  k_groth16_products<<<1, 32, 0, s1>>>(res, glv, prod);
   EV_REC(e_prod, s1);
   EV_WAIT(st, e_prod);
   EV_WAIT(st, e_b2);

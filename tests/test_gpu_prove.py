@@ -152,6 +152,10 @@ def test_prove_argument_errors(mods, golden_dir):
         groth16.GenerateProofs(cc, pk, g["witness"][:-1], g["px"], r=1, s=1)
     with pytest.raises(_lib.B200Error):                      # len(hx) > len(PowersTauDelta): reference panics
         groth16.GenerateProofs(cc, pk, g["witness"], g["px"] + [0] * 8, r=1, s=1)
+    for rr, ss in ((o.R - 1, o.R - 2), (1, o.R - 1), ((1 << 128) + 5, (1 << 64) - 1)):    # full-range / edge blinding scalars
+        got = groth16.GenerateProofs(cc, pk, g["witness"], g["px"], r=rr, s=ss)
+        exp, _ = o.groth16_prove(cc["NVars"], cc["NPublic"], pk, g["witness"], g["px"], rr, ss)
+        assert affeq(G1, got["PiA"], exp["PiA"]) and affeq(G2, got["PiB"], exp["PiB"]) and affeq(G1, got["PiC"], exp["PiC"])
     ok = groth16.GenerateProofs(cc, pk, g["witness"], g["px"], r=0, s=0)       # r = s = 0: no blinding
     ref, _ = o.groth16_prove(cc["NVars"], cc["NPublic"], pk, g["witness"], g["px"], 0, 0)
     assert affeq(G1, ok["PiC"], ref["PiC"]) and affeq(G1, ok["PiA"], ref["PiA"])
