@@ -637,6 +637,32 @@ int poly_eval_host(const uint64_t* v, size_t n, const uint64_t* x, uint64_t* out
   return check_err_flag<Fr>("poly_eval");
 }
 
+int poly_eval_batch_host(const uint64_t* polys, size_t m, size_t n, const uint64_t* x, uint64_t* out) {
+  if (!polys || !x || !out || m == 0 || n == 0) return fail(B200_EINVAL, "poly_eval_batch: bad arguments");
+  Fr xs = fr_load_std(x);
+  if (xs.geq_modulus()) return fail(B200_ERANGE, "poly_eval_batch: x >= r");
+  DevBuf dp, dout;
+  CU(dp.alloc(m * n * sizeof(Fr)));
+  CU(dout.alloc(m * sizeof(Fr)));
+  CU(cudaMemcpyAsync(dp.p, polys, m * n * sizeof(Fr), cudaMemcpyHostToDevice, g_stream));
+  k_poly_eval_batch<<<(unsigned)m, 64, 0, g_stream>>>(dp.as<Fr>(), (uint32_t)n, xs, dout.as<Fr>(), g_d_err);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, m * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("poly_eval_batch");
+}
+
+int zero_poly_host(size_t n, uint64_t* out) {   // coefficients of prod_{i=1..n} (x - i), n + 1 of them
+  if (!out || n > 8191) return fail(B200_EINVAL, "zero_poly: bad arguments (n <= 8191)");
+  DevBuf zn, zz;
+  CU(zn.alloc((n + 1) * sizeof(Fr)));
+  CU(zz.alloc((n + 1) * sizeof(Fr)));
+  k_zero_poly<<<1, 1024, 0, g_stream>>>(zn.as<Fr>(), (uint32_t)n);
+  k_poly_store<<<nblk(n + 1, 256), 256, 0, g_stream>>>(zn.as<Fr>(), (uint32_t)(n + 1), 0, 1, zz.as<Fr>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, zz.p, (n + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fr>("zero_poly");
+}
+
 template <class F>
 int group_op_host(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
   if (!p || !out || (op == 0 && !q)) return fail(B200_EINVAL, "group op: null pointer");
@@ -772,6 +798,8 @@ int b200_combine_polynomials(const uint64_t* r, size_t m, const uint64_t* ap, co
 int b200_poly_add(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) { B200_API_BODY(poly_addsub_host(a, na, b, nb, 0, out)) }
 int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out) { B200_API_BODY(poly_addsub_host(a, na, b, nb, 1, out)) }
 int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]) { B200_API_BODY(poly_eval_host(v, n, x, out)) }
+int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out) { B200_API_BODY(poly_eval_batch_host(polys, m, n, x, out)) }
+int b200_zero_poly(size_t n, uint64_t* out) { B200_API_BODY(zero_poly_host(n, out)) }
 int b200_g1_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(0, p, q, n, out)) }
 int b200_g1_double_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(1, p, nullptr, n, out)) }
 int b200_g1_neg_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(2, p, nullptr, n, out)) }

@@ -157,6 +157,40 @@ __global__ void k_poly_eval(const Fr* __restrict__ v, uint32_t n, Fr x_std, Fr* 
   if (t == 0) out[0] = part[0].from_mont();
 }
 
+// out[i] = sum_k P[i][k] x^k for m polynomials of n coefficients (row-major, standard form): one block per
+// polynomial.  Serves the trusted setup's At / Bt / Ct = Eval(alphas[i], tau) loops (groth16/groth16.go:164-205).
+__global__ void k_poly_eval_batch(const Fr* __restrict__ P, uint32_t n, Fr x_std, Fr* __restrict__ out, int* err) {
+  __shared__ Fr part[256];
+  const Fr* v = P + (size_t)blockIdx.x * n;
+  uint32_t t = threadIdx.x, T = blockDim.x;
+  Fr x = x_std.to_mont();
+  Fr xp = Fr::one(), base = x;
+  for (uint32_t e = t; e; e >>= 1) {
+    if (e & 1) xp = xp * base;
+    base = base.sqr();
+  }
+  Fr xT = Fr::one();
+  base = x;
+  for (uint32_t e = T; e; e >>= 1) {
+    if (e & 1) xT = xT * base;
+    base = base.sqr();
+  }
+  Fr acc = Fr::zero();
+  for (uint32_t i = t; i < n; i += T) {
+    Fr c = v[i];
+    if (c.geq_modulus()) atomicOr(err, 2);
+    else if (!c.is_zero()) acc = acc + c.to_mont() * xp;
+    xp = xp * xT;
+  }
+  part[t] = acc;
+  __syncthreads();
+  for (uint32_t s = T / 2; s > 0; s >>= 1) {
+    if (t < s) part[t] = part[t] + part[t + s];
+    __syncthreads();
+  }
+  if (t == 0) out[blockIdx.x] = part[0].from_mont();
+}
+
 // ---- element-wise group operations with the reference's own formulas --------
 // op 0: Add(p, q)   op 1: Double(p)   op 2: Neg(p)     (Jacobian standard form in/out)
 template <class F>

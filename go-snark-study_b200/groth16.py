@@ -80,3 +80,64 @@ def GenerateProofs(circuit, pk, w, px, r=None, s=None):
     wl = ints_to_limbs([reduce_scalar(x) for x in w])
     pl = ints_to_limbs([int(x) % R for x in px])
     return dpk.prove_limbs(wl, pl, r, s)
+
+
+def GenerateTrustedSetup(witnessLength, circuit, alphas, betas, gammas, toxic=None):
+    """groth16.GenerateTrustedSetup (groth16/groth16.go:94-222) with the heavy loops on the GPU: the
+    Eval(alphas[i], tau) evaluations (b200_poly_eval_batch), the z polynomial (b200_zero_poly) and every
+    G.MulScalar(generator, k) (b200_g{1,2}_mul_batch_bcast — the reference's own double-and-add, so the
+    points are X,Y,Z-identical to the reference's for the same toxic values).  ``toxic`` = dict
+    T, Kalpha, Kbeta, Kgamma, Kdelta; drawn like the reference (Fq.Rand) when omitted.  ``witnessLength`` is
+    unused, as in the reference.  Returns {"Toxic", "Pk", "Vk"} shaped like groth16.Setup."""
+    from . import bn128
+    from ._lib import limbs_to_ints
+    n_vars, n_public = _attr(circuit, "NVars"), _attr(circuit, "NPublic")
+    n_signals = len(_attr(circuit, "Signals")) if (isinstance(circuit, dict) and "Signals" in circuit) else n_vars
+    tox = toxic or {k: rand_fr() for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta")}
+    t, ka, kb, kg, kd = (int(tox[k]) % R for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta"))
+    m = len(alphas)
+    nz = m - 2                                                   # z pol: prod_{i=1}^{len(alphas)-2} (x - i), :122-132
+    zl = np.zeros((nz + 1, 4), dtype=np.uint64)
+    check(lib().b200_zero_poly(nz, ptr(zl)))
+    zpol = limbs_to_ints(zl)
+    tl = ints_to_limbs([t])
+
+    def evals(polys):
+        n = len(polys[0])
+        P = ints_to_limbs([int(x) % R for row in polys for x in row])
+        out = np.zeros((len(polys), 4), dtype=np.uint64)
+        check(lib().b200_poly_eval_batch(ptr(P), len(polys), n, ptr(tl), ptr(out)))
+        return limbs_to_ints(out)
+
+    zt = evals([zpol])[0]
+    inv_delta = pow(kd, -1, R)
+    zt_inv_delta = inv_delta * zt % R
+    g1, g2 = bn128.G1(), bn128.G2()
+    ptd_k, t_encr = [zt_inv_delta], t                            # :139-149
+    for _ in range(1, len(zpol)):
+        ptd_k.append(t_encr * zt_inv_delta % R)
+        t_encr = t_encr * t % R
+    at = evals(alphas[:n_signals])
+    bt = evals(betas[:n_signals])
+    ct = evals(gammas[:n_signals])
+    inv_gamma = pow(kg, -1, R)
+    c_k = [inv_delta * ((at[i] * kb + bt[i] * ka + ct[i]) % R) % R for i in range(n_public + 1, n_vars)]     # :181-200
+    ic_k = [inv_gamma * ((at[i] * kb + bt[i] * ka + ct[i]) % R) % R for i in range(n_public + 1)]            # :202-219
+    # one batched scalar multiplication of the G1 generator for every G1 point of the setup
+    k1 = ptd_k + [ka, kb, kd] + at + bt + c_k + ic_k
+    p1 = g1.MulScalarBatch([g1.G], k1)
+    k2 = [kb, kg, kd] + bt
+    p2 = g2.MulScalarBatch([g2.G], k2)
+    o = 0
+    ptd = p1[o:o + len(ptd_k)]; o += len(ptd_k)
+    alpha1, beta1, delta1 = p1[o:o + 3]; o += 3
+    At = p1[o:o + len(at)]; o += len(at)
+    B1 = p1[o:o + len(bt)]; o += len(bt)
+    Cd = p1[o:o + len(c_k)]; o += len(c_k)
+    IC = p1[o:o + len(ic_k)]
+    beta2, gamma2, delta2 = p2[:3]
+    pk = {"BACDelta": [(0, 0, 0)] * (n_public + 1) + Cd, "Z": zpol, "PowersTauDelta": ptd,
+          "G1": {"Alpha": alpha1, "Beta": beta1, "Delta": delta1, "At": At, "BACGamma": B1},
+          "G2": {"Beta": beta2, "Gamma": gamma2, "Delta": delta2, "BACGamma": p2[3:]}}
+    vk = {"IC": IC, "G1": {"Alpha": alpha1}, "G2": {"Beta": beta2, "Gamma": gamma2, "Delta": delta2}}
+    return {"Toxic": {"T": t, "Kalpha": ka, "Kbeta": kb, "Kgamma": kg, "Kdelta": kd}, "Pk": pk, "Vk": vk}

@@ -171,6 +171,12 @@ int b200_poly_add(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, uint64_t* out); /* r1csqap.go:106-115 */
 int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]);        /* r1csqap.go:118-126 */
 
+/* out[i] = Eval(polys[i], x) for m polynomials of n coefficients each (row-major): the At/Bt/Ct loops of
+ * GenerateTrustedSetup (groth16/groth16.go:164-205, snark.go:181-218).                                        */
+int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out);
+/* out[0..n] = coefficients of prod_{i=1}^{n} (x - i): the "z pol" of groth16.go:122-132 / snark.go:221-232.   */
+int b200_zero_poly(size_t n, uint64_t* out);
+
 /* ---- dense QAP API upstream of GenerateProofs (small n; the prove path consumes px) ---- */
 /* PolynomialField.R1CSToQAP (r1csqap/r1csqap.go:161-188).  a, b, c: n x m row-major R1CS matrices (coefficients
  * reduced mod r).  alphas/betas/gammas: m x n (row i = coefficients of signal i's polynomial over the domain {1..n});
