@@ -1,0 +1,140 @@
+// Package b200 is the cgo binding of libb200snark (include/b200snark.h): the marshalling layer a
+// maintainer of arnaucube/go-snark-study links under groth16.GenerateProofs / snark.GenerateProofs /
+// r1csqap.PolynomialField / bn128.G1,G2 to run the prove path on a B200.
+//
+// NOT COMPILED IN THIS REPOSITORY: neither the build image nor the GPU box has a Go toolchain
+// (`go version`: not found).  The identical marshalling is exercised through ctypes by the Python
+// mirror (go-snark-study_b200/_lib.py) in tests/.  See INTEGRATION.md.
+package b200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../go-snark-study_b200/lib -lb200snark
+#include <stdlib.h>
+#include "b200snark.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"math/big"
+	"unsafe"
+)
+
+// R is the BN254 scalar-field order (bn128/bn128.go:46).
+var R, _ = new(big.Int).SetString("21888242871839275222246405745257275088548364400416034343698204186575808495617", 10)
+
+func check(rc C.int) error {
+	if rc == 0 {
+		return nil
+	}
+	return errors.New("libb200snark: " + C.GoString(C.b200_last_error()))
+}
+
+// limbs appends the 4 little-endian 64-bit limbs of x (0 <= x < 2^256) to dst.
+func limbs(dst []uint64, x *big.Int) []uint64 {
+	w := x.Bits() // amd64: big.Word is 64-bit, little endian
+	for i := 0; i < 4; i++ {
+		if i < len(w) {
+			dst = append(dst, uint64(w[i]))
+		} else {
+			dst = append(dst, 0)
+		}
+	}
+	return dst
+}
+
+// Scalar is what crosses the ABI for a *big.Int scalar: |e| mod r (the reference's MulScalar
+// consumes |e|: fields/fq.go:138-140).
+func Scalar(e *big.Int) *big.Int { return new(big.Int).Mod(new(big.Int).Abs(e), R) }
+
+// Coeff is what crosses the ABI for a polynomial coefficient: e mod r (Euclidean, like Fq.Add/Mul).
+func Coeff(e *big.Int) *big.Int { return new(big.Int).Mod(e, R) }
+
+func FlatFr(v []*big.Int, reduce func(*big.Int) *big.Int) []uint64 {
+	out := make([]uint64, 0, 4*len(v))
+	for _, x := range v {
+		out = limbs(out, reduce(x))
+	}
+	return out
+}
+func FlatG1(pts [][3]*big.Int) []uint64 {
+	out := make([]uint64, 0, 12*len(pts))
+	for _, p := range pts {
+		for k := 0; k < 3; k++ {
+			out = limbs(out, p[k])
+		}
+	}
+	return out
+}
+func FlatG2(pts [][3][2]*big.Int) []uint64 {
+	out := make([]uint64, 0, 24*len(pts))
+	for _, p := range pts {
+		for k := 0; k < 3; k++ {
+			out = limbs(limbs(out, p[k][0]), p[k][1])
+		}
+	}
+	return out
+}
+func fromLimbs(w []uint64) *big.Int {
+	words := make([]big.Word, len(w))
+	for i, x := range w {
+		words[i] = big.Word(x)
+	}
+	return new(big.Int).SetBits(words)
+}
+func G1FromLimbs(w []uint64) [3]*big.Int {
+	return [3]*big.Int{fromLimbs(w[0:4]), fromLimbs(w[4:8]), fromLimbs(w[8:12])}
+}
+func G2FromLimbs(w []uint64) [3][2]*big.Int {
+	var p [3][2]*big.Int
+	for k := 0; k < 3; k++ {
+		p[k] = [2]*big.Int{fromLimbs(w[8*k : 8*k+4]), fromLimbs(w[8*k+4 : 8*k+8])}
+	}
+	return p
+}
+func u64(v []uint64) *C.uint64_t { return (*C.uint64_t)(unsafe.Pointer(&v[0])) }
+
+// Groth16Key is a device-resident proving key (b200_pk_t).
+type Groth16Key struct{ h C.b200_pk_t }
+
+// LoadGroth16 uploads groth16.Pk once (b200_groth16_pk_load).
+func LoadGroth16(at, b1 [][3]*big.Int, b2 [][3][2]*big.Int, bacDelta, ptd [][3]*big.Int, z []*big.Int,
+	alpha1, beta1, delta1 [3]*big.Int, beta2, delta2 [3][2]*big.Int, nVars, nPublic int) (*Groth16Key, error) {
+	fa, fb1, fb2, fc, fp := FlatG1(at[:nVars]), FlatG1(b1[:nVars]), FlatG2(b2[:nVars]), FlatG1(bacDelta[:nVars]), FlatG1(ptd)
+	fz := FlatFr(z, Coeff)
+	a1, be1, d1 := FlatG1([][3]*big.Int{alpha1}), FlatG1([][3]*big.Int{beta1}), FlatG1([][3]*big.Int{delta1})
+	be2, d2 := FlatG2([][3][2]*big.Int{beta2}), FlatG2([][3][2]*big.Int{delta2})
+	var k Groth16Key
+	rc := C.b200_groth16_pk_load(u64(fa), u64(fb1), u64(fb2), u64(fc), C.size_t(nVars), u64(fp), C.size_t(len(ptd)),
+		u64(fz), C.size_t(len(z)), u64(a1), u64(be1), u64(d1), u64(be2), u64(d2), C.size_t(nPublic), 0, &k.h)
+	return &k, check(rc)
+}
+
+// Prove is groth16.GenerateProofs after the randomness has been drawn (groth16.go:231-238).
+func (k *Groth16Key) Prove(w, px []*big.Int, r, s *big.Int) (piA [3]*big.Int, piB [3][2]*big.Int, piC [3]*big.Int, err error) {
+	fw, fpx := FlatFr(w, Scalar), FlatFr(px, Coeff)
+	fr, fs := limbs(nil, r), limbs(nil, s)
+	a, b, c := make([]uint64, 12), make([]uint64, 24), make([]uint64, 12)
+	rc := C.b200_groth16_prove(k.h, u64(fw), C.size_t(len(w)), u64(fpx), C.size_t(len(px)), u64(fr), u64(fs), u64(a), u64(b), u64(c))
+	if err = check(rc); err != nil {
+		return
+	}
+	return G1FromLimbs(a), G2FromLimbs(b), G1FromLimbs(c), nil
+}
+
+func (k *Groth16Key) Free() { C.b200_pk_free(k.h) }
+
+// PolyMul / PolyDiv back r1csqap.PolynomialField.Mul / Div (r1csqap/r1csqap.go:57-84).
+func PolyMul(a, b []*big.Int) ([]*big.Int, error) {
+	fa, fb := FlatFr(a, Coeff), FlatFr(b, Coeff)
+	out := make([]uint64, 4*(len(a)+len(b)-1))
+	if err := check(C.b200_poly_mul(u64(fa), C.size_t(len(a)), u64(fb), C.size_t(len(b)), u64(out))); err != nil {
+		return nil, err
+	}
+	res := make([]*big.Int, len(a)+len(b)-1)
+	for i := range res {
+		res[i] = fromLimbs(out[4*i : 4*i+4])
+	}
+	return res, nil
+}
