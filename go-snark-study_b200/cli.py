@@ -1,0 +1,124 @@
+"""File-compatible stand-in for the prove commands of the reference's CLI (cli/main.go):
+
+    python -m gosnark_b200.cli groth16 genproofs      # cli/main.go:455-518
+    python -m gosnark_b200.cli genproofs              # cli/main.go:303-366   (Pinocchio)
+
+Reads the files the Go CLI writes/reads in the current directory (compiledcircuit.json,
+trustedsetup.json, privateInputs.json, publicInputs.json — Go encoding/json of the structs, big.Int as
+JSON numbers, Jacobian coordinates), runs witness -> R1CSToQAP -> CombinePolynomials -> GenerateProofs on
+the GPU and writes proofs.json in the same layout, so the unmodified `go-snark-cli [groth16] verify`
+accepts it.  Host glue only; no kernel logic here.
+"""
+import json
+import sys
+
+from . import _lib, groth16, r1csqap, snark
+
+
+def calculate_witness(circuit, private_inputs, public_inputs):
+    """circuitcompiler.Circuit.CalculateWitness (circuitcompiler/circuit.go:158-186) over the compiled
+    circuit's flat constraint list (unreduced integers, as in the reference)."""
+    if len(private_inputs) != len(circuit["PrivateInputs"]) or len(public_inputs) != len(circuit["PublicInputs"]):
+        raise ValueError("given inputs != circuit inputs")
+    signals = circuit["Signals"]
+    w = [0] * len(signals)
+    w[0] = 1
+    for i, v in enumerate(public_inputs):
+        w[i + 1] = int(v)
+    for i, v in enumerate(private_inputs):
+        w[i + len(public_inputs) + 1] = int(v)
+
+    def grab(s):                                   # grabVar, circuit.go:141-149
+        try:
+            return int(s)
+        except ValueError:
+            return w[signals.index(s)]
+
+    for c in circuit["Constraints"]:
+        op = c["Op"]
+        if op == "in":
+            continue
+        a, b = grab(c["V1"]), grab(c["V2"])
+        out = signals.index(c["Out"])
+        if op == "+":
+            w[out] = a + b
+        elif op == "-":
+            w[out] = a - b
+        elif op == "*":
+            w[out] = a * b
+        elif op == "/":
+            w[out] = int(a / b) if b else 0           # big.Int.Div is Euclidean; inputs are non-negative here
+    return w
+
+
+def _t3(p):
+    return tuple(p)
+
+
+def _g2(p):
+    return tuple(tuple(c) for c in p)
+
+
+def _load(name):
+    with open(name) as f:
+        return json.load(f)
+
+
+def _qap_px(circuit, w):
+    pf = r1csqap.PolynomialField()
+    r1cs = circuit["R1CS"]
+    alphas, betas, gammas, _ = pf.R1CSToQAP(r1cs["A"], r1cs["B"], r1cs["C"])
+    _, _, _, px = pf.CombinePolynomials(w, alphas, betas, gammas)
+    return px
+
+
+def groth16_genproofs():
+    circuit, setup = _load("compiledcircuit.json"), _load("trustedsetup.json")
+    w = calculate_witness(circuit, _load("privateInputs.json"), _load("publicInputs.json"))
+    px = _qap_px(circuit, w)
+    pk = setup["Pk"]
+    pkd = {"Z": pk["Z"], "BACDelta": [_t3(p) for p in pk["BACDelta"]], "PowersTauDelta": [_t3(p) for p in pk["PowersTauDelta"]],
+           "G1": {"Alpha": _t3(pk["G1"]["Alpha"]), "Beta": _t3(pk["G1"]["Beta"]), "Delta": _t3(pk["G1"]["Delta"]),
+                  "At": [_t3(p) for p in pk["G1"]["At"]], "BACGamma": [_t3(p) for p in pk["G1"]["BACGamma"]]},
+           "G2": {"Beta": _g2(pk["G2"]["Beta"]), "Delta": _g2(pk["G2"]["Delta"]),
+                  "BACGamma": [_g2(p) for p in pk["G2"]["BACGamma"]]}}
+    proof = groth16.GenerateProofs(circuit, pkd, w, px)
+    out = {"PiA": list(proof["PiA"]), "PiB": [list(c) for c in proof["PiB"]], "PiC": list(proof["PiC"])}
+    with open("proofs.json", "w") as f:
+        json.dump(out, f)
+    print("witness", w)
+    print("Proofs data written to  proofs.json")
+
+
+def pinocchio_genproofs():
+    circuit, setup = _load("compiledcircuit.json"), _load("trustedsetup.json")
+    w = calculate_witness(circuit, _load("privateInputs.json"), _load("publicInputs.json"))
+    px = _qap_px(circuit, w)
+    pk = {k: [_t3(p) for p in setup["Pk"][k]] for k in ("A", "C", "Kp", "Ap", "Bp", "Cp")}
+    pk["B"] = [_g2(p) for p in setup["Pk"]["B"]]
+    pk["Z"] = setup["Pk"]["Z"]
+    # the prebuilt CLI is one commit older than snark.go: G1T sits at the top level of the setup
+    pk["G1T"] = [_t3(p) for p in (setup["Pk"].get("G1T") or setup["G1T"])]
+    proof = snark.GenerateProofs(circuit, pk, w, px)
+    out = {k: (list(v) if k != "PiB" else [list(c) for c in v]) for k, v in proof.items()}
+    with open("proofs.json", "w") as f:
+        json.dump(out, f)
+    print("witness", w)
+    print("Proofs data written to  proofs.json")
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    _lib.init()
+    if argv[:2] == ["groth16", "genproofs"]:
+        groth16_genproofs()
+    elif argv[:1] == ["genproofs"]:
+        pinocchio_genproofs()
+    else:
+        print("usage: python -m gosnark_b200.cli [groth16] genproofs", file=sys.stderr)
+        return 2
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
