@@ -14,13 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOBIN = os.path.join(ROOT, "oracle", "_ref", "go-snark-cli")
 
 
-def test_calculate_witness_matches_go(golden_dir):
-    from gosnark_b200.cli import calculate_witness
-    for name in ("x3x5", "mul", "chain21"):
-        g = json.load(open(os.path.join(golden_dir, f"gobin_{name}.json")))
-        assert calculate_witness(g["compiledcircuit"], g["private"], g["public"]) == g["witness"]   # circuit_test.go:81-82
-
-
 @pytest.mark.parametrize("name,proto", [("x3x5", "groth16"), ("chain21", "groth16"), ("x3x5", "pinocchio")])
 def test_go_cli_verifies_files_we_write(golden_dir, name, proto):
     if not os.path.exists(GOBIN):

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Emulate every rank of an N-way sharded proof on ONE GPU and time each rank's partial prove (development aid:
+shows which rank bounds the multi-GPU step)."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from gosnark_b200 import _lib
+from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+from gosnark_b200.shard import shard_ranges
+from gosnark_b200.synthetic import SyntheticGroth16
+
+logn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+_lib.init(0)
+L = lib()
+syn = SyntheticGroth16(logn)
+r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
+d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
+d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
+d_out = torch.zeros(128, dtype=torch.int64, device="cuda")
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+for rk in range(world):
+    pk = syn.load_pk(rk, world)
+    for _ in range(3):
+        check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), syn.m, d_px.data_ptr(), 2 * syn.n - 1, ptr(r_l), ptr(s_l), d_out.data_ptr(), stream.cuda_stream))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), syn.m, d_px.data_ptr(), 2 * syn.n - 1, ptr(r_l), ptr(s_l), d_out.data_ptr(), stream.cuda_stream))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sh = shard_ranges(syn.m, syn.npublic, syn.n_ptd, rk, world)
+    desc = " ".join(f"{n}[{s['lo']}:{s['hi']}{'+t' if s['tail'] else ''}]" for n, s in zip("A B1 B2 CH".split(), sh["sets"]) if s["lo"] < s["hi"] or s["tail"])
+    print(f"rank {rk}/{world}: {e0.elapsed_time(e1)/5:.3f} ms   {desc}")
+    check(L.b200_pk_free(pk))
