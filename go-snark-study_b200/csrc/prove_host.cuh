@@ -184,25 +184,31 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
       if (pk->sort_src[k] == k && pk->lo[k] == pk->lo[j] && pk->hi[k] == pk->hi[j] && pk->tail[k] == pk->tail[j] &&
           (pk->lo[k] < pk->hi[k] || pk->tail[k]))
         pk->sort_src[k] = pk->sort_src[j];
+  // Accumulation kernel per rank: the batched-affine tree pays off when the rank has enough overlapping work to
+  // cover its per-round inversion gaps; a rank left with one or two small MSMs (4+ GPUs at 2^20) is faster with
+  // the XYZZ kernel (measured per-rank at 2^20: N=8 5.05 vs 6.45 ms, N=4 8.10 vs 8.29, N=2 14.5 vs 12.1).
+  double weighted_terms = 0;
+  for (int k = 0; k < 4; k++) weighted_terms += wgt[k] * (double)(pk->hi[k] - pk->lo[k]);
+  const bool affine_ok = weighted_terms >= 2.0e6;
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
   if (has(0)) {
     PointCat cat(12);
     cat.add(at + 12 * pk->lo[0], pk->hi[0] - pk->lo[0]);
     if (pk->tail[0]) { cat.add(alpha1, 1); cat.add(delta1, 1); cat.add(inf1, 1); }
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], true))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], affine_ok))) return rc;
   }
   if (has(1)) {
     PointCat cat(12);
     cat.add(b1 + 12 * pk->lo[1], pk->hi[1] - pk->lo[1]);
     if (pk->tail[1]) { cat.add(beta1, 1); cat.add(inf1, 1); cat.add(delta1, 1); }
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], true))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], affine_ok))) return rc;
   }
   if (has(2)) {
     PointCat cat(24);
     cat.add(b2 + 24 * pk->lo[2], pk->hi[2] - pk->lo[2]);
     if (pk->tail[2]) { cat.add(beta2, 1); cat.add(inf2, 1); cat.add(delta2, 1); }
-    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], true))) return rc;
+    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], affine_ok))) return rc;
   }
   if (has(3)) {
     PointCat cat(12);
@@ -212,7 +218,7 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
     cat.add(bacdelta + 12 * (l1 + c_lo), c_hi - c_lo);
     cat.add(ptd + 12 * p_lo, p_hi - p_lo);
     if (pk->tail[3]) cat.add(delta1, 1);
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], true))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], affine_ok))) return rc;
   }
   CU(pk->s3.alloc((m + n_ptd + 4) * sizeof(Fr)));
   CU(pk->s4.alloc((m + 4) * sizeof(Fr)));
