@@ -211,13 +211,28 @@ def main():
 
     host_out = (np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64))
 
+    # sharded ranks stage only what they read: their witness index ranges, and px only if they hold PTD points
+    info = np.zeros(12, dtype=np.uint64)
+    check(L.b200_groth16_shard_info(pk, ptr(info)))
+    w_ranges, needs_px = [], bool(info[8])
+    for lo, hi in sorted({(int(info[2 * k]), int(info[2 * k + 1])) for k in range(4)}):
+        if lo < hi:
+            if w_ranges and lo <= w_ranges[-1][1]:
+                w_ranges[-1] = (w_ranges[-1][0], max(w_ranges[-1][1], hi))
+            else:
+                w_ranges.append((lo, hi))
+    h2d_bytes = (32 * m + 32 * npx) if world == 1 else (sum(32 * (hi - lo) for lo, hi in w_ranges) + (32 * npx if needs_px else 0))
+    d_w2, h_w2 = d_w.view(-1, 4), h_w.view(-1, 4)
+
     def step_e2e():
         if world == 1:      # the reference-facing call: host pointers in, proof out
             check(L.b200_groth16_prove(pk, h_w.data_ptr(), m, h_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
                                        ptr(host_out[0]), ptr(host_out[1]), ptr(host_out[2])))
             return None
-        d_w.copy_(h_w, non_blocking=True)
-        d_px.copy_(h_px, non_blocking=True)
+        for lo, hi in w_ranges:
+            d_w2[lo:hi].copy_(h_w2[lo:hi], non_blocking=True)
+        if needs_px:
+            d_px.copy_(h_px, non_blocking=True)
         step_device()
         return d_out.cpu()
 
@@ -360,7 +375,10 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)", "data": "synthetic", "config": config,
         "constraints_per_sec": value * n, "parity_vs_known_dlog": parity,
         "e2e": {"value": 1e3 / e2e_ms, "unit": "proofs/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 32 * m + 32 * npx, "d2h_bytes_per_step": 384},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 384,
+                "note": "N=1: the host-pointer C ABI call b200_groth16_prove; N>1: per rank, pinned->device copies of the "
+                        "witness ranges it reads (+ px on ranks holding PowersTauDelta), partial prove, NCCL all-gather, "
+                        "finalize, device->host read of the proof; h2d bytes are rank 0's"},
         "gpu_launches": int(prof[6]),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "G1 bucket accumulation phase (k_affine_forward/invert/backward<Fq> rounds; "

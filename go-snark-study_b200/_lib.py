@@ -55,6 +55,7 @@ _SIGNATURES = {
     "b200_groth16_pk_load_shard": [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _sz, _int,
                                    _int, _int, ctypes.POINTER(_h)],
     "b200_groth16_finalize_device": [_h, _vp, _int, _vp, _vp, _vp, _vp],
+    "b200_groth16_shard_info": [_h, _vp],
     "b200_poly_add": [_vp, _sz, _vp, _sz, _vp],
     "b200_poly_sub": [_vp, _sz, _vp, _sz, _vp],
     "b200_poly_eval": [_vp, _sz, _vp, _vp],

@@ -748,6 +748,22 @@ int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const vo
   return groth16_enqueue(p, (const Fr*)d_w, nw, (const Fr*)d_px, npx, r, s, (Fq*)d_out,
                          stream ? (cudaStream_t)stream : g_stream);
 }
+int b200_groth16_shard_info(b200_pk_t pk, uint64_t out[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  ProvingKey* p = find_pk(pk, 1);
+  if (!p || !out) return fail(B200_EINVAL, "groth16_shard_info: bad arguments");
+  const size_t l1 = p->npublic + 1, ncf = p->n_c_full;
+  for (int k = 0; k < 3; k++) { out[2 * k] = p->lo[k]; out[2 * k + 1] = p->hi[k]; }
+  size_t lo3 = p->lo[3], hi3 = p->hi[3];
+  size_t c_lo = lo3 < ncf ? lo3 : ncf, c_hi = hi3 < ncf ? hi3 : ncf;
+  out[6] = l1 + c_lo;                       // witness range feeding this rank's C part
+  out[7] = l1 + c_hi;
+  out[8] = hi3 > ncf ? 1 : 0;               // holds PowersTauDelta indices => needs px
+  out[9] = (uint64_t)p->rank;
+  out[10] = (uint64_t)p->world;
+  out[11] = p->m;
+  return B200_OK;
+}
 int b200_profile(int enable) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_prof = (enable & 1) != 0;

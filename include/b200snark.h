@@ -134,6 +134,10 @@ int b200_groth16_pk_load_shard(const uint64_t* at, const uint64_t* b1, const uin
                                const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
                                const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
                                int rank, int world, b200_pk_t* out);
+/* What a sharded key reads: out = { A lo, hi, B1 lo, hi, B2 lo, hi (witness index ranges), C-part witness
+ * range lo, hi, needs_px (0/1), rank, world, NVars }.  A caller that stages inputs per proof only has to upload
+ * those witness ranges, and px only when needs_px is set.                                                        */
+int b200_groth16_shard_info(b200_pk_t pk, uint64_t out[12]);
 int b200_groth16_finalize_device(b200_pk_t pk, const void* d_parts, int nparts, const uint64_t r[4],
                                  const uint64_t s[4], void* d_out, void* stream);
 /* Pinocchio proving key (snark.Pk, snark.go:16-26): A, Ap, Bp, C, Cp, Kp in G1 and
