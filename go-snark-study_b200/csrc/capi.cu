@@ -287,12 +287,12 @@ void launch_accumulate_l(const Affine<F>* table, const uint32_t* entries, SliceT
                          XYZZ<F>* out, uint32_t max_slices, cudaStream_t st) {
   unsigned grid = nblocks((size_t)max_slices * LPB, 128);
   if constexpr (sizeof(F) == sizeof(Fq)) {
-    k_accumulate<F, LPB, 4, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
   } else {
     static const int minb = getenv("B200_ACC_MINB_G2") ? atoi(getenv("B200_ACC_MINB_G2")) : 1;  // tuning knob
-    if (minb >= 4) k_accumulate<F, LPB, 4, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
-    else if (minb >= 2) k_accumulate<F, LPB, 2, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
-    else k_accumulate<F, LPB, 1, false><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    if (minb >= 4) k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    else if (minb >= 2) k_accumulate<F, LPB, 2><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    else k_accumulate<F, LPB, 1><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
   }
 }
 template <class F>

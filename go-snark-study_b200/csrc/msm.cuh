@@ -280,7 +280,9 @@ __global__ void k_fill_slices(const uint32_t* __restrict__ counts, const uint32_
 // LPB lanes cooperate on one slice (normally = one bucket): lane l takes entries
 // l, l+LPB, ... (coalesced reads of `entries`), gathers the precomputed affine
 // points and mixed-adds them; a warp-shuffle tree then merges the LPB partials.
-template <class F, int LPB, int MINB = 1, bool PREFETCH = true>
+// (A software-prefetch variant — next point fetched before the current add — and 80..154-register builds were
+// measured within 2 % of this one: the kernel is bound by the multiply pipe, profiles/r1_notes.md.)
+template <class F, int LPB, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries, SliceTables st,
              uint32_t m, XYZZ<F>* __restrict__ slice_out) {
@@ -291,30 +293,11 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
   bool live = sid < nslices;
   uint32_t start = live ? st.slice_start[sid] : 0, end = live ? st.slice_end[sid] : 0;
   XYZZ<F> acc = XYZZ<F>::inf();
-  uint32_t k = start + lane;
-  if (PREFETCH) {
-    if (k < end) {
-      uint32_t e = entries[k];
-      Affine<F> p = ld_affine_gather(&table[e >> 1]);
-      uint32_t neg = e & 1;
-      for (k += LPB; k < end; k += LPB) {  // software pipeline: fetch next point before the add
-        uint32_t e2 = entries[k];
-        Affine<F> p2 = ld_affine_gather(&table[e2 >> 1]);
-        if (neg) p.y = p.y.neg();
-        xyzz_madd(acc, p);
-        p = p2;
-        neg = e2 & 1;
-      }
-      if (neg) p.y = p.y.neg();
-      xyzz_madd(acc, p);
-    }
-  } else {
-    for (; k < end; k += LPB) {
-      uint32_t e = entries[k];
-      Affine<F> p = ld_affine_gather(&table[e >> 1]);
-      if (e & 1) p.y = p.y.neg();
-      xyzz_madd(acc, p);
-    }
+  for (uint32_t k = start + lane; k < end; k += LPB) {
+    uint32_t e = entries[k];
+    Affine<F> p = ld_affine_gather(&table[e >> 1]);
+    if (e & 1) p.y = p.y.neg();
+    xyzz_madd(acc, p);
   }
 #pragma unroll
   for (int off = LPB / 2; off > 0; off >>= 1) {

@@ -116,10 +116,6 @@ __global__ void k_two_minus(Fr* t, uint32_t n, uint32_t n_pad) {
   if (i == 0) v = v + Fr::one() + Fr::one();
   t[i] = v;
 }
-__global__ void k_zero_tail(Fr* t, uint32_t from, uint32_t to) {
-  uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < to) t[i] = Fr::zero();
-}
 // g[0] = 1 / f[0]   (f Montgomery); flag |= 4 if f[0] == 0
 __global__ void k_series_inv0(const Fr* f, Fr* g, int* err) {
   if (threadIdx.x | blockIdx.x) return;

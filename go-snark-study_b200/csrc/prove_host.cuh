@@ -35,7 +35,6 @@ struct ProvingKey {
   size_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};  // index range inside set k
   bool tail[4] = {false, false, false, false};        // this rank also holds set k's blinding points
   size_t n_c_full = 0;                                // length of the C part of the C||PTD set (m - npublic - 1)
-  bool shared_w = false;                              // sets 0..2 cover identical ranges -> one shared digit sort
   int sort_src[3] = {0, 1, 2};                        // set k reuses the digit sort of set sort_src[k] (same scalars)
   DevBuf s4;                                          // extra scalar vector (non-shared case)
   DevBuf h_full;              // full quotient (sharded mode)
@@ -177,8 +176,7 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   }
   // a set whose end falls exactly on a cut: the rank holding its last element owns the tail (checked above);
   // if no rank holds elements of it (len == 0) the last rank does.
-  pk->shared_w = pk->lo[0] == pk->lo[1] && pk->lo[1] == pk->lo[2] && pk->hi[0] == pk->hi[1] && pk->hi[1] == pk->hi[2] &&
-                 pk->tail[0] && pk->tail[1] && pk->tail[2];
+  // sets that consume identical scalar slices share one digit sort
   for (int k = 1; k < 3; k++)
     for (int j = 0; j < k; j++)
       if (pk->sort_src[k] == k && pk->lo[k] == pk->lo[j] && pk->hi[k] == pk->hi[j] && pk->tail[k] == pk->tail[j] &&
@@ -437,7 +435,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   size_t nterm[4] = {0, 0, 0, 0};
   for (int k = 0; k < 3; k++) {
     if (!pk->g[k]) continue;
-    if (pk->shared_w && k > 0) { nterm[k] = nterm[0]; continue; }
+    if (pk->sort_src[k] != k) { nterm[k] = nterm[pk->sort_src[k]]; continue; }   // shares the sort of an identical slice
     size_t cnt = pk->hi[k] - pk->lo[k];
     if (cnt) CU(cudaMemcpyAsync(sv[k], d_w + pk->lo[k], cnt * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     if (pk->tail[k]) CU(cudaMemcpyAsync(sv[k] + cnt, pk->rs.as<Fr>(), 3 * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
