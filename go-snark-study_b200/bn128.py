@@ -177,3 +177,21 @@ class G2(_Group):
          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
           4082367875863433681332203403145435568316851327593401208105741076214120093531),
          (1, 0))                                    # bn128/bn128.go:57-83
+
+
+class Bn128:
+    """bn128.Bn128 (bn128/bn128.go:11-36): the pairing entry point."""
+    G1 = G1()
+    G2 = G2()
+
+    def PairingBatch(self, p1s, p2s):
+        n = len(p1s)
+        a, b = _flatten_g1(p1s), _flatten_g2(p2s)
+        out = np.zeros(n * 48, dtype=np.uint64)
+        check(lib().b200_pairing_batch(ptr(a), ptr(b), n, ptr(out)))
+        v = limbs_to_ints(out)
+        return [tuple(tuple((v[12 * i + 6 * h + 2 * k], v[12 * i + 6 * h + 2 * k + 1]) for k in range(3)) for h in range(2))
+                for i in range(n)]
+
+    def Pairing(self, p1, p2):              # bn128.go:179-186 -> [2][3][2] tuple of ints
+        return self.PairingBatch([p1], [p2])[0]

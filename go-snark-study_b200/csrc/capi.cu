@@ -18,6 +18,7 @@
 #include "bucket_affine.cuh"
 #include "poly_host.cuh"
 #include "qap.cuh"
+#include "pairing.cuh"
 
 using namespace b200;
 
@@ -663,6 +664,115 @@ int zero_poly_host(size_t n, uint64_t* out) {   // coefficients of prod_{i=1..n}
   return check_err_flag<Fr>("zero_poly");
 }
 
+// ---- pairing / verification -------------------------------------------------------
+__device__ void pairing_from_jacobian(const Fq* g1, const Fq2* g2, F12& out) {
+  Jacobian<Fq> p{g1[0].to_mont(), g1[1].to_mont(), g1[2].to_mont()};
+  Jacobian<Fq2> q{g2[0].to_mont(), g2[1].to_mont(), g2[2].to_mont()};
+  Affine<Fq> pa = jac_to_affine(p);                      // preComputeG1: G1.Affine, infinity -> (0, 0)
+  Affine<Fq2> qa = jac_to_affine(q);                     // G2.Affine, infinity -> ((0,0),(1,0),(0,0)) (g2.go:25-27)
+  if (q.is_inf()) qa = Affine<Fq2>{Fq2::zero(), Fq2::one()};
+  F2::B px, py;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { px.l[i] = pa.x.l[i]; py.l[i] = pa.y.l[i]; }
+  out = pairing_affine(px, py, qa.x, qa.y);
+}
+__device__ void store_f12_std(const F12& f, Fq2* out) {
+  out[0] = f.a.a.from_mont(); out[1] = f.a.b.from_mont(); out[2] = f.a.c.from_mont();
+  out[3] = f.b.a.from_mont(); out[4] = f.b.b.from_mont(); out[5] = f.b.c.from_mont();
+}
+__global__ void __launch_bounds__(32) k_pairing_batch(const Fq* g1, const Fq2* g2, size_t n, Fq2* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F12 f;
+  pairing_from_jacobian(g1 + 3 * i, g2 + 3 * i, f);
+  store_f12_std(f, out + 6 * i);
+}
+// groth16.VerifyProof (groth16/groth16.go:281-305): e(A,B) == e(alpha,beta) * (e(icPubl,gamma) * e(C,delta)).
+// pts1: A, alpha1, icPubl, C ; pts2: B, beta2, gamma2, delta2 (Jacobian standard form).  Four threads, one pairing each.
+__global__ void __launch_bounds__(128) k_groth16_verify(const Fq* pts1, const Fq2* pts2, int* ok) {
+  __shared__ F12 e[4];
+  uint32_t t = threadIdx.x;
+  if ((t & 31) == 0) pairing_from_jacobian(pts1 + 3 * (t >> 5), pts2 + 3 * (t >> 5), e[t >> 5]);
+  __syncthreads();
+  if (t == 0) {
+    F12 rhs = f12_mul(e[1], f12_mul(e[2], e[3]));
+    const Fq2* a = &e[0].a.a;
+    const Fq2* b = &rhs.a.a;
+    bool eq = true;
+    for (int k = 0; k < 6; k++) eq = eq && (a[k] == b[k]);
+    *ok = eq ? 1 : 0;
+  }
+}
+// icPubl = IC[0] + sum publicSignals[i] * IC[i+1], reference order and formulas (groth16.go:283-286)
+__global__ void k_ic_publ(const Fq* ic, const Fr* sig, size_t npub, Fq* out) {
+  if (threadIdx.x | blockIdx.x) return;
+  Jacobian<Fq> acc{ic[0].to_mont(), ic[1].to_mont(), ic[2].to_mont()};
+  for (size_t i = 0; i < npub; i++) {
+    Jacobian<Fq> p{ic[3 * (i + 1)].to_mont(), ic[3 * (i + 1) + 1].to_mont(), ic[3 * (i + 1) + 2].to_mont()};
+    Fr s = sig[i];
+    Jacobian<Fq> q = Jacobian<Fq>::inf();
+    bool started = false;
+    for (int w = 7; w >= 0; w--)
+      for (int b = 31; b >= 0; b--) {
+        uint32_t bit = (s.l[w] >> b) & 1;
+        if (!started && !bit) continue;
+        started = true;
+        q = jac_double_ref(q);
+        if (bit) q = jac_add_ref(q, p);
+      }
+    acc = jac_add_ref(acc, q);
+  }
+  out[0] = acc.X.from_mont();
+  out[1] = acc.Y.from_mont();
+  out[2] = acc.Z.from_mont();
+}
+
+int pairing_batch_host(const uint64_t* g1, const uint64_t* g2, size_t n, uint64_t* out) {
+  if (!g1 || !g2 || !out) return fail(B200_EINVAL, "pairing_batch: null pointer");
+  if (n == 0) return B200_OK;
+  DevBuf d1, d2, dout;
+  CU(d1.alloc(n * 3 * sizeof(Fq)));
+  CU(d2.alloc(n * 3 * sizeof(Fq2)));
+  CU(dout.alloc(n * 6 * sizeof(Fq2)));
+  CU(cudaMemcpyAsync(d1.p, g1, n * 3 * sizeof(Fq), cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(d2.p, g2, n * 3 * sizeof(Fq2), cudaMemcpyHostToDevice, g_stream));
+  k_pairing_batch<<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, n * 6 * sizeof(Fq2), cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fq>("pairing_batch");
+}
+
+int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1, const uint64_t* beta2,
+                        const uint64_t* gamma2, const uint64_t* delta2, const uint64_t* pi_a, const uint64_t* pi_b,
+                        const uint64_t* pi_c, const uint64_t* pub, size_t npub, int* ok) {
+  if (!ic || !alpha1 || !beta2 || !gamma2 || !delta2 || !pi_a || !pi_b || !pi_c || !ok || (npub && !pub))
+    return fail(B200_EINVAL, "groth16_verify: null pointer");
+  if (n_ic < npub + 1) return fail(B200_EINVAL, "groth16_verify: len(IC) < len(publicSignals) + 1");
+  DevBuf dic, dsig, d1, d2, dok;
+  CU(dic.alloc(n_ic * 3 * sizeof(Fq)));
+  CU(dsig.alloc((npub ? npub : 1) * sizeof(Fr)));
+  CU(d1.alloc(4 * 3 * sizeof(Fq)));
+  CU(d2.alloc(4 * 3 * sizeof(Fq2)));
+  CU(dok.alloc(sizeof(int)));
+  cudaStream_t st = g_stream;
+  CU(cudaMemcpyAsync(dic.p, ic, n_ic * 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
+  if (npub) CU(cudaMemcpyAsync(dsig.p, pub, npub * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  Fq* p1 = d1.as<Fq>();
+  Fq2* p2 = d2.as<Fq2>();
+  CU(cudaMemcpyAsync(p1, pi_a, 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p1 + 3, alpha1, 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p1 + 9, pi_c, 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p2, pi_b, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p2 + 3, beta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p2 + 6, gamma2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(p2 + 9, delta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
+  k_ic_publ<<<1, 32, 0, st>>>(dic.as<Fq>(), dsig.as<Fr>(), npub, p1 + 6);
+  k_groth16_verify<<<1, 128, 0, st>>>(p1, p2, dok.as<int>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return check_err_flag<Fq>("groth16_verify");
+}
+
 template <class F>
 int group_op_host(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
   if (!p || !out || (op == 0 && !q)) return fail(B200_EINVAL, "group op: null pointer");
@@ -816,6 +926,13 @@ int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]) { B200_API_BODY(poly_eval_host(v, n, x, out)) }
 int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out) { B200_API_BODY(poly_eval_batch_host(polys, m, n, x, out)) }
 int b200_zero_poly(size_t n, uint64_t* out) { B200_API_BODY(zero_poly_host(n, out)) }
+int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out) { B200_API_BODY(pairing_batch_host(g1_jac, g2_jac, n, out)) }
+int b200_groth16_verify(const uint64_t* ic, size_t n_ic, const uint64_t alpha1[12], const uint64_t beta2[24],
+                        const uint64_t gamma2[24], const uint64_t delta2[24], const uint64_t pi_a[12],
+                        const uint64_t pi_b[24], const uint64_t pi_c[12], const uint64_t* public_signals, size_t n_public,
+                        int* ok) {
+  B200_API_BODY(groth16_verify_host(ic, n_ic, alpha1, beta2, gamma2, delta2, pi_a, pi_b, pi_c, public_signals, n_public, ok))
+}
 int b200_g1_add_batch(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(0, p, q, n, out)) }
 int b200_g1_double_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(1, p, nullptr, n, out)) }
 int b200_g1_neg_batch(const uint64_t* p, size_t n, uint64_t* out) { B200_API_BODY(group_op_host<Fq>(2, p, nullptr, n, out)) }

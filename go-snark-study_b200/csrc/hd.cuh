@@ -14,10 +14,12 @@
 #ifdef __CUDACC__
 #define HD __host__ __device__ __forceinline__
 #define HDC __host__ __device__ __forceinline__ constexpr
+#define HDN __host__ __device__ __noinline__  // big tower routines: one copy, called (pairing.cuh)
 #define DEV __device__ __forceinline__
 #else
 #define HD inline
 #define HDC inline constexpr
+#define HDN inline
 #define DEV inline
 #endif
 

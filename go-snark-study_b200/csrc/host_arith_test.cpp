@@ -2,7 +2,7 @@
 // (tests/test_host_arith.py loads this via ctypes and compares with the
 // oracle).  Not part of the product library.
 #include <cstring>
-#include "ec.cuh"
+#include "pairing.cuh"
 
 using namespace b200;
 
@@ -73,6 +73,15 @@ void t_fq2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   store(out, r.from_mont());
 }
 int t_geq(int field, const uint32_t* a) { return field == 0 ? load<Fq>(a).geq_modulus() : load<Fr>(a).geq_modulus(); }
+// pairing of AFFINE standard-form inputs: g1 = (x, y), g2 = (x.c0, x.c1, y.c0, y.c1); out = 12 field elements in
+// the reference's [2][3][2] order
+void t_pairing(const uint32_t* g1, const uint32_t* g2, uint32_t* out) {
+  F2::B px = load<F2::B>(g1).to_mont(), py = load<F2::B>(g1 + 8).to_mont();
+  F2 qx = load<F2>(g2).to_mont(), qy = load<F2>(g2 + 16).to_mont();
+  F12 f = pairing_affine(px, py, qx, qy);
+  const F2* parts[6] = {&f.a.a, &f.a.b, &f.a.c, &f.b.a, &f.b.b, &f.b.c};
+  for (int k = 0; k < 6; k++) store(out + 16 * k, parts[k]->from_mont());
+}
 void t_g1_xyzz(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { ec_ops<Fq>(op, a, b, out); }
 void t_g2_xyzz(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { ec_ops<Fq2>(op, a, b, out); }
 void t_g1_jac(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) { jac_ops<Fq>(op, a, b, out); }

@@ -141,3 +141,20 @@ def GenerateTrustedSetup(witnessLength, circuit, alphas, betas, gammas, toxic=No
           "G2": {"Beta": beta2, "Gamma": gamma2, "Delta": delta2, "BACGamma": p2[3:]}}
     vk = {"IC": IC, "G1": {"Alpha": alpha1}, "G2": {"Beta": beta2, "Gamma": gamma2, "Delta": delta2}}
     return {"Toxic": {"T": t, "Kalpha": ka, "Kbeta": kb, "Kgamma": kg, "Kdelta": kd}, "Pk": pk, "Vk": vk}
+
+
+def VerifyProof(vk, proof, publicSignals, debug=False):
+    """groth16.VerifyProof(vk, proof, publicSignals, debug) (groth16/groth16.go:281-305) on the GPU:
+    vk = {"IC", "G1": {"Alpha"}, "G2": {"Beta", "Gamma", "Delta"}}, proof = {"PiA", "PiB", "PiC"}."""
+    import ctypes
+    ic = _flatten_g1(vk["IC"])
+    pub = ints_to_limbs([reduce_scalar(x) for x in publicSignals]) if len(publicSignals) else np.zeros((1, 4), dtype=np.uint64)
+    ok = ctypes.c_int(0)
+    check(lib().b200_groth16_verify(ptr(ic), len(vk["IC"]), ptr(_flatten_g1([vk["G1"]["Alpha"]])),
+                                    ptr(_flatten_g2([vk["G2"]["Beta"]])), ptr(_flatten_g2([vk["G2"]["Gamma"]])),
+                                    ptr(_flatten_g2([vk["G2"]["Delta"]])), ptr(_flatten_g1([proof["PiA"]])),
+                                    ptr(_flatten_g2([proof["PiB"]])), ptr(_flatten_g1([proof["PiC"]])), ptr(pub),
+                                    len(publicSignals), ctypes.byref(ok)))
+    if debug:
+        print("✓ groth16 verification passed" if ok.value else "❌ groth16 verification not passed")
+    return bool(ok.value)

@@ -181,6 +181,18 @@ int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64
 /* out[0..n] = coefficients of prod_{i=1}^{n} (x - i): the "z pol" of groth16.go:122-132 / snark.go:221-232.   */
 int b200_zero_poly(size_t n, uint64_t* out);
 
+/* ---- verifier side ------------------------------------------------------------------ */
+/* out[i] = Bn128.Pairing(g1[i], g2[i]) (bn128/bn128.go:179-186): optimal-ate Miller loop + the reference's plain
+ * final exponentiation, one GPU thread per pairing; 48 uint64 per result in the reference's [2][3][2]*big.Int order.
+ * Bit-identical to the reference (golden: externalVerif/circom-test/verification_key.json vk_alfabeta_12).          */
+int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out);
+/* groth16.VerifyProof (groth16/groth16.go:281-305): *ok = 1 iff e(A,B) == e(alpha,beta) * (e(icPubl,gamma) * e(C,delta)),
+ * icPubl = IC[0] + sum publicSignals[i] * IC[i+1].  The four pairings run concurrently.                              */
+int b200_groth16_verify(const uint64_t* ic, size_t n_ic, const uint64_t alpha1[12], const uint64_t beta2[24],
+                        const uint64_t gamma2[24], const uint64_t delta2[24], const uint64_t pi_a[12],
+                        const uint64_t pi_b[24], const uint64_t pi_c[12], const uint64_t* public_signals, size_t n_public,
+                        int* ok);
+
 /* ---- dense QAP API upstream of GenerateProofs (small n; the prove path consumes px) ---- */
 /* PolynomialField.R1CSToQAP (r1csqap/r1csqap.go:161-188).  a, b, c: n x m row-major R1CS matrices (coefficients
  * reduced mod r).  alphas/betas/gammas: m x n (row i = coefficients of signal i's polynomial over the domain {1..n});

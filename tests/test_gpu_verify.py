@@ -1,0 +1,86 @@
+"""GPU: the verifier side — bn128.Pairing and groth16.VerifyProof on the device, bit-exact
+against the snarkjs golden (K8), the reference's own test literals (bn128/bn128_test.go:45-67) and the oracle."""
+import json
+import os
+import random
+
+import pytest
+
+from oracle import ref_py as o
+from test_gpu_setup_flow import A, B, C, W
+
+pytestmark = pytest.mark.gpu
+R = o.R
+G1, G2 = o.BN.G1, o.BN.G2
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from gosnark_b200 import _lib, bn128, groth16, r1csqap
+    _lib.init()
+    return bn128.Bn128(), groth16, r1csqap.PolynomialField()
+
+
+def _circom(golden_dir):
+    c = json.load(open(os.path.join(golden_dir, "circom_groth16.json")))
+    vk, pr = c["vk"], c["proof"]
+    i3 = lambda p: tuple(int(x) for x in p)
+    i32 = lambda p: tuple(tuple(int(x) for x in q) for q in p)
+    ovk = {"IC": [i3(p) for p in vk["IC"]], "G1": {"Alpha": i3(vk["vk_alfa_1"])},
+           "G2": {"Beta": i32(vk["vk_beta_2"]), "Gamma": i32(vk["vk_gamma_2"]), "Delta": i32(vk["vk_delta_2"])}}
+    proof = {"PiA": i3(pr["pi_a"]), "PiB": i32(pr["pi_b"]), "PiC": i3(pr["pi_c"])}
+    gold = tuple(tuple(tuple(int(x) for x in f2) for f2 in f6) for f6 in vk["vk_alfabeta_12"])
+    return ovk, proof, [int(x) for x in c["public"]], gold
+
+
+def test_k8_golden_pairing(mods, golden_dir):
+    """e(vk_alfa_1, vk_beta_2) == vk_alfabeta_12 (externalVerif/circom-test/verification_key.json:62-91)."""
+    bn, _, _ = mods
+    vk, _, _, gold = _circom(golden_dir)
+    assert bn.Pairing(vk["G1"]["Alpha"], vk["G2"]["Beta"]) == gold
+
+
+def test_reference_pairing_literal_and_bilinearity(mods):
+    """bn128_test.go:45-67: e(25 G1, 30 G2) == e(30 G1, 25 G2), with the first coefficient the test prints."""
+    bn, _, _ = mods
+    p1, q1 = G1.mul_scalar(G1.G, 25), G2.mul_scalar(G2.G, 30)      # Jacobian, Z != 1: the kernel normalises like preComputeG1
+    p2, q2 = G1.mul_scalar(G1.G, 30), G2.mul_scalar(G2.G, 25)
+    e1, e2 = bn.PairingBatch([p1, p2], [q1, q2])
+    assert e1 == e2 == o.BN.pairing(p1, q1)
+    assert e1[0][0][0] == 8016119724813186033542830391460394070015218389456422587891475873290878009957
+
+
+def test_pairing_batch_vs_oracle_and_infinity(mods):
+    bn, _, _ = mods
+    rng = random.Random(5)
+    ps = [G1.mul_scalar(G1.G, rng.randrange(1, R)) for _ in range(2)] + [G1.zero3(), G1.G]
+    qs = [G2.mul_scalar(G2.G, rng.randrange(1, R)) for _ in range(2)] + [G2.G, G2.zero3()]
+    got = bn.PairingBatch(ps, qs)
+    for p, q, e in zip(ps, qs, got):
+        assert e == o.BN.pairing(p, q)
+    assert bn.PairingBatch([], []) == []
+
+
+def test_verify_circom_proof(mods, golden_dir):
+    """externalVerif/circomVerifier_test.go:9-13: the snarkjs proof verifies; a wrong public input does not."""
+    _, groth16, _ = mods
+    vk, proof, public, _ = _circom(golden_dir)
+    assert groth16.VerifyProof(vk, proof, public, True)
+    assert not groth16.VerifyProof(vk, proof, [public[0] + 1], True)
+    bad = dict(proof, PiC=G1.double(proof["PiC"]))
+    assert not groth16.VerifyProof(vk, bad, public)
+
+
+def test_minimal_flow_all_gpu(mods):
+    """TestGroth16MinimalFlow (groth16/groth16_test.go:16-107) with every step on the GPU, verify included."""
+    _, groth16, pf = mods
+    circuit = {"NVars": 8, "NPublic": 1}
+    alphas, betas, gammas, _ = pf.R1CSToQAP(A, B, C)
+    _, _, _, px = pf.CombinePolynomials(W, alphas, betas, gammas)
+    setup = groth16.GenerateTrustedSetup(len(W), circuit, alphas, betas, gammas)
+    proof = groth16.GenerateProofs(circuit, setup["Pk"], W, px)
+    assert groth16.VerifyProof(setup["Vk"], proof, [35])                 # :100
+    assert not groth16.VerifyProof(setup["Vk"], proof, [34])             # :106
+    assert o.groth16_verify(setup["Vk"], proof, [35])
+    with pytest.raises(Exception):
+        groth16.VerifyProof(setup["Vk"], proof, [35, 1, 2])              # more signals than IC entries
