@@ -1,6 +1,7 @@
 """File-compatible stand-in for the prove commands of the reference's CLI (cli/main.go):
 
     python -m gosnark_b200.cli groth16 genproofs      # cli/main.go:455-518
+    python -m gosnark_b200.cli groth16 verify         # cli/main.go:520-549
     python -m gosnark_b200.cli genproofs              # cli/main.go:303-366   (Pinocchio)
 
 Reads the files the Go CLI writes/reads in the current directory (compiledcircuit.json,
@@ -107,15 +108,29 @@ def pinocchio_genproofs():
     print("Proofs data written to  proofs.json")
 
 
+def groth16_verify():
+    """cli/main.go:520-549 — the proof of proofs.json against trustedsetup.json's Vk and publicInputs.json, on the GPU."""
+    proof, setup, public = _load("proofs.json"), _load("trustedsetup.json"), _load("publicInputs.json")
+    vk = setup["Vk"]
+    vkd = {"IC": [_t3(p) for p in vk["IC"]], "G1": {"Alpha": _t3(vk["G1"]["Alpha"])},
+           "G2": {k: _g2(vk["G2"][k]) for k in ("Beta", "Gamma", "Delta")}}
+    pr = {"PiA": _t3(proof["PiA"]), "PiB": _g2(proof["PiB"]), "PiC": _t3(proof["PiC"])}
+    verified = groth16.VerifyProof(vkd, pr, [int(x) for x in public], True)
+    print("Proofs verified" if verified else "ERROR: proofs not verified")
+    return verified
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     _lib.init()
     if argv[:2] == ["groth16", "genproofs"]:
         groth16_genproofs()
+    elif argv[:2] == ["groth16", "verify"]:
+        groth16_verify()
     elif argv[:1] == ["genproofs"]:
         pinocchio_genproofs()
     else:
-        print("usage: python -m gosnark_b200.cli [groth16] genproofs", file=sys.stderr)
+        print("usage: python -m gosnark_b200.cli groth16 genproofs|verify  |  genproofs", file=sys.stderr)
         return 2
     return 0
 

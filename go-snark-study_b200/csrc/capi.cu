@@ -175,6 +175,7 @@ int check_err_flag(const char* what) {
   CU(cudaStreamSynchronize(g_stream));
   if (h) {
     CU(cudaMemset(g_d_err, 0, sizeof(int)));
+    if (h & 8) return fail(B200_EINVAL, "%s: q1[2] != Fq2.One() (G2 point at infinity; the reference panics, bn128.go:238-241)", what);
     if (h & 4) return fail(B200_EDIVZERO, "%s: divisor has a zero leading coefficient", what);
     return fail(B200_ERANGE, "%s: %s", what, (h & 1) ? "point coordinate >= q" : "scalar / coefficient >= r");
   }
@@ -665,12 +666,18 @@ int zero_poly_host(size_t n, uint64_t* out) {   // coefficients of prod_{i=1..n}
 }
 
 // ---- pairing / verification -------------------------------------------------------
-__device__ void pairing_from_jacobian(const Fq* g1, const Fq2* g2, F12& out) {
+__device__ void pairing_from_jacobian(const Fq* g1, const Fq2* g2, F12& out, int* err) {
+  bool bad = false;
+  for (int k = 0; k < 3; k++) bad = bad || g1[k].geq_modulus() || g2[k].c0.geq_modulus() || g2[k].c1.geq_modulus();
   Jacobian<Fq> p{g1[0].to_mont(), g1[1].to_mont(), g1[2].to_mont()};
   Jacobian<Fq2> q{g2[0].to_mont(), g2[1].to_mont(), g2[2].to_mont()};
+  if (bad || q.is_inf()) {  // G2 infinity: preComputeG2 panics "q1[2] != Fq2.One()" (bn128.go:238-241)
+    atomicOr(err, bad ? 1 : 8);
+    out = F12::one();
+    return;
+  }
   Affine<Fq> pa = jac_to_affine(p);                      // preComputeG1: G1.Affine, infinity -> (0, 0)
-  Affine<Fq2> qa = jac_to_affine(q);                     // G2.Affine, infinity -> ((0,0),(1,0),(0,0)) (g2.go:25-27)
-  if (q.is_inf()) qa = Affine<Fq2>{Fq2::zero(), Fq2::one()};
+  Affine<Fq2> qa = jac_to_affine(q);
   F2::B px, py;
 #pragma unroll
   for (int i = 0; i < 8; i++) { px.l[i] = pa.x.l[i]; py.l[i] = pa.y.l[i]; }
@@ -680,19 +687,19 @@ __device__ void store_f12_std(const F12& f, Fq2* out) {
   out[0] = f.a.a.from_mont(); out[1] = f.a.b.from_mont(); out[2] = f.a.c.from_mont();
   out[3] = f.b.a.from_mont(); out[4] = f.b.b.from_mont(); out[5] = f.b.c.from_mont();
 }
-__global__ void __launch_bounds__(32) k_pairing_batch(const Fq* g1, const Fq2* g2, size_t n, Fq2* out) {
+__global__ void __launch_bounds__(32) k_pairing_batch(const Fq* g1, const Fq2* g2, size_t n, Fq2* out, int* err) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   F12 f;
-  pairing_from_jacobian(g1 + 3 * i, g2 + 3 * i, f);
+  pairing_from_jacobian(g1 + 3 * i, g2 + 3 * i, f, err);
   store_f12_std(f, out + 6 * i);
 }
 // groth16.VerifyProof (groth16/groth16.go:281-305): e(A,B) == e(alpha,beta) * (e(icPubl,gamma) * e(C,delta)).
 // pts1: A, alpha1, icPubl, C ; pts2: B, beta2, gamma2, delta2 (Jacobian standard form).  Four threads, one pairing each.
-__global__ void __launch_bounds__(128) k_groth16_verify(const Fq* pts1, const Fq2* pts2, int* ok) {
+__global__ void __launch_bounds__(128) k_groth16_verify(const Fq* pts1, const Fq2* pts2, int* ok, int* err) {
   __shared__ F12 e[4];
   uint32_t t = threadIdx.x;
-  if ((t & 31) == 0) pairing_from_jacobian(pts1 + 3 * (t >> 5), pts2 + 3 * (t >> 5), e[t >> 5]);
+  if ((t & 31) == 0) pairing_from_jacobian(pts1 + 3 * (t >> 5), pts2 + 3 * (t >> 5), e[t >> 5], err);
   __syncthreads();
   if (t == 0) {
     F12 rhs = f12_mul(e[1], f12_mul(e[2], e[3]));
@@ -704,8 +711,12 @@ __global__ void __launch_bounds__(128) k_groth16_verify(const Fq* pts1, const Fq
   }
 }
 // icPubl = IC[0] + sum publicSignals[i] * IC[i+1], reference order and formulas (groth16.go:283-286)
-__global__ void k_ic_publ(const Fq* ic, const Fr* sig, size_t npub, Fq* out) {
+__global__ void k_ic_publ(const Fq* ic, const Fr* sig, size_t npub, Fq* out, int* err) {
   if (threadIdx.x | blockIdx.x) return;
+  for (size_t i = 0; i < 3 * (npub + 1); i++)
+    if (ic[i].geq_modulus()) atomicOr(err, 1);
+  for (size_t i = 0; i < npub; i++)
+    if (sig[i].geq_modulus()) atomicOr(err, 2);
   Jacobian<Fq> acc{ic[0].to_mont(), ic[1].to_mont(), ic[2].to_mont()};
   for (size_t i = 0; i < npub; i++) {
     Jacobian<Fq> p{ic[3 * (i + 1)].to_mont(), ic[3 * (i + 1) + 1].to_mont(), ic[3 * (i + 1) + 2].to_mont()};
@@ -736,7 +747,7 @@ int pairing_batch_host(const uint64_t* g1, const uint64_t* g2, size_t n, uint64_
   CU(dout.alloc(n * 6 * sizeof(Fq2)));
   CU(cudaMemcpyAsync(d1.p, g1, n * 3 * sizeof(Fq), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(d2.p, g2, n * 3 * sizeof(Fq2), cudaMemcpyHostToDevice, g_stream));
-  k_pairing_batch<<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>());
+  k_pairing_batch<<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>(), g_d_err);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, dout.p, n * 6 * sizeof(Fq2), cudaMemcpyDeviceToHost, g_stream));
   return check_err_flag<Fq>("pairing_batch");
@@ -766,8 +777,8 @@ int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1,
   CU(cudaMemcpyAsync(p2 + 3, beta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(p2 + 6, gamma2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(p2 + 9, delta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
-  k_ic_publ<<<1, 32, 0, st>>>(dic.as<Fq>(), dsig.as<Fr>(), npub, p1 + 6);
-  k_groth16_verify<<<1, 128, 0, st>>>(p1, p2, dok.as<int>());
+  k_ic_publ<<<1, 32, 0, st>>>(dic.as<Fq>(), dsig.as<Fr>(), npub, p1 + 6, g_d_err);
+  k_groth16_verify<<<1, 128, 0, st>>>(p1, p2, dok.as<int>(), g_d_err);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   return check_err_flag<Fq>("groth16_verify");

@@ -138,3 +138,24 @@ func PolyMul(a, b []*big.Int) ([]*big.Int, error) {
 	}
 	return res, nil
 }
+
+// Fq12FromLimbs unpacks b200_pairing_batch's 48 words into the reference's [2][3][2]*big.Int (fields/fq12.go).
+func Fq12FromLimbs(w []uint64) (r [2][3][2]*big.Int) {
+	for h := 0; h < 2; h++ {
+		for k := 0; k < 3; k++ {
+			for c := 0; c < 2; c++ {
+				o := 4 * (6*h + 2*k + c)
+				r[h][k][c] = fromLimbs(w[o : o+4])
+			}
+		}
+	}
+	return
+}
+
+// Pairing backs bn128.Bn128.Pairing (bn128/bn128.go:179-186).
+func Pairing(p1 [3]*big.Int, p2 [3][2]*big.Int) ([2][3][2]*big.Int, error) {
+	out := make([]uint64, 48)
+	g1, g2 := FlatG1([][3]*big.Int{p1}), FlatG2([][3][2]*big.Int{p2})
+	err := check(C.b200_pairing_batch(u64(g1), u64(g2), 1, u64(out)))
+	return Fq12FromLimbs(out), err
+}

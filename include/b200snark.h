@@ -184,7 +184,9 @@ int b200_zero_poly(size_t n, uint64_t* out);
 /* ---- verifier side ------------------------------------------------------------------ */
 /* out[i] = Bn128.Pairing(g1[i], g2[i]) (bn128/bn128.go:179-186): optimal-ate Miller loop + the reference's plain
  * final exponentiation, one GPU thread per pairing; 48 uint64 per result in the reference's [2][3][2]*big.Int order.
- * Bit-identical to the reference (golden: externalVerif/circom-test/verification_key.json vk_alfabeta_12).          */
+ * Bit-identical to the reference (golden: externalVerif/circom-test/verification_key.json vk_alfabeta_12).
+ * A G2 point at infinity returns B200_EINVAL where the reference panics "q1[2] != Fq2.One()" (bn128.go:238-241);
+ * a G1 point at infinity is processed like the reference does (Affine -> (0,0)).                                    */
 int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out);
 /* groth16.VerifyProof (groth16/groth16.go:281-305): *ok = 1 iff e(A,B) == e(alpha,beta) * (e(icPubl,gamma) * e(C,delta)),
  * icPubl = IC[0] + sum publicSignals[i] * IC[i+1].  The four pairings run concurrently.                              */

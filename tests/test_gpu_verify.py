@@ -53,12 +53,16 @@ def test_reference_pairing_literal_and_bilinearity(mods):
 def test_pairing_batch_vs_oracle_and_infinity(mods):
     bn, _, _ = mods
     rng = random.Random(5)
-    ps = [G1.mul_scalar(G1.G, rng.randrange(1, R)) for _ in range(2)] + [G1.zero3(), G1.G]
-    qs = [G2.mul_scalar(G2.G, rng.randrange(1, R)) for _ in range(2)] + [G2.G, G2.zero3()]
+    ps = [G1.mul_scalar(G1.G, rng.randrange(1, R)) for _ in range(2)] + [G1.zero3()]
+    qs = [G2.mul_scalar(G2.G, rng.randrange(1, R)) for _ in range(2)] + [G2.G]
     got = bn.PairingBatch(ps, qs)
     for p, q, e in zip(ps, qs, got):
         assert e == o.BN.pairing(p, q)
     assert bn.PairingBatch([], []) == []
+    with pytest.raises(Exception, match="Fq2.One"):           # the reference panics (bn128.go:238-241)
+        bn.Pairing(G1.G, G2.zero3())
+    with pytest.raises(Exception, match=">= q"):
+        bn.Pairing((o.Q, 2, 1), G2.G)
 
 
 def test_verify_circom_proof(mods, golden_dir):
