@@ -396,6 +396,12 @@ def main():
                             "share_of_serial_step": (prof_x[3] / max(prof_x[4], 1)) / ms_serial if ms_serial else None,
                             "achieved": 160.0 * (prof_x[5] / max(prof_x[4], 1)) / (prof_x[3] / max(prof_x[4], 1) * 1e-3) / 1e9
                             if prof_x[3] > 0 else None},
+                     "alu": (lambda macs: {"achieved": macs, "peak": 9.3e12, "unit": "32x32+64 multiply-accumulates/s",
+                                           "frac": macs / 9.3e12,
+                                           "note": "6 Montgomery multiplies per batched-affine bucket add x 136 IMAD.WIDE-equivalent "
+                                                   "slots each (SASS of fp_mul_outlined); peak = IMAD.WIDE carry-chain rate measured "
+                                                   "by tools/micro/imad_bench.cu on this GPU class (29.6 / clk / SM)"})(
+                         6 * 136 * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3)) if g1_ms > 0 else None,
                      "overlapped": {"g1_avg_ms": prof[0] / max(prof[1], 1), "g2_avg_ms": prof[3] / max(prof[4], 1)}},
         "algorithmic_bytes_per_proof": syn.algorithmic_bytes(),
         "g1_msm_2p20": msm_extra,

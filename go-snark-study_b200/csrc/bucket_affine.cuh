@@ -96,6 +96,94 @@ __device__ __forceinline__ int aff_denominator(const Affine<F>& P, const Affine<
   return 0;
 }
 
+// x-coordinate only, for the forward pass (a G2 point is a full 128-byte line: its x is half of it)
+template <class P, bool I>
+__device__ __forceinline__ Fp<P, I> ld_x_gather(const Affine<Fp<P, I>>* p) { Fp<P, I> r; ld256_g64(&p->x, r.l); return r; }
+template <bool I>
+__device__ __forceinline__ Fq2T<I> ld_x_gather(const Affine<Fq2T<I>>* p) { return ld_fe(&p->x); }
+
+// Denominator of pair `p` for the forward pass.  The generic case needs only the two x-coordinates, so only those
+// are fetched (half the registers and load instructions of the full operands -> the forward kernel runs at twice the
+// occupancy, which is what hides its dependent index -> point gathers); whenever an x is zero (infinity) or the x's
+// coincide (doubling / P = -Q) the full operands decide, exactly as in the backward pass.
+template <class F>
+__device__ __forceinline__ bool aff_forward_denominator(const AffineRound<F>& a, uint32_t p, uint32_t npairs, F& d) {
+  if (p >= npairs) return false;
+  uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
+  const Affine<F>*pp, *qp;
+  if (a.round == 1) {
+    uint32_t s = a.slice_start[slice], e = a.slice_end[slice];
+    uint32_t i0 = s + 2 * j, i1 = i0 + 1;
+    if (i1 >= e) {  // at most one live operand: nothing to invert
+      d = F::one();
+      return true;
+    }
+    pp = &a.table[a.entries[i0] >> 1];
+    qp = &a.table[a.entries[i1] >> 1];
+  } else {
+    size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
+    pp = &a.prev[base];
+    qp = &a.prev[base + 1];
+  }
+  F x1 = a.round == 1 ? ld_x_gather(pp) : ld_fe(&pp->x);
+  F x2 = a.round == 1 ? ld_x_gather(qp) : ld_fe(&qp->x);
+  F dx = x2 - x1;
+  if (x1.is_zero() || x2.is_zero() || dx.is_zero()) {
+    Affine<F> P, Q;
+    aff_operands(a, p, npairs, P, Q);
+    aff_denominator(P, Q, d);
+  } else {
+    d = dx;
+  }
+  return true;
+}
+
+// ---- L2 prefetch of the next iteration's operands -------------------------------------------------
+// A thread walks its T pairs one after another and every pair starts with a dependent chain
+// slice -> entry id -> 64/128-byte point gather from a >= 1 GB table.  The warp cannot run ahead of its own
+// multiply chain, so the gather latency sits in front of every iteration.  Registers are the scarce resource
+// (a register-staged software pipeline was measured slower), but `prefetch.global.L2` needs none: the entry ids of
+// iteration k-2 are loaded during iteration k (two registers), the points of iteration k-1 are prefetched during
+// iteration k, and by the time the warp gets there its gathers are L2 hits.
+struct PairIdx { uint32_t e0, e1; };
+constexpr uint32_t kNoEntry = 0xffffffffu;
+
+template <class F>
+__device__ __forceinline__ PairIdx aff_pair_idx(const AffineRound<F>& a, uint32_t p, uint32_t npairs) {
+  PairIdx r{kNoEntry, kNoEntry};
+  if (a.round == 1 && p < npairs) {
+    uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
+    uint32_t s = a.slice_start[slice], e = a.slice_end[slice];
+    uint32_t i0 = s + 2 * j, i1 = i0 + 1;
+    if (i0 < e) r.e0 = a.entries[i0];
+    if (i1 < e) r.e1 = a.entries[i1];
+  }
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int BYTES>
+__device__ __forceinline__ void prefetch_span(const void* p) {
+#pragma unroll
+  for (int o = 0; o < BYTES; o += 32) prefetch_l2(reinterpret_cast<const char*>(p) + o);
+}
+// XONLY: the forward pass reads x-coordinates only (and nothing when the pair has a single live operand)
+template <class F, bool XONLY>
+__device__ __forceinline__ void aff_prefetch(const AffineRound<F>& a, uint32_t p, uint32_t npairs, PairIdx ix) {
+  if (p >= npairs) return;
+  constexpr int kBytes = XONLY ? (int)sizeof(F) : (int)sizeof(Affine<F>);
+  if (a.round == 1) {
+    if (XONLY && ix.e1 == kNoEntry) return;
+    if (ix.e0 != kNoEntry) prefetch_span<kBytes>(&a.table[ix.e0 >> 1]);
+    if (ix.e1 != kNoEntry) prefetch_span<kBytes>(&a.table[ix.e1 >> 1]);
+  } else {
+    uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
+    size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
+    prefetch_span<kBytes>(&a.prev[base]);
+    prefetch_span<kBytes>(&a.prev[base + 1]);
+  }
+  if (!XONLY) prefetch_span<(int)sizeof(F)>(&a.pre[p]);
+}
+
 template <class F>
 __device__ __forceinline__ F shfl_up_fe(const F& v, int delta) {
   F r;
@@ -124,7 +212,7 @@ __device__ __forceinline__ F shfl_idx_fe(const F& v, int lane) {
   return r;
 }
 
-template <class F, int kAffT, int MINB = 1>
+template <class F, int kAffT, int MINB = 1, bool PF = false>
 __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_forward(AffineRound<F> a) {
   __shared__ F wtot[kAffBlock / 32];
   const uint32_t nslices = *a.nslices_ptr;
@@ -136,12 +224,16 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_forward(AffineRound<
   }
   const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
   F run = F::one();
+  PairIdx ix_next{kNoEntry, kNoEntry};
+  if (PF) ix_next = aff_pair_idx(a, block_base + kAffBlock + t, npairs);
   for (int k = 0; k < kAffT; k++) {
     uint32_t p = block_base + k * kAffBlock + t;  // block-interleaved: coalesced across the warp
-    Affine<F> P, Q;
+    if (PF) {
+      if (k + 1 < kAffT) aff_prefetch<F, true>(a, p + kAffBlock, npairs, ix_next);
+      if (k + 2 < kAffT) ix_next = aff_pair_idx(a, p + 2 * kAffBlock, npairs);
+    }
     F d;
-    if (aff_operands(a, p, npairs, P, Q)) {
-      aff_denominator(P, Q, d);
+    if (aff_forward_denominator(a, p, npairs, d)) {
       a.pre[p] = run;
       run = run * d;
     }
@@ -182,7 +274,7 @@ __global__ void k_affine_invert(F* btot, uint32_t nblocks_live) {
   btot[i] = btot[i].inverse();
 }
 
-template <class F, int kAffT, int MINB = 1>
+template <class F, int kAffT, int MINB = 1, bool PF = false>
 __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound<F> a) {
   const uint32_t nslices = *a.nslices_ptr;
   const uint32_t npairs = nslices << a.q_log;
@@ -191,8 +283,14 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound
   const uint32_t t = threadIdx.x;
   uint32_t gthread = blockIdx.x * kAffBlock + t;
   F inv_run = a.btot[blockIdx.x] * a.others[gthread];  // 1 / (product of this thread's denominators)
+  PairIdx ix_next{kNoEntry, kNoEntry};
+  if (PF) ix_next = aff_pair_idx(a, block_base + (kAffT - 2) * kAffBlock + t, npairs);
   for (int k = kAffT - 1; k >= 0; k--) {
     uint32_t p = block_base + k * kAffBlock + t;
+    if (PF) {
+      if (k >= 1) aff_prefetch<F, false>(a, p - kAffBlock, npairs, ix_next);
+      if (k >= 2) ix_next = aff_pair_idx(a, p - 2 * kAffBlock, npairs);
+    }
     Affine<F> P, Q;
     if (!aff_operands(a, p, npairs, P, Q)) continue;
     F d;

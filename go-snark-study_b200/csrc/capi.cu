@@ -405,15 +405,28 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       static const int t_env = getenv("B200_AFF_T") ? atoi(getenv("B200_AFF_T")) : 32;  // tuning knob
       const unsigned T = t_env == 16 ? 16 : 32;
       unsigned nb = (unsigned)((npairs_max + kAffBlock * T - 1) / (kAffBlock * T));
-      static const int mb_env = getenv("B200_AFF_MINB") ? atoi(getenv("B200_AFF_MINB")) : 4;  // tuning knob (4: -3 % at 2^20)
+      // CTAs/SM bounds (register caps) of the backward / forward kernels; G2 variants above 4 spill (ptxas -v)
+      static const int mb_g1 = getenv("B200_AFF_MINB") ? atoi(getenv("B200_AFF_MINB")) : 5;          // 20.8 -> 19.6 ms / 2^20 proof
+      static const int mf_g1 = getenv("B200_AFF_MINB_FWD") ? atoi(getenv("B200_AFF_MINB_FWD")) : 8;  // together with the x-only forward
+      static const int mb_g2 = getenv("B200_AFF_MINB_G2") ? atoi(getenv("B200_AFF_MINB_G2")) : 4;
+      static const int mf_g2 = getenv("B200_AFF_MINB_FWD_G2") ? atoi(getenv("B200_AFF_MINB_FWD_G2")) : 4;
+      const int mb_env = sizeof(F) == 32 ? mb_g1 : mb_g2, mf_env = sizeof(F) == 32 ? mf_g1 : mf_g2;
+      static const int pf_env = getenv("B200_AFF_PF") ? atoi(getenv("B200_AFF_PF")) : 0;  // bit 0: forward, bit 1: backward L2 prefetch
       if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (mb_env >= 3) k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
-      else k_affine_forward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (pf_env & 1) {
+        if (mf_env >= 8) k_affine_forward<F, 32, 8, true><<<nb, kAffBlock, 0, st>>>(ar);
+        else k_affine_forward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
+      } else if (mf_env >= 8) k_affine_forward<F, 32, 8><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (mf_env >= 4) k_affine_forward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
+      else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       k_affine_invert<F><<<nblocks(nb, 64), 64, 0, st>>>(ar.btot, nb);
       if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (pf_env & 2) {
+        if (mb_env >= 5) k_affine_backward<F, 32, 5, true><<<nb, kAffBlock, 0, st>>>(ar);
+        else k_affine_backward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
+      } else if (mb_env >= 5) k_affine_backward<F, 32, 5><<<nb, kAffBlock, 0, st>>>(ar);
       else if (mb_env >= 4) k_affine_backward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (mb_env >= 3) k_affine_backward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
-      else k_affine_backward<F, 32><<<nb, kAffBlock, 0, st>>>(ar);
+      else k_affine_backward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       prev = ar.out;
       g_launches += 3;
     }

@@ -5,14 +5,15 @@ import csv
 import sys
 
 path = sys.argv[1]
-marker = sys.argv[2] if len(sys.argv) > 2 else "k_groth16_tails"
+marker = sys.argv[2] if len(sys.argv) > 2 else "k_groth16_combine"
 with open(path) as f:
     lines = [l for l in f if l.startswith('"')]
 rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
-# last step = from the last occurrence of the marker kernel to the end
-starts = [i for i, n in enumerate(names) if marker in n]
-lo = starts[-1] if starts else 0
+# one prove step = the launches between the last two occurrences of the marker kernel (the step's final launch)
+ends = [i for i, n in enumerate(names) if marker in n]
+lo = ends[-2] + 1 if len(ends) >= 2 else 0
+rows = rows[:ends[-1] + 1] if ends else rows
 agg = collections.OrderedDict()
 tot = 0.0
 for r in rows[lo:]:
