@@ -16,8 +16,8 @@
 //                      stores the running prefix product, and a block-wide
 //                      shuffle/shared-memory scan gives every thread the product
 //                      of all OTHER threads' totals; the block total goes to HBM
-//   k_affine_invert    one Fermat inversion per block total (a few thousand per
-//                      round — negligible work, and it never stalls a worker)
+//   k_affine_invert    one inversion per block total (a few thousand per round —
+//                      negligible work, pure latency: binary Euclid, a warp each)
 //   k_affine_backward  thread t derives 1/total_t, walks its pairs backwards
 //                      peeling 1/d off the running inverse, and writes the sums
 // After R rounds every slice is one affine point; k_merge_slices_affine folds the
@@ -267,11 +267,13 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_forward(AffineRound<
   if (t == 0) a.btot[blockIdx.x] = other_warps * wtot[0];
 }
 
+// One warp per block total, lane 0 working: the binary-Euclid inversion has data-dependent control flow, and this
+// launch is pure latency (a few thousand inversions between two machine-filling passes) -- 182 us with a^(p-2).
 template <class F>
-__global__ void k_affine_invert(F* btot, uint32_t nblocks_live) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nblocks_live) return;
-  btot[i] = btot[i].inverse();
+__global__ void __launch_bounds__(128) k_affine_invert(F* btot, uint32_t nblocks_live) {
+  uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if ((threadIdx.x & 31u) || i >= nblocks_live) return;
+  btot[i] = btot[i].inverse_vartime();
 }
 
 template <class F, int kAffT, int MINB = 1, bool PF = false>

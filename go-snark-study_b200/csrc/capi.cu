@@ -182,12 +182,12 @@ int check_err_flag(const char* what) {
   return B200_OK;
 }
 
-// in_pipeline: the base set belongs to a proving key, whose MSMs run concurrently on several streams —
-// there the batched-affine accumulation wins (its per-round inversion latency is covered by the other
-// streams: 21.5 vs 26.3 ms per 2^20 proof).  A stand-alone MSM has nothing to overlap with and is faster
-// with the XYZZ kernel (4.7 vs 5.3 ms at 2^20), so it keeps that unless B200_ACC_MODE=affine forces it.
+// prefer_affine: batched-affine bucket accumulation (6 multiplies per add instead of 10) whenever the buckets are
+// populated enough to amortise its per-round launches; since the per-round inversion became a binary-Euclid warp
+// (182 -> ~45 us) it also wins for a stand-alone MSM (2^20: G1 4.40 vs 4.46 ms, G2 9.26 vs 11.80 ms XYZZ).  A proving-key
+// shard that leaves a rank only a small MSM passes false (prove_host.cuh); B200_ACC_MODE=xyzz|affine forces either.
 template <class F>
-int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_ptr<Bases>& out_b, bool in_pipeline = false) {
+int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_ptr<Bases>& out_b, bool prefer_affine = true) {
   if (!pts || n == 0 || n > (1u << 26)) return fail(B200_EINVAL, "bases_load: bad arguments");
   if (c == 0) c = pick_window_bits(n);
   if (c < 2 || c > 24) return fail(B200_EINVAL, "window_bits must be in [2,24]");
@@ -209,7 +209,7 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
     // accumulation mode: batched affine (default) or XYZZ mixed adds (B200_ACC_MODE=xyzz)
     static const bool force_xyzz = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "xyzz");
     static const bool force_affine = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "affine");
-    const bool xyzz_mode = force_xyzz || (!in_pipeline && !force_affine);
+    const bool xyzz_mode = force_xyzz || (!prefer_affine && !force_affine);
     uint32_t S = 0;
     uint64_t mean = ((uint64_t)sh.nwin * n) / sh.nbuckets;
     static const int min_mean = getenv("B200_AFF_MIN_MEAN") ? atoi(getenv("B200_AFF_MIN_MEAN")) : 96;  // tuning knob
@@ -419,7 +419,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       } else if (mf_env >= 8) k_affine_forward<F, 32, 8><<<nb, kAffBlock, 0, st>>>(ar);
       else if (mf_env >= 4) k_affine_forward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
       else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
-      k_affine_invert<F><<<nblocks(nb, 64), 64, 0, st>>>(ar.btot, nb);
+      k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
       if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 2) {
         if (mb_env >= 5) k_affine_backward<F, 32, 5, true><<<nb, kAffBlock, 0, st>>>(ar);

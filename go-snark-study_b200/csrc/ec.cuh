@@ -138,11 +138,13 @@ HD void xyzz_add(XYZZ<F>& a, const XYZZ<F>& b) {
   a.ZZZ = a.ZZZ * b.ZZZ * PPP;
 }
 
-template <class F>
+// VT: binary-Euclid inversion (single-thread tails, where the inversion latency is the whole kernel)
+template <class F, bool VT = false>
 HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
   if (p.is_inf()) return Affine<F>::inf();
   // 1/ZZZ = i ; 1/ZZ = (ZZZ * i)^2 ... cheaper: invert ZZ*ZZZ once
-  F i = (p.ZZ * p.ZZZ).inverse();
+  F zp = p.ZZ * p.ZZZ;
+  F i = VT ? zp.inverse_vartime() : zp.inverse();
   F izz = i * p.ZZZ;
   F izzz = i * p.ZZ;
   return Affine<F>{p.X * izz, p.Y * izzz};

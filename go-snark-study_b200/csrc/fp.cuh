@@ -28,6 +28,8 @@ template <class P>
 __device__ __noinline__ Fp<P, false> fp_mul_outlined(Fp<P, false> a, Fp<P, false> b);
 template <class P, bool INL>
 __device__ __noinline__ Fp<P, INL> fp_inverse_outlined(Fp<P, INL> a);
+template <class P, bool INL>
+__device__ __noinline__ Fp<P, INL> fp_inverse_vartime_outlined(Fp<P, INL> a);
 #endif
 
 template <class P, bool INL = false>
@@ -308,6 +310,79 @@ struct alignas(32) Fp {
     return res;
   }
 
+  // Same value by the binary extended Euclid (right-shift) algorithm on the Montgomery representative:
+  // ~250 subtract steps and ~500 halvings of 8-limb integers instead of ~380 dependent Montgomery products
+  // -- a ~5x shorter latency chain, for the places where ONE inversion per warp sits on a critical path
+  // (k_affine_invert between the forward and backward pass of every round, the final Jacobian -> affine).
+  // Data-dependent control flow: give it a warp of its own (one active lane), or accept the divergence.
+  // The inputs of those call sites are public group elements; nothing secret-dependent is timed here.
+  HD Fp inverse_vartime() const {
+#ifdef __CUDA_ARCH__
+    return fp_inverse_vartime_outlined<P, INL>(*this);
+#else
+    return inverse_vartime_impl();
+#endif
+  }
+  static HD void shr1(uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[7] >>= 1;
+  }
+  // x <- x / 2 mod p for x in [0, p): (x + p) / 2 when x is odd (x + p < 2^255)
+  static HD void halve_mod(uint32_t* x) {
+    uint32_t m = 0u - (x[0] & 1u);
+    x[0] = cc::add_cc(x[0], P::MOD(0) & m);
+#pragma unroll
+    for (int i = 1; i < 7; i++) x[i] = cc::addc_cc(x[i], P::MOD(i) & m);
+    x[7] = cc::addc(x[7], P::MOD(7) & m);
+    shr1(x);
+  }
+  static HD bool is_one_int(const uint32_t* a) {
+    uint32_t o = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 8; i++) o |= a[i];
+    return o == 0;
+  }
+  HD Fp inverse_vartime_impl() const {
+    if (is_zero()) return zero();
+    uint32_t u[8], v[8];
+    Fp x1 = zero(), x2 = zero();
+    x1.l[0] = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u[i] = l[i];
+      v[i] = P::MOD(i);
+    }
+    // invariants: x1 * A = u, x2 * A = v (mod p); gcd(u, v) = 1; v odd
+    while (!is_one_int(u) && !is_one_int(v)) {
+      while (!(u[0] & 1u)) {
+        shr1(u);
+        halve_mod(x1.l);
+      }
+      while (!(v[0] & 1u)) {
+        shr1(v);
+        halve_mod(x2.l);
+      }
+      uint32_t t[8];
+      t[0] = cc::sub_cc(u[0], v[0]);
+#pragma unroll
+      for (int i = 1; i < 8; i++) t[i] = cc::subc_cc(u[i], v[i]);
+      uint32_t borrow = cc::subc(0u, 0u);
+      if (!borrow) {  // u >= v
+#pragma unroll
+        for (int i = 0; i < 8; i++) u[i] = t[i];
+        x1 = x1 - x2;
+      } else {
+        v[0] = cc::sub_cc(v[0], u[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) v[i] = cc::subc_cc(v[i], u[i]);
+        x2 = x2 - x1;
+      }
+    }
+    Fp r = is_one_int(u) ? x1 : x2;  // = A^-1 = a^-1 R^-1 (plain inverse of the representative)
+    return r * (r2() * r2());       // * R^3 / R -> a^-1 R
+  }
+
   // value >= p ?  (for validating standard-form inputs)
   HD bool geq_modulus() const {
     using namespace cc;
@@ -331,6 +406,17 @@ __device__ __noinline__ Fp<P, INL> fp_inverse_outlined(Fp<P, INL> a) {
 #pragma unroll
   for (int i = 0; i < 8; i++) t.l[i] = a.l[i];
   t = t.inverse_impl();
+  Fp<P, INL> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = t.l[i];
+  return r;
+}
+template <class P, bool INL>
+__device__ __noinline__ Fp<P, INL> fp_inverse_vartime_outlined(Fp<P, INL> a) {
+  Fp<P, false> t;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l[i] = a.l[i];
+  t = t.inverse_vartime_impl();
   Fp<P, INL> r;
 #pragma unroll
   for (int i = 0; i < 8; i++) r.l[i] = t.l[i];

@@ -100,6 +100,10 @@ struct alignas(32) Fq2T {
     B t = (c0.sqr() + c1.sqr()).inverse();
     return Fq2T{c0 * t, (c1 * t).neg()};
   }
+  HD Fq2T inverse_vartime() const {  // same value, Fp::inverse_vartime for the norm
+    B t = (c0.sqr() + c1.sqr()).inverse_vartime();
+    return Fq2T{c0 * t, (c1 * t).neg()};
+  }
   HD bool geq_modulus() const { return c0.geq_modulus() || c1.geq_modulus(); }
 };
 

@@ -54,6 +54,7 @@ void t_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* 
       case 1: r = x - y; break;
       case 2: r = x * y; break;
       case 3: r = x.inverse(); break;
+      case 6: r = x.inverse_vartime(); break;
       default: r = x.neg(); break;
     }
     store(out, r.from_mont());
@@ -68,6 +69,7 @@ void t_fq2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 2: r = x * y; break;
     case 3: r = x.inverse(); break;
     case 4: r = x.sqr(); break;
+    case 6: r = x.inverse_vartime(); break;
     default: r = x.neg(); break;
   }
   store(out, r.from_mont());

@@ -403,7 +403,7 @@ k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t per_block,
 template <class F>
 __global__ void k_finalize(const XYZZ<F>* in, F* out_jac_std) {
   if (threadIdx.x | blockIdx.x) return;
-  Affine<F> a = xyzz_to_affine(in[0]);
+  Affine<F> a = xyzz_to_affine<F, true>(in[0]);
   if (a.is_inf()) {
     out_jac_std[0] = F::zero();
     out_jac_std[1] = F::zero();

@@ -187,7 +187,8 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   // the XYZZ kernel (measured per-rank at 2^20: N=8 5.05 vs 6.45 ms, N=4 8.10 vs 8.29, N=2 14.5 vs 12.1).
   double weighted_terms = 0;
   for (int k = 0; k < 4; k++) weighted_terms += wgt[k] * (double)(pk->hi[k] - pk->lo[k]);
-  const bool affine_ok = weighted_terms >= 2.0e6;
+  static const double min_terms = getenv("B200_AFF_MIN_TERMS") ? atof(getenv("B200_AFF_MIN_TERMS")) : 2.0e6;  // tuning knob
+  const bool affine_ok = weighted_terms >= min_terms;
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
   if (has(0)) {

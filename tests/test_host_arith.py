@@ -66,6 +66,10 @@ def test_fp_ops(lib, field, p):
         A = to_u32([a])
         exp = pow(a, -1, p) if a else 0
         assert call(lib.t_fp_op, field, 3, ptr(A), ptr(A), nout=1)[0] == exp
+    for a in vs + [1 << k for k in range(0, 254, 7)] + [p - (1 << k) for k in range(1, 250, 11)]:
+        A = to_u32([a])                               # binary-Euclid inversion: same value as a^(p-2)
+        exp = pow(a, -1, p) if a else 0
+        assert call(lib.t_fp_op, field, 6, ptr(A), ptr(A), nout=1)[0] == exp
     assert lib.t_geq(field, ptr(to_u32([p]))) == 1
     assert lib.t_geq(field, ptr(to_u32([p - 1]))) == 0
     assert lib.t_geq(field, ptr(to_u32([(1 << 256) - 1]))) == 1
@@ -86,6 +90,7 @@ def test_fq2_ops(lib):
         assert tuple(call(lib.t_fq2_op, 5, ptr(A), ptr(B), nout=2)) == F2.neg(a)
         if a != (0, 0) and i < 25:
             assert tuple(call(lib.t_fq2_op, 3, ptr(A), ptr(B), nout=2)) == F2.inverse(a)  # fq2.go:99-108
+            assert tuple(call(lib.t_fq2_op, 6, ptr(A), ptr(B), nout=2)) == F2.inverse(a)
 
 
 def test_fq2_lazy_reduction_extremes(lib):
