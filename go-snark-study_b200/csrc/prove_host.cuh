@@ -184,10 +184,11 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
         pk->sort_src[k] = pk->sort_src[j];
   // Accumulation kernel per rank: the batched-affine tree pays off when the rank has enough overlapping work to
   // cover its per-round inversion gaps; a rank left with one or two small MSMs (4+ GPUs at 2^20) is faster with
-  // the XYZZ kernel (measured per-rank at 2^20: N=8 5.05 vs 6.45 ms, N=4 8.10 vs 8.29, N=2 14.5 vs 12.1).
+  // the XYZZ kernel (measured per-rank maxima at 2^20, XYZZ vs affine: N=8 5.06 vs 5.89 ms, N=4 8.12 vs 7.40,
+  // N=2 14.5 vs 11.4 -- profiles/r1_notes.md); the threshold sits between the N=4 and N=8 shares.
   double weighted_terms = 0;
   for (int k = 0; k < 4; k++) weighted_terms += wgt[k] * (double)(pk->hi[k] - pk->lo[k]);
-  static const double min_terms = getenv("B200_AFF_MIN_TERMS") ? atof(getenv("B200_AFF_MIN_TERMS")) : 2.0e6;  // tuning knob
+  static const double min_terms = getenv("B200_AFF_MIN_TERMS") ? atof(getenv("B200_AFF_MIN_TERMS")) : 1.3e6;  // tuning knob
   const bool affine_ok = weighted_terms >= min_terms;
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
