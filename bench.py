@@ -127,6 +127,16 @@ def cpu_reference(syn, budget_s=16.0):
     return 1.0 / secs, info
 
 
+def _nwin(n):
+    """Windows per scalar the library uses for an n-term base set (mirror of pick_window_bits, csrc/capi.cu)."""
+    best, best_cost = 8, float("inf")
+    for c in range(8, 19):
+        cost = ((255 + c - 1) // c) * float(n) * 10.0 + 2.0 * float(1 << (c - 1)) * 14.0 * 4.0
+        if cost < best_cost:
+            best, best_cost = c, cost
+    return (255 + best - 1) // best
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -397,11 +407,12 @@ def main():
                             "achieved": 160.0 * (prof_x[5] / max(prof_x[4], 1)) / (prof_x[3] / max(prof_x[4], 1) * 1e-3) / 1e9
                             if prof_x[3] > 0 else None},
                      "alu": (lambda macs: {"achieved": macs, "peak": 9.3e12, "unit": "32x32+64 multiply-accumulates/s",
+                                           "windows_per_term": _nwin(g1_terms / g1_l),
                                            "frac": macs / 9.3e12,
-                                           "note": "6 Montgomery multiplies per batched-affine bucket add x 136 IMAD.WIDE-equivalent "
-                                                   "slots each (SASS of fp_mul_outlined); peak = IMAD.WIDE carry-chain rate measured "
+                                           "note": "one bucket add per term and window; 6 Montgomery multiplies per batched-affine add x 136 "
+                                                   "IMAD.WIDE-equivalent slots each (SASS of fp_mul_outlined); peak = IMAD.WIDE carry-chain rate measured "
                                                    "by tools/micro/imad_bench.cu on this GPU class (29.6 / clk / SM)"})(
-                         6 * 136 * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3)) if g1_ms > 0 else None,
+                         6 * 136 * _nwin(g1_terms / g1_l) * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3)) if g1_ms > 0 else None,
                      "overlapped": {"g1_avg_ms": prof[0] / max(prof[1], 1), "g2_avg_ms": prof[3] / max(prof[4], 1)}},
         "algorithmic_bytes_per_proof": syn.algorithmic_bytes(),
         "g1_msm_2p20": msm_extra,
