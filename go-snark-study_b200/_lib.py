@@ -62,6 +62,7 @@ _SIGNATURES = {
     "b200_poly_eval_batch": [_vp, _sz, _sz, _vp, _vp],
     "b200_zero_poly": [_sz, _vp],
     "b200_pairing_batch": [_vp, _vp, _sz, _vp],
+    "b200_fq12_mul_batch": [_vp, _vp, _sz, _vp],
     "b200_groth16_verify": [_vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.POINTER(_int)],
     "b200_r1cs_to_qap": [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp],
     "b200_combine_polynomials": [_vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp],

@@ -193,5 +193,20 @@ class Bn128:
         return [tuple(tuple((v[12 * i + 6 * h + 2 * k], v[12 * i + 6 * h + 2 * k + 1]) for k in range(3)) for h in range(2))
                 for i in range(n)]
 
+    @staticmethod
+    def _flatten_fq12(vals):
+        return ints_to_limbs([c for v in vals for h in v for f2 in h for c in f2])
+
+    def Fq12MulBatch(self, xs, ys):         # fields/fq12.go:72-84, element-wise over two lists
+        n = len(xs)
+        out = np.zeros(n * 48, dtype=np.uint64)
+        check(lib().b200_fq12_mul_batch(ptr(self._flatten_fq12(xs)), ptr(self._flatten_fq12(ys)), n, ptr(out)))
+        v = limbs_to_ints(out)
+        return [tuple(tuple((v[12 * i + 6 * h + 2 * k], v[12 * i + 6 * h + 2 * k + 1]) for k in range(3)) for h in range(2))
+                for i in range(n)]
+
+    def Fq12Mul(self, x, y):
+        return self.Fq12MulBatch([x], [y])[0]
+
     def Pairing(self, p1, p2):              # bn128.go:179-186 -> [2][3][2] tuple of ints
         return self.PairingBatch([p1], [p2])[0]

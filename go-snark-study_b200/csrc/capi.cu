@@ -700,6 +700,23 @@ __device__ void store_f12_std(const F12& f, Fq2* out) {
   out[0] = f.a.a.from_mont(); out[1] = f.a.b.from_mont(); out[2] = f.a.c.from_mont();
   out[3] = f.b.a.from_mont(); out[4] = f.b.b.from_mont(); out[5] = f.b.c.from_mont();
 }
+// out[i] = a[i] * b[i] in F_q^12 (fields/fq12.go:72-84), standard form in/out, [2][3][2] order
+__global__ void __launch_bounds__(32) k_fq12_mul_batch(const Fq2* a, const Fq2* b, size_t n, Fq2* out, int* err) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F12 x, y;
+  Fq2* xs = &x.a.a;
+  Fq2* ys = &y.a.a;
+  bool bad = false;
+  for (int k = 0; k < 6; k++) {
+    Fq2 u = a[6 * i + k], v = b[6 * i + k];
+    bad = bad || u.geq_modulus() || v.geq_modulus();
+    xs[k] = u.to_mont();
+    ys[k] = v.to_mont();
+  }
+  if (bad) atomicOr(err, 1);
+  store_f12_std(f12_mul(x, y), out + 6 * i);
+}
 __global__ void __launch_bounds__(32) k_pairing_batch(const Fq* g1, const Fq2* g2, size_t n, Fq2* out, int* err) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -764,6 +781,22 @@ int pairing_batch_host(const uint64_t* g1, const uint64_t* g2, size_t n, uint64_
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, dout.p, n * 6 * sizeof(Fq2), cudaMemcpyDeviceToHost, g_stream));
   return check_err_flag<Fq>("pairing_batch");
+}
+
+int fq12_mul_batch_host(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  if (!a || !b || !out) return fail(B200_EINVAL, "fq12_mul_batch: null pointer");
+  if (n == 0) return B200_OK;
+  DevBuf da, db, dout;
+  size_t bytes = n * 6 * sizeof(Fq2);
+  CU(da.alloc(bytes));
+  CU(db.alloc(bytes));
+  CU(dout.alloc(bytes));
+  CU(cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, g_stream));
+  k_fq12_mul_batch<<<nblk(n, 32), 32, 0, g_stream>>>(da.as<Fq2>(), db.as<Fq2>(), n, dout.as<Fq2>(), g_d_err);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, g_stream));
+  return check_err_flag<Fq>("fq12_mul_batch");
 }
 
 int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1, const uint64_t* beta2,
@@ -950,6 +983,7 @@ int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]) { B200_API_BODY(poly_eval_host(v, n, x, out)) }
 int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out) { B200_API_BODY(poly_eval_batch_host(polys, m, n, x, out)) }
 int b200_zero_poly(size_t n, uint64_t* out) { B200_API_BODY(zero_poly_host(n, out)) }
+int b200_fq12_mul_batch(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) { B200_API_BODY(fq12_mul_batch_host(a, b, n, out)) }
 int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out) { B200_API_BODY(pairing_batch_host(g1_jac, g2_jac, n, out)) }
 int b200_groth16_verify(const uint64_t* ic, size_t n_ic, const uint64_t alpha1[12], const uint64_t beta2[24],
                         const uint64_t gamma2[24], const uint64_t delta2[24], const uint64_t pi_a[12],

@@ -188,6 +188,9 @@ int b200_zero_poly(size_t n, uint64_t* out);
  * A G2 point at infinity returns B200_EINVAL where the reference panics "q1[2] != Fq2.One()" (bn128.go:238-241);
  * a G1 point at infinity is processed like the reference does (Affine -> (0,0)).                                    */
 int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out);
+/* out[i] = a[i] * b[i] in F_q^12 (fields/fq12.go:72-84; 48 uint64 per element, same order as b200_pairing_batch):
+ * the product step of the verification equations (snark.go:338-341,357; groth16.go:297-301).                      */
+int b200_fq12_mul_batch(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
 /* groth16.VerifyProof (groth16/groth16.go:281-305): *ok = 1 iff e(A,B) == e(alpha,beta) * (e(icPubl,gamma) * e(C,delta)),
  * icPubl = IC[0] + sum publicSignals[i] * IC[i+1].  The four pairings run concurrently.                              */
 int b200_groth16_verify(const uint64_t* ic, size_t n_ic, const uint64_t alpha1[12], const uint64_t beta2[24],

@@ -755,6 +755,72 @@ def pinocchio_prove(n_vars, n_public, pk, w, px):
     return p, hx
 
 
+def pinocchio_setup(n_vars, n_public, alphas, betas, gammas, toxic):
+    """snark.go:98-251 with the toxic values injected (``toxic`` = dict T, Ka, Kb, Kc, Kbeta, Kgamma, RhoA, RhoB;
+    RhoC = RhoA*RhoB as in :150).  Returns (pk, vk) in the current struct layout (G1T inside Pk, snark.go:16-37)."""
+    G1, G2, F = BN.G1, BN.G2, FQR
+    t, ka, kb, kc = toxic["T"], toxic["Ka"], toxic["Kb"], toxic["Kc"]
+    kbeta, kgamma, rho_a, rho_b = toxic["Kbeta"], toxic["Kgamma"], toxic["RhoA"], toxic["RhoB"]
+    rho_c = F.mul(rho_a, rho_b)
+    kbg = F.mul(kbeta, kgamma)
+    vk = {"Vka": G2.mul_scalar(G2.G, ka), "Vkb": G1.mul_scalar(G1.G, kb), "Vkc": G2.mul_scalar(G2.G, kc), "IC": [],
+          "G1Kbg": G1.mul_scalar(G1.G, kbg), "G2Kbg": G2.mul_scalar(G2.G, kbg), "G2Kg": G2.mul_scalar(G2.G, kgamma)}
+    pk = {k: [] for k in ("A", "B", "C", "Kp", "Ap", "Bp", "Cp")}
+    for i in range(n_vars):                                   # :171-207
+        rho_a_at = F.mul(rho_a, PF.eval(alphas[i], t))
+        a = G1.mul_scalar(G1.G, rho_a_at)
+        pk["A"].append(a)
+        if i <= n_public:
+            vk["IC"].append(a)
+        rho_b_bt = F.mul(rho_b, PF.eval(betas[i], t))
+        bg1 = G1.mul_scalar(G1.G, rho_b_bt)
+        pk["B"].append(G2.mul_scalar(G2.G, rho_b_bt))
+        rho_c_ct = F.mul(rho_c, PF.eval(gammas[i], t))
+        c = G1.mul_scalar(G1.G, rho_c_ct)
+        pk["C"].append(c)
+        kt = F.add(F.add(rho_a_at, rho_b_bt), rho_c_ct)
+        k_ = G1.mul_scalar(G1.G, kt)
+        assert G1.affine(k_) == G1.affine(G1.add(G1.add(a, bg1), c))     # the reference's os.Exit(1) self-check, :194-199
+        pk["Ap"].append(G1.mul_scalar(a, ka))
+        pk["Bp"].append(G1.mul_scalar(bg1, kb))
+        pk["Cp"].append(G1.mul_scalar(c, kc))
+        pk["Kp"].append(G1.mul_scalar(k_, kbeta))
+    zpol = [1]
+    for i in range(1, len(alphas) - 1):                       # :210-221
+        zpol = PF.mul(zpol, [F.neg(i), 1])
+    pk["Z"] = zpol
+    vk["Vkz"] = G2.mul_scalar(G2.G, F.mul(rho_c, PF.eval(zpol, t)))      # :224-227
+    gt1 = [G1.G]
+    t_encr = t
+    for i in range(1, len(zpol)):                             # :230-237
+        gt1.append(G1.mul_scalar(G1.G, t_encr))
+        t_encr = F.mul(t_encr, t)
+    pk["G1T"] = gt1
+    return pk, vk
+
+
+def pinocchio_verify(vk, proof, public_signals):
+    """snark.go:292-372: the five pairing checks, in the reference's order; returns (ok, index of the first failed check or 0)."""
+    G1, G2, F12 = BN.G1, BN.G2, BN.Fq12
+    if not F12.equal(BN.pairing(proof["PiA"], vk["Vka"]), BN.pairing(proof["PiAp"], G2.G)):
+        return False, 1
+    if not F12.equal(BN.pairing(vk["Vkb"], proof["PiB"]), BN.pairing(proof["PiBp"], G2.G)):
+        return False, 2
+    if not F12.equal(BN.pairing(proof["PiC"], vk["Vkc"]), BN.pairing(proof["PiCp"], G2.G)):
+        return False, 3
+    vkxpia = vk["IC"][0]
+    for i, sig in enumerate(public_signals):
+        vkxpia = G1.add(vkxpia, G1.mul_scalar(vk["IC"][i + 1], sig))
+    if not F12.equal(BN.pairing(G1.add(vkxpia, proof["PiA"]), proof["PiB"]),
+                     F12.mul(BN.pairing(proof["PiH"], vk["Vkz"]), BN.pairing(proof["PiC"], G2.G))):
+        return False, 4
+    pia_pic = G1.add(G1.add(vkxpia, proof["PiA"]), proof["PiC"])
+    lhs = F12.mul(BN.pairing(pia_pic, vk["G2Kbg"]), BN.pairing(vk["G1Kbg"], proof["PiB"]))
+    if not F12.equal(lhs, BN.pairing(proof["PiKp"], vk["G2Kg"])):
+        return False, 5
+    return True, 0
+
+
 # ---------------------------------------------------- generic helper (MSM)
 def msm_reference_order(group, points, scalars):
     """The reference has no MSM routine; this is its hot loop shape

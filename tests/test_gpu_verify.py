@@ -88,3 +88,51 @@ def test_minimal_flow_all_gpu(mods):
     assert o.groth16_verify(setup["Vk"], proof, [35])
     with pytest.raises(Exception):
         groth16.VerifyProof(setup["Vk"], proof, [35, 1, 2])              # more signals than IC entries
+
+
+def test_fq12_mul_batch(mods):
+    """fields/fq12.go:72-84 on the device, against the oracle (random elements and the identity)."""
+    bn, _, _ = mods
+    rng = random.Random(12)
+    rnd = lambda: tuple(tuple((rng.randrange(o.Q), rng.randrange(o.Q)) for _ in range(3)) for _ in range(2))
+    one = (((1, 0), (0, 0), (0, 0)), ((0, 0), (0, 0), (0, 0)))
+    xs, ys = [rnd(), rnd(), one], [rnd(), one, rnd()]
+    got = bn.Fq12MulBatch(xs, ys)
+    assert got == [o.BN.Fq12.mul(x, y) for x, y in zip(xs, ys)]
+    assert got[1] == xs[1] and got[2] == ys[2]
+
+
+def test_pinocchio_setup_and_verify_on_gpu(mods, golden_dir):
+    """snark.GenerateTrustedSetup (snark.go:98-251) minted on the GPU equals the oracle X,Y,Z-exactly for injected toxic
+    values; the GPU proof under it passes snark.VerifyProof (:292-372) on the GPU and the oracle's; the Go binary's own
+    Pinocchio proof verifies too, and a wrong public input fails at the QAP check like the reference."""
+    from gosnark_b200 import snark
+    g = json.load(open(os.path.join(golden_dir, "gobin_x3x5.json")))
+    cc = g["compiledcircuit"]
+    r1 = cc["R1CS"]
+    _, _, pf = mods
+    alphas, betas, gammas, _ = pf.R1CSToQAP(r1["A"], r1["B"], r1["C"])
+    tox = {"T": 0x1234567, "Ka": 0x1111, "Kb": 0x2222, "Kc": 0x3333, "Kbeta": 0x4444, "Kgamma": 0x5555,
+           "RhoA": 0x6666, "RhoB": 0x7777}
+    setup = snark.GenerateTrustedSetup(len(g["witness"]), cc, alphas, betas, gammas, toxic=tox)
+    opk, ovk = o.pinocchio_setup(cc["NVars"], cc["NPublic"], alphas, betas, gammas, tox)
+    for k in opk:
+        assert setup["Pk"][k] == opk[k], k
+    for k in ovk:
+        assert setup["Vk"][k] == ovk[k], k
+    w = [int(x) for x in g["witness"]]
+    _, _, _, px = pf.CombinePolynomials(w, alphas, betas, gammas)
+    proof = snark.GenerateProofs(cc, setup["Pk"], w, px)
+    assert proof == o.pinocchio_prove(cc["NVars"], cc["NPublic"], opk, w, px)[0] or \
+        all(G1.affine(proof[k]) == G1.affine(v) for k, v in o.pinocchio_prove(cc["NVars"], cc["NPublic"], opk, w, px)[0].items() if k != "PiB")
+    assert snark.VerifyProof(setup["Vk"], proof, [35], True)
+    assert not snark.VerifyProof(setup["Vk"], proof, [34])
+    assert o.pinocchio_verify(setup["Vk"], proof, [35])[0]
+    # the Go binary's setup and proof (older JSON layout)
+    st, pr = g["pinocchio_setup"], g["pinocchio_proofs"]
+    t3 = lambda p: tuple(p)
+    t2 = lambda p: tuple(tuple(c) for c in p)
+    vk = {k: ([t3(p) for p in v] if k == "IC" else (t2(v) if isinstance(v[0], list) else t3(v))) for k, v in st["Vk"].items()}
+    gproof = {k: (t2(v) if k == "PiB" else t3(v)) for k, v in pr.items()}
+    assert snark.VerifyProof(vk, gproof, [35])
+    assert not snark.VerifyProof(vk, gproof, [34])
