@@ -2,6 +2,9 @@
 
     python -m gosnark_b200.cli groth16 genproofs      # cli/main.go:455-518
     python -m gosnark_b200.cli groth16 verify         # cli/main.go:520-549
+    python -m gosnark_b200.cli groth16 trustedsetup   # cli/main.go:407-453
+    python -m gosnark_b200.cli trustedsetup [wasm]    # cli/main.go:231-301   (Pinocchio)
+    python -m gosnark_b200.cli verify                 # cli/main.go:368-396   (Pinocchio)
     python -m gosnark_b200.cli genproofs              # cli/main.go:303-366   (Pinocchio)
 
 Reads the files the Go CLI writes/reads in the current directory (compiledcircuit.json,
@@ -120,6 +123,71 @@ def groth16_verify():
     return verified
 
 
+def _qap(circuit):
+    pf = r1csqap.PolynomialField()
+    r1cs = circuit["R1CS"]
+    return pf.R1CSToQAP(r1cs["A"], r1cs["B"], r1cs["C"])
+
+
+def _jl(p):
+    """Jacobian point -> the nested JSON lists Go's encoding/json writes for [3]*big.Int / [3][2]*big.Int."""
+    return [list(c) if isinstance(c, (tuple, list)) else c for c in p]
+
+
+def _write_setup(obj, wasm_obj=None):
+    with open("trustedsetup.json", "w") as f:
+        json.dump(obj, f)
+    print("Trusted Setup data written to  trustedsetup.json")
+    if wasm_obj is not None:
+        with open("trustedsetupString.json", "w") as f:
+            json.dump(wasm_obj, f)
+
+
+def groth16_trustedsetup():
+    """cli/main.go:407-453: compiledcircuit.json + inputs -> trustedsetup.json (Toxic erased, like the reference)."""
+    circuit = _load("compiledcircuit.json")
+    w = calculate_witness(circuit, _load("privateInputs.json"), _load("publicInputs.json"))
+    alphas, betas, gammas, _ = _qap(circuit)
+    setup = groth16.GenerateTrustedSetup(len(w), circuit, alphas, betas, gammas)
+    pk, vk = setup["Pk"], setup["Vk"]
+    out = {"Toxic": {k: None for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta")},
+           "Pk": {"BACDelta": [_jl(p) for p in pk["BACDelta"]], "Z": pk["Z"],
+                  "G1": {"Alpha": _jl(pk["G1"]["Alpha"]), "Beta": _jl(pk["G1"]["Beta"]), "Delta": _jl(pk["G1"]["Delta"]),
+                         "At": [_jl(p) for p in pk["G1"]["At"]], "BACGamma": [_jl(p) for p in pk["G1"]["BACGamma"]]},
+                  "G2": {"Beta": _jl(pk["G2"]["Beta"]), "Gamma": _jl(pk["G2"]["Gamma"]), "Delta": _jl(pk["G2"]["Delta"]),
+                         "BACGamma": [_jl(p) for p in pk["G2"]["BACGamma"]]},
+                  "PowersTauDelta": [_jl(p) for p in pk["PowersTauDelta"]]},
+           "Vk": {"IC": [_jl(p) for p in vk["IC"]], "G1": {"Alpha": _jl(vk["G1"]["Alpha"])},
+                  "G2": {k: _jl(vk["G2"][k]) for k in ("Beta", "Gamma", "Delta")}}}
+    _write_setup(out)
+
+
+def pinocchio_trustedsetup(wasm=False):
+    """cli/main.go:231-301 (`trustedsetup [wasm]`).  G1T is written both inside Pk (snark.go:16-26) and at the top level
+    (the layout of the prebuilt binary, one commit older — SURVEY E2); Go's json.Unmarshal ignores the one it does not know."""
+    circuit = _load("compiledcircuit.json")
+    w = calculate_witness(circuit, _load("privateInputs.json"), _load("publicInputs.json"))
+    alphas, betas, gammas, _ = _qap(circuit)
+    setup = snark.GenerateTrustedSetup(len(w), circuit, alphas, betas, gammas)
+    pk, vk = setup["Pk"], setup["Vk"]
+    jpk = {k: ([_jl(p) for p in v] if k != "Z" else v) for k, v in pk.items()}
+    jvk = {k: ([_jl(p) for p in v] if k == "IC" else _jl(v)) for k, v in vk.items()}
+    out = {"Toxic": {k: None for k in ("T", "Ka", "Kb", "Kc", "Kbeta", "Kgamma", "RhoA", "RhoB", "RhoC")},
+           "G1T": jpk["G1T"], "G2T": None, "Pk": jpk, "Vk": jvk}
+    from . import utils
+    _write_setup(out, utils.SetupToString(setup) if wasm else None)
+
+
+def pinocchio_verify():
+    """cli/main.go:368-396 — proofs.json against trustedsetup.json's Vk and publicInputs.json, pairings on the GPU."""
+    proof, setup, public = _load("proofs.json"), _load("trustedsetup.json"), _load("publicInputs.json")
+    vk = {k: ([_t3(p) for p in v] if k == "IC" else (_g2(v) if isinstance(v[0], list) else _t3(v))) for k, v in setup["Vk"].items()}
+    pr = {k: (_g2(v) if k == "PiB" else _t3(v)) for k, v in proof.items()}
+    verified = snark.VerifyProof(vk, pr, [int(x) for x in public], True)
+    print("Proofs verified" if verified else "ERROR: proofs not verified")
+    return verified
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     _lib.init()
@@ -127,10 +195,16 @@ def main(argv=None):
         groth16_genproofs()
     elif argv[:2] == ["groth16", "verify"]:
         groth16_verify()
+    elif argv[:2] == ["groth16", "trustedsetup"]:
+        groth16_trustedsetup()
     elif argv[:1] == ["genproofs"]:
         pinocchio_genproofs()
+    elif argv[:1] == ["verify"]:
+        pinocchio_verify()
+    elif argv[:1] == ["trustedsetup"]:
+        pinocchio_trustedsetup(wasm=argv[1:2] == ["wasm"])
     else:
-        print("usage: python -m gosnark_b200.cli groth16 genproofs|verify  |  genproofs", file=sys.stderr)
+        print("usage: python -m gosnark_b200.cli [groth16] trustedsetup|genproofs|verify", file=sys.stderr)
         return 2
     return 0
 

@@ -159,3 +159,22 @@ func Pairing(p1 [3]*big.Int, p2 [3][2]*big.Int) ([2][3][2]*big.Int, error) {
 	err := check(C.b200_pairing_batch(u64(g1), u64(g2), 1, u64(out)))
 	return Fq12FromLimbs(out), err
 }
+
+// Fq12Mul backs fields.Fq12.Mul in the verification equations (fields/fq12.go:72-84).
+func Fq12Mul(a, b [2][3][2]*big.Int) ([2][3][2]*big.Int, error) {
+	flat := func(x [2][3][2]*big.Int) []uint64 {
+		out := make([]uint64, 0, 48)
+		for h := 0; h < 2; h++ {
+			for k := 0; k < 3; k++ {
+				for c := 0; c < 2; c++ {
+					out = append(out, limbs(make([]uint64, 4), x[h][k][c])...)
+				}
+			}
+		}
+		return out
+	}
+	fa, fb := flat(a), flat(b)
+	out := make([]uint64, 48)
+	err := check(C.b200_fq12_mul_batch(u64(fa), u64(fb), 1, u64(out)))
+	return Fq12FromLimbs(out), err
+}

@@ -95,6 +95,28 @@ class StandIn:
         _wr(out, [PF.eval(coeffs[i * n:(i + 1) * n], xv) for i in range(m)])
         return 0
 
+    def b200_r1cs_to_qap(self, a, b, c, n, m, alphas, betas, gammas, z):
+        for src, dst in ((a, alphas), (b, betas), (c, gammas)):
+            v = _rd(src, 4 * n * m)
+            rows = [v[j * m:(j + 1) * m] for j in range(n)]
+            _wr(dst, [x for col in o.transpose(rows) for x in PF.lagrange_interpolation(col)])
+        zp = [1]
+        for i in range(1, m - 1):
+            zp = PF.mul(zp, [F.neg(i), 1])
+        _wr(z, zp)
+        return 0
+
+    def b200_combine_polynomials(self, r, m, ap, bp, cp, n, ax, bx, cx, px):
+        rv = _rd(r, 4 * m)
+        mats = [[v[i * n:(i + 1) * n] for i in range(m)] for v in (_rd(p, 4 * m * n) for p in (ap, bp, cp))]
+        res = PF.combine_polynomials(rv, *mats)
+        for dst, val, ln in zip((ax, bx, cx, px), res, (n, n, n, 2 * n - 1)):
+            _wr(dst, list(val) + [0] * (ln - len(val)))
+        return 0
+
+    def b200_init(self, dev):
+        return 0
+
     def b200_pairing_batch(self, g1, g2, n, out):
         self.calls.append(("pairing", n))
         A, B = _g1s(_rd(g1, 12 * n)), _g2s(_rd(g2, 24 * n))
@@ -127,8 +149,8 @@ class StandIn:
 def install(monkeypatch):
     """Route the mirrors' lib() to a StandIn (every module binds `lib` by name at import)."""
     import gosnark_b200  # noqa: F401  (import shim)
-    from gosnark_b200 import _lib, bn128, groth16, snark
+    from gosnark_b200 import _lib, bn128, groth16, r1csqap, snark
     s = StandIn()
-    for mod in (_lib, bn128, groth16, snark):
+    for mod in (_lib, bn128, groth16, r1csqap, snark):
         monkeypatch.setattr(mod, "lib", lambda s=s: s)
     return s

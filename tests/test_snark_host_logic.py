@@ -105,3 +105,66 @@ def test_groth16_verify_mirror_marshalling(monkeypatch, golden_dir):
     assert not groth16.VerifyProof(vkd, proof, [int(g["public"][0]) + 1])
     with pytest.raises(Exception, match="len\\(IC\\)"):
         groth16.VerifyProof(vkd, proof, [1, 2, 3])
+
+
+def test_verify_from_circom_files(monkeypatch, golden_dir, tmp_path, capsys):
+    """externalVerif.VerifyFromCircom (circomVerifier.go:26-96; circomVerifier_test.go:9-13) over the snarkjs fixture."""
+    abi_standin.install(monkeypatch)
+    from gosnark_b200 import externalVerif
+    c = json.load(open(os.path.join(golden_dir, "circom_groth16.json")))
+    paths = {}
+    for name, obj in (("verification_key.json", c["vk"]), ("proof.json", c["proof"]), ("public.json", c["public"])):
+        paths[name] = str(tmp_path / name)
+        json.dump(obj, open(paths[name], "w"))
+    ok, err = externalVerif.VerifyFromCircom(paths["verification_key.json"], paths["proof.json"], paths["public.json"])
+    assert ok and err is None
+    out = capsys.readouterr().out
+    assert "vk parsed:" in out and "proof parsed:" in out and "publicSignals parsed:" in out and "✓" in out
+    json.dump([str(int(c["public"][0]) + 1)], open(paths["public.json"], "w"))
+    ok, err = externalVerif.VerifyFromCircom(paths["verification_key.json"], paths["proof.json"], paths["public.json"])
+    assert not ok and err is None
+    ok, err = externalVerif.VerifyFromCircom(paths["verification_key.json"], str(tmp_path / "missing.json"), paths["public.json"])
+    assert not ok and isinstance(err, OSError)
+    json.dump(["12x"], open(paths["public.json"], "w"))
+    ok, err = externalVerif.VerifyFromCircom(paths["verification_key.json"], paths["proof.json"], paths["public.json"])
+    assert not ok and "error parsing px from pxString" in str(err)
+
+
+@pytest.mark.parametrize("proto", ["groth16", "pinocchio"])
+def test_cli_trustedsetup_files_feed_the_go_binary(monkeypatch, golden_dir, proto, capsys):
+    """File-level interop in the other direction (cli/main.go:231-301, 407-453): OUR `trustedsetup` writes
+    trustedsetup.json, the UNMODIFIED Go binary proves with it and verifies; our `verify` accepts the Go proof."""
+    if not os.path.exists(GOBIN):
+        pytest.skip("oracle/_ref/go-snark-cli not staged")
+    abi_standin.install(monkeypatch)
+    from gosnark_b200 import cli
+    g = json.load(open(os.path.join(golden_dir, "gobin_x3x5.json")))
+    d = tempfile.mkdtemp(prefix="clits_")
+    cwd = os.getcwd()
+    pre = ["groth16"] if proto == "groth16" else []
+    try:
+        for fname, key in (("compiledcircuit.json", "compiledcircuit"), ("privateInputs.json", "private"),
+                           ("publicInputs.json", "public")):
+            json.dump(g[key], open(os.path.join(d, fname), "w"))
+        os.chdir(d)
+        assert cli.main(pre + ["trustedsetup"] + (["wasm"] if proto == "pinocchio" else [])) == 0
+        written = json.load(open("trustedsetup.json"))
+        assert all(v is None for v in written["Toxic"].values())          # toxic waste is not written (main.go:273-277)
+        b = os.path.join(d, "gsc")
+        shutil.copy(GOBIN, b)
+        os.chmod(b, 0o755)
+        p = subprocess.run([b, *pre, "genproofs"], cwd=d, capture_output=True, text=True, timeout=120)
+        assert os.path.exists("proofs.json"), p.stdout[-500:] + p.stderr[-500:]
+        p = subprocess.run([b, *pre, "verify"], cwd=d, capture_output=True, text=True, timeout=120)
+        out = p.stdout + p.stderr
+        assert ("verification passed" in out) if proto == "groth16" else ("Proofs verified" in out and "❌" not in out), out
+        capsys.readouterr()
+        assert cli.main(pre + ["verify"]) == 0
+        assert "Proofs verified" in capsys.readouterr().out
+        if proto == "pinocchio":
+            from gosnark_b200 import utils
+            s = json.load(open("trustedsetupString.json"))
+            assert utils.SetupFromString(s)["Vk"]["Vkb"] == tuple(written["Vk"]["Vkb"])
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(d)
