@@ -167,7 +167,7 @@ func Fq12Mul(a, b [2][3][2]*big.Int) ([2][3][2]*big.Int, error) {
 		for h := 0; h < 2; h++ {
 			for k := 0; k < 3; k++ {
 				for c := 0; c < 2; c++ {
-					out = append(out, limbs(make([]uint64, 4), x[h][k][c])...)
+					out = limbs(out, x[h][k][c])
 				}
 			}
 		}
