@@ -316,6 +316,197 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound
   }
 }
 
+// ---- EXPERIMENT (off by default, B200_AFF_SP): software-pipelined variants with the multiply INLINED ------------
+// Hypothesis to measure in the next round: an out-of-line multiply is a scoreboard barrier (loads cannot stay in flight
+// across a CALL), so in the kernels above every iteration pays its index -> point gather latency in front of its
+// multiplies, and only other warps can hide it.  Here the field type is the inlined-multiply one (FqH, same memory
+// layout) and the operand fetches are staged explicitly three deep: slice bounds of pair k+3, entry ids of pair k+2 and
+// the point gathers of pair k+1 are issued before the multiplies of pair k.
+template <class F>
+struct AffStage {
+  const AffineRound<F>& a;
+  uint32_t npairs;
+  __device__ __forceinline__ uint2 bounds(uint32_t p) const {
+    if (a.round != 1 || p >= npairs) return make_uint2(0u, 0u);
+    uint32_t slice = p >> a.q_log;
+    return make_uint2(a.slice_start[slice], a.slice_end[slice]);
+  }
+  __device__ __forceinline__ PairIdx entries(uint32_t p, uint2 sb) const {
+    PairIdx r{kNoEntry, kNoEntry};
+    if (a.round == 1 && p < npairs) {
+      uint32_t j = p & ((1u << a.q_log) - 1u);
+      uint32_t i0 = sb.x + 2 * j;
+      if (i0 < sb.y) r.e0 = a.entries[i0];
+      if (i0 + 1 < sb.y) r.e1 = a.entries[i0 + 1];
+    }
+    return r;
+  }
+  __device__ __forceinline__ size_t node_base(uint32_t p) const {
+    uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
+    return ((size_t)slice << (a.q_log + 1)) + 2 * j;
+  }
+};
+
+template <class F, int kAffT, int MINB>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_forward_sp(AffineRound<F> a) {
+  __shared__ F wtot[kAffBlock / 32];
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t npairs = nslices << a.q_log;
+  const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);
+  if (block_base >= npairs) {
+    if (threadIdx.x == 0) a.btot[blockIdx.x] = F::one();
+    return;
+  }
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const AffStage<F> st{a, npairs};
+  // gather the two x-coordinates of pair p: 0 = beyond the range, 1 = single live operand (d = 1), 2 = fetched
+  auto gather = [&](uint32_t p, PairIdx ix, F& x1, F& x2) -> uint32_t {
+    if (p >= npairs) return 0u;
+    if (a.round == 1) {
+      if (ix.e1 == kNoEntry) return 1u;
+      x1 = ld_x_gather(&a.table[ix.e0 >> 1]);
+      x2 = ld_x_gather(&a.table[ix.e1 >> 1]);
+      return 2u;
+    }
+    size_t base = st.node_base(p);
+    x1 = ld_fe(&a.prev[base].x);
+    x2 = ld_fe(&a.prev[base + 1].x);
+    return 2u;
+  };
+  const uint32_t p0 = block_base + t;
+  uint2 sb = st.bounds(p0 + 2 * kAffBlock);                                   // bounds of pair k+2
+  PairIdx ix = st.entries(p0 + kAffBlock, st.bounds(p0 + kAffBlock));           // entries of pair k+1
+  F cx1 = F::zero(), cx2 = F::zero();
+  uint32_t cst = gather(p0, st.entries(p0, st.bounds(p0)), cx1, cx2);
+  F run = F::one();
+#pragma unroll 1
+  for (int k = 0; k < kAffT; k++) {
+    const uint32_t p = p0 + k * kAffBlock;
+    F nx1 = F::zero(), nx2 = F::zero();
+    uint32_t nst = 0;
+    if (k + 1 < kAffT) nst = gather(p + kAffBlock, ix, nx1, nx2);
+    if (k + 2 < kAffT) ix = st.entries(p + 2 * kAffBlock, sb);
+    if (k + 3 < kAffT) sb = st.bounds(p + 3 * kAffBlock);
+    if (cst) {
+      F d = F::one();
+      if (cst == 2) {
+        F dx = cx2 - cx1;
+        if (cx1.is_zero() || cx2.is_zero() || dx.is_zero()) {  // infinity / doubling / P = -Q: the full operands decide
+          Affine<F> P, Q;
+          aff_operands(a, p, npairs, P, Q);
+          aff_denominator(P, Q, d);
+        } else {
+          d = dx;
+        }
+      }
+      a.pre[p] = run;
+      run = run * d;
+    }
+    cx1 = nx1;
+    cx2 = nx2;
+    cst = nst;
+  }
+  F incl = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    F up = shfl_up_fe(incl, off);
+    if ((int)lane >= off) incl = incl * up;
+  }
+  F sincl = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    F dn = shfl_down_fe(sincl, off);
+    if ((int)lane + off < 32) sincl = sincl * dn;
+  }
+  F pex = shfl_up_fe(incl, 1), sex = shfl_down_fe(sincl, 1);
+  if (lane == 0) pex = F::one();
+  if (lane == 31) sex = F::one();
+  F warp_total = shfl_idx_fe(incl, 31);
+  if (lane == 0) wtot[warp] = warp_total;
+  __syncthreads();
+  F other_warps = F::one();
+#pragma unroll
+  for (int w = 0; w < kAffBlock / 32; w++)
+    if (w != (int)warp) other_warps = other_warps * wtot[w];
+  a.others[blockIdx.x * kAffBlock + t] = pex * sex * other_warps;
+  if (t == 0) a.btot[blockIdx.x] = other_warps * wtot[0];
+}
+
+template <class F, int kAffT, int MINB>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_sp(AffineRound<F> a) {
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t npairs = nslices << a.q_log;
+  const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);
+  if (block_base >= npairs) return;
+  const uint32_t t = threadIdx.x;
+  const AffStage<F> st{a, npairs};
+  // fetch both operands and the prefix product of pair p (signs of round-1 entries are applied at use)
+  auto gather = [&](uint32_t p, PairIdx ix, Affine<F>& P, Affine<F>& Q, F& pre) -> uint32_t {
+    if (p >= npairs) return 0u;
+    P = Affine<F>::inf();
+    Q = Affine<F>::inf();
+    if (a.round == 1) {
+      if (ix.e0 != kNoEntry) P = ld_affine_gather(&a.table[ix.e0 >> 1]);
+      if (ix.e1 != kNoEntry) Q = ld_affine_gather(&a.table[ix.e1 >> 1]);
+    } else {
+      size_t base = st.node_base(p);
+      P = ld_affine(&a.prev[base]);
+      Q = ld_affine(&a.prev[base + 1]);
+    }
+    pre = ld_fe(&a.pre[p]);
+    return 1u;
+  };
+  const uint32_t pl = block_base + (kAffT - 1) * kAffBlock + t;   // last pair of this thread: processed first
+  F inv_run = a.btot[blockIdx.x] * a.others[blockIdx.x * kAffBlock + t];
+  uint2 sb = st.bounds(pl - 2 * kAffBlock);
+  PairIdx ix = st.entries(pl - kAffBlock, st.bounds(pl - kAffBlock));
+  PairIdx cix = st.entries(pl, st.bounds(pl));
+  Affine<F> cP, cQ;
+  F cpre = F::zero();
+  uint32_t cst = gather(pl, cix, cP, cQ, cpre);
+#pragma unroll 1
+  for (int k = kAffT - 1; k >= 0; k--) {
+    const uint32_t p = block_base + k * kAffBlock + t;
+    Affine<F> nP, nQ;
+    F npre = F::zero();
+    uint32_t nst = 0;
+    const PairIdx nix = ix;
+    if (k >= 1) nst = gather(p - kAffBlock, ix, nP, nQ, npre);
+    if (k >= 2) ix = st.entries(p - 2 * kAffBlock, sb);
+    if (k >= 3) sb = st.bounds(p - 3 * kAffBlock);
+    if (cst) {
+      Affine<F> P = cP, Q = cQ;
+      if (a.round == 1) {
+        if (cix.e0 != kNoEntry && (cix.e0 & 1u) && !P.is_inf()) P.y = P.y.neg();
+        if (cix.e1 != kNoEntry && (cix.e1 & 1u) && !Q.is_inf()) Q.y = Q.y.neg();
+      }
+      F d;
+      int kind = aff_denominator(P, Q, d);
+      F inv_d = inv_run * cpre;
+      inv_run = inv_run * d;
+      Affine<F> Rr;
+      if (kind == 1) {
+        F lam = (Q.y - P.y) * inv_d;
+        F x3 = lam.sqr() - P.x - Q.x;
+        Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+      } else if (kind == 2) {
+        F xx = P.x.sqr();
+        F lam = (xx.dbl() + xx) * inv_d;
+        F x3 = lam.sqr() - P.x.dbl();
+        Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+      } else {
+        Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
+      }
+      a.out[p] = Rr;
+    }
+    cP = nP;
+    cQ = nQ;
+    cpre = npre;
+    cst = nst;
+    cix = nix;
+  }
+}
+
 // Tail of the tree (tuning knob B200_AFF_ROUNDS): after fewer than log2(S) affine rounds every slice
 // still holds `q` nodes; LPB lanes per bucket add the (contiguous) nodes of all its slices with XYZZ mixed
 // adds and merge through a shuffle tree.

@@ -412,6 +412,14 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       static const int mf_g2 = getenv("B200_AFF_MINB_FWD_G2") ? atoi(getenv("B200_AFF_MINB_FWD_G2")) : 4;
       const int mb_env = sizeof(F) == 32 ? mb_g1 : mb_g2, mf_env = sizeof(F) == 32 ? mf_g1 : mf_g2;
       static const int pf_env = getenv("B200_AFF_PF") ? atoi(getenv("B200_AFF_PF")) : 0;  // bit 0: forward, bit 1: backward L2 prefetch
+      // experiment (G1 only): software-pipelined kernels with the multiply inlined; bit 0 forward, bit 1 backward
+      static const int sp_env = getenv("B200_AFF_SP") ? atoi(getenv("B200_AFF_SP")) : 0;
+      const bool sp_ok = sizeof(F) == 32 && T == 32;
+      const AffineRound<FqH>& arh = reinterpret_cast<const AffineRound<FqH>&>(ar);   // same layout, inlined multiply
+      if (sp_ok && (sp_env & 1)) {
+        if (mf_env >= 6) k_affine_forward_sp<FqH, 32, 6><<<nb, kAffBlock, 0, st>>>(arh);
+        else k_affine_forward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
+      } else
       if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 1) {
         if (mf_env >= 8) k_affine_forward<F, 32, 8, true><<<nb, kAffBlock, 0, st>>>(ar);
@@ -420,7 +428,10 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       else if (mf_env >= 4) k_affine_forward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
       else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-      if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      if (sp_ok && (sp_env & 2)) {
+        if (mb_env >= 4) k_affine_backward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
+        else k_affine_backward_sp<FqH, 32, 3><<<nb, kAffBlock, 0, st>>>(arh);
+      } else if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 2) {
         if (mb_env >= 5) k_affine_backward<F, 32, 5, true><<<nb, kAffBlock, 0, st>>>(ar);
         else k_affine_backward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
