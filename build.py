@@ -49,18 +49,22 @@ def _run(cmd, log=None):
     return p
 
 
-def build_cuda(force=False):
+# experiment builds, selected at run time with B200_LIB_VARIANT=<name> (go-snark-study_b200/_lib.py); never built by default
+VARIANTS = {"k": ["-DB200_KARATSUBA", "-DB200_NO_PAIRING"]}       # Karatsuba 512-bit products (fp.cuh: mul_full_k)
+
+
+def build_cuda(force=False, variant=None):
     os.makedirs(LIBDIR, exist_ok=True)
-    target = os.path.join(LIBDIR, "libb200snark.so")
+    target = os.path.join(LIBDIR, "libb200snark.so" if not variant else f"libb200snark_{variant}.so")
     if not force and not _newer(target, _all_sources()):
         return target
     if not os.path.exists(NVCC):
         if os.path.exists(target):
             return target          # GPU box without a toolchain change: use the shipped build
         raise RuntimeError("nvcc not found and no prebuilt libb200snark.so")
-    cmd = [NVCC, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    cmd = [NVCC, *NVCC_FLAGS, *(VARIANTS[variant] if variant else []), "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-o", target, *[os.path.join(CSRC, s) for s in CUDA_SOURCES]]
-    _run(cmd, log=os.path.join(LIBDIR, "nvcc_build.log"))
+    _run(cmd, log=os.path.join(LIBDIR, "nvcc_build.log" if not variant else f"nvcc_build_{variant}.log"))
     return target
 
 

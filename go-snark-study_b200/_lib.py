@@ -5,7 +5,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so")
+# B200_LIB_VARIANT=<name> loads an experiment build (build.py VARIANTS) instead of the product library
+_VARIANT = os.environ.get("B200_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so" if not _VARIANT else f"libb200snark_{_VARIANT}.so")
 
 B200_OK = 0
 ERRORS = {-1: "ENODEVICE", -2: "ECUDA", -3: "EINVAL", -4: "ERANGE", -5: "EDIVZERO", -6: "ENOMEM"}

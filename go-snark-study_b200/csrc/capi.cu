@@ -18,7 +18,9 @@
 #include "bucket_affine.cuh"
 #include "poly_host.cuh"
 #include "qap.cuh"
+#ifndef B200_NO_PAIRING
 #include "pairing.cuh"
+#endif
 
 using namespace b200;
 
@@ -689,6 +691,7 @@ int zero_poly_host(size_t n, uint64_t* out) {   // coefficients of prod_{i=1..n}
   return check_err_flag<Fr>("zero_poly");
 }
 
+#ifndef B200_NO_PAIRING
 // ---- pairing / verification -------------------------------------------------------
 __device__ void pairing_from_jacobian(const Fq* g1, const Fq2* g2, F12& out, int* err) {
   bool bad = false;
@@ -840,6 +843,15 @@ int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1,
   CU(cudaMemcpyAsync(ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   return check_err_flag<Fq>("groth16_verify");
 }
+
+#else  // experiment builds without the verifier side (ptxas 12.9 crashes on the pairing kernels under -DB200_KARATSUBA)
+int pairing_batch_host(const uint64_t*, const uint64_t*, size_t, uint64_t*) { return fail(B200_EINVAL, "pairing: not in this build variant"); }
+int fq12_mul_batch_host(const uint64_t*, const uint64_t*, size_t, uint64_t*) { return fail(B200_EINVAL, "fq12_mul: not in this build variant"); }
+int groth16_verify_host(const uint64_t*, size_t, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
+                        const uint64_t*, const uint64_t*, const uint64_t*, size_t, int*) {
+  return fail(B200_EINVAL, "groth16_verify: not in this build variant");
+}
+#endif
 
 template <class F>
 int group_op_host(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
