@@ -414,12 +414,17 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       static const int mf_g2 = getenv("B200_AFF_MINB_FWD_G2") ? atoi(getenv("B200_AFF_MINB_FWD_G2")) : 4;
       const int mb_env = sizeof(F) == 32 ? mb_g1 : mb_g2, mf_env = sizeof(F) == 32 ? mf_g1 : mf_g2;
       static const int pf_env = getenv("B200_AFF_PF") ? atoi(getenv("B200_AFF_PF")) : 0;  // bit 0: forward, bit 1: backward L2 prefetch
-      // experiment (G1 only): software-pipelined kernels with the multiply inlined; bit 0 forward, bit 1 backward
+      // experiment: software-pipelined kernels (operand fetches staged three deep); bit 0 forward, bit 1 backward;
+      // bit 2: keep the out-of-line multiply (all groups) instead of the inlined one (G1 only)
       static const int sp_env = getenv("B200_AFF_SP") ? atoi(getenv("B200_AFF_SP")) : 0;
-      const bool sp_ok = sizeof(F) == 32 && T == 32;
+      const bool sp_inl = !(sp_env & 4);
+      const bool sp_ok = T == 32 && (sizeof(F) == 32 || !sp_inl);
       const AffineRound<FqH>& arh = reinterpret_cast<const AffineRound<FqH>&>(ar);   // same layout, inlined multiply
       if (sp_ok && (sp_env & 1)) {
-        if (mf_env >= 6) k_affine_forward_sp<FqH, 32, 6><<<nb, kAffBlock, 0, st>>>(arh);
+        if (!sp_inl) {
+          if (mf_env >= 6) k_affine_forward_sp<F, 32, 6><<<nb, kAffBlock, 0, st>>>(ar);
+          else k_affine_forward_sp<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
+        } else if (mf_env >= 6) k_affine_forward_sp<FqH, 32, 6><<<nb, kAffBlock, 0, st>>>(arh);
         else k_affine_forward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
       } else
       if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
@@ -431,7 +436,10 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
       if (sp_ok && (sp_env & 2)) {
-        if (mb_env >= 4) k_affine_backward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
+        if (!sp_inl) {
+          if (mb_env >= 4) k_affine_backward_sp<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
+          else k_affine_backward_sp<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
+        } else if (mb_env >= 4) k_affine_backward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
         else k_affine_backward_sp<FqH, 32, 3><<<nb, kAffBlock, 0, st>>>(arh);
       } else if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 2) {
