@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of the next round: validate and time the prepared experiments.
+#   gpurun --timeout 900 -- 'tools/r2_experiments.sh > gpurun_out/r2_experiments.log 2>&1; tail -40 gpurun_out/r2_experiments.log'
+# 1. parity of the pipelined kernels (inlined and out-of-line multiply), 2. bench sweep, 3. the Karatsuba build variant.
+set -u
+cd "$(dirname "$0")/.."
+echo "== parity, B200_AFF_SP=3 (inlined multiply, G1)"
+B200_AFF_SP=3 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
+echo "== parity, B200_AFF_SP=7 (out-of-line multiply, G1 + G2)"
+B200_AFF_SP=7 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
+echo "== bench sweep: ms/step, e2e ms, parity, G1 phase ms, G2 phase ms"
+timeout 500 tools/sweep_env.sh "B200_X=0" "B200_AFF_SP=1" "B200_AFF_SP=2" "B200_AFF_SP=3" "B200_AFF_SP=3 B200_AFF_MINB=3" \
+  "B200_AFF_SP=5" "B200_AFF_SP=6" "B200_AFF_SP=7" "B200_AFF_SP=3 B200_AFF_MINB_FWD=6"
+if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
+  echo "== Karatsuba build variant: parity, then bench"
+  B200_LIB_VARIANT=k timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py tests/test_gpu_poly.py -x -q 2>&1 | tail -2
+  timeout 200 tools/sweep_env.sh "B200_LIB_VARIANT=k" "B200_LIB_VARIANT=k B200_AFF_SP=3"
+else
+  echo "(build the variant first: python -c \"import build; build.build_cuda(variant='k')\")"
+fi
