@@ -507,6 +507,95 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_sp(AffineRo
   }
 }
 
+// ---- EXPERIMENT (off by default, B200_AFF_LR): backward pass ordered for short live ranges -------------------------
+// The backward kernel above fetches both operands (4 field elements) before its first multiply, which for G2 is 64
+// registers of operands alone and makes the 128-register build spill (336 B).  Here the generic case is ordered so
+// that at most ~5 field elements are live: prefix -> 1/d, then the x's -> running inverse, then the y's -> lambda, x3,
+// y3.  Pairs with an absent operand, a zero x (infinity) or equal x's (doubling / P = -Q) take the out-of-line slow path
+// with the original logic.
+template <class F>
+__device__ __noinline__ void aff_backward_slow(const AffineRound<F>& a, uint32_t p, uint32_t npairs, F& inv_run) {
+  Affine<F> P, Q;
+  if (!aff_operands(a, p, npairs, P, Q)) return;
+  F d;
+  int kind = aff_denominator(P, Q, d);
+  F inv_d = inv_run * a.pre[p];
+  inv_run = inv_run * d;
+  Affine<F> Rr;
+  if (kind == 1) {
+    F lam = (Q.y - P.y) * inv_d;
+    F x3 = lam.sqr() - P.x - Q.x;
+    Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+  } else if (kind == 2) {
+    F xx = P.x.sqr();
+    F lam = (xx.dbl() + xx) * inv_d;
+    F x3 = lam.sqr() - P.x.dbl();
+    Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+  } else {
+    Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
+  }
+  a.out[p] = Rr;
+}
+
+template <class F, int kAffT, int MINB>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_lr(AffineRound<F> a) {
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t npairs = nslices << a.q_log;
+  const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);
+  if (block_base >= npairs) return;
+  const uint32_t t = threadIdx.x;
+  F inv_run = a.btot[blockIdx.x] * a.others[blockIdx.x * kAffBlock + t];
+#pragma unroll 1
+  for (int k = kAffT - 1; k >= 0; k--) {
+    const uint32_t p = block_base + k * kAffBlock + t;
+    if (p >= npairs) continue;
+    const uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
+    const Affine<F>*pp = nullptr, *qp = nullptr;
+    uint32_t neg1 = 0, neg2 = 0;
+    if (a.round == 1) {
+      uint32_t s = a.slice_start[slice], e = a.slice_end[slice];
+      uint32_t i0 = s + 2 * j;
+      if (i0 + 1 < e) {
+        uint32_t e0 = a.entries[i0], e1 = a.entries[i0 + 1];
+        pp = &a.table[e0 >> 1];
+        qp = &a.table[e1 >> 1];
+        neg1 = e0 & 1u;
+        neg2 = e1 & 1u;
+      }
+    } else {
+      size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
+      pp = &a.prev[base];
+      qp = &a.prev[base + 1];
+    }
+    bool fast = pp != nullptr;
+    F x1, x2, dx;
+    if (fast) {
+      x1 = a.round == 1 ? ld_x_gather(pp) : ld_fe(&pp->x);
+      x2 = a.round == 1 ? ld_x_gather(qp) : ld_fe(&qp->x);
+      dx = x2 - x1;
+      fast = !(x1.is_zero() || x2.is_zero() || dx.is_zero());
+    }
+    if (!fast) {
+      aff_backward_slow(a, p, npairs, inv_run);
+      continue;
+    }
+    F lam;
+    {
+      F inv_d = inv_run * ld_fe(&a.pre[p]);
+      inv_run = inv_run * dx;
+      F y2 = ld_fe(&qp->y);
+      if (neg2) y2 = y2.neg();
+      F y1 = ld_fe(&pp->y);
+      if (neg1) y1 = y1.neg();
+      lam = (y2 - y1) * inv_d;
+    }
+    F x3 = lam.sqr() - x1 - x2;
+    F y1 = ld_fe(&pp->y);                     // re-read (L1 hit) instead of keeping it live across two multiplies
+    if (neg1) y1 = y1.neg();
+    a.out[p] = Affine<F>{x3, lam * (x1 - x3) - y1};
+  }
+}
+
 // Tail of the tree (tuning knob B200_AFF_ROUNDS): after fewer than log2(S) affine rounds every slice
 // still holds `q` nodes; LPB lanes per bucket add the (contiguous) nodes of all its slices with XYZZ mixed
 // adds and merge through a shuffle tree.

@@ -435,7 +435,12 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       else if (mf_env >= 4) k_affine_forward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
       else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-      if (sp_ok && (sp_env & 2)) {
+      static const int lr_env = getenv("B200_AFF_LR") ? atoi(getenv("B200_AFF_LR")) : 0;  // experiment: bit 0 G1, bit 1 G2
+      if (T == 32 && (lr_env & (sizeof(F) == 32 ? 1 : 2))) {
+        if (mb_env >= 6) k_affine_backward_lr<F, 32, 6><<<nb, kAffBlock, 0, st>>>(ar);
+        else if (mb_env >= 5) k_affine_backward_lr<F, 32, 5><<<nb, kAffBlock, 0, st>>>(ar);
+        else k_affine_backward_lr<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
+      } else if (sp_ok && (sp_env & 2)) {
         if (!sp_inl) {
           if (mb_env >= 4) k_affine_backward_sp<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
           else k_affine_backward_sp<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);

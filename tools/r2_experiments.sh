@@ -8,7 +8,11 @@ echo "== parity, B200_AFF_SP=3 (inlined multiply, G1)"
 B200_AFF_SP=3 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
 echo "== parity, B200_AFF_SP=7 (out-of-line multiply, G1 + G2)"
 B200_AFF_SP=7 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
+echo "== parity, B200_AFF_LR=3 (short-live-range backward, G1 + G2)"
+B200_AFF_LR=3 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
 echo "== bench sweep: ms/step, e2e ms, parity, G1 phase ms, G2 phase ms"
+timeout 400 tools/sweep_env.sh "B200_AFF_LR=1" "B200_AFF_LR=2" "B200_AFF_LR=3" "B200_AFF_LR=3 B200_AFF_MINB_G2=5" \
+  "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=5" "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=6"
 timeout 500 tools/sweep_env.sh "B200_X=0" "B200_AFF_SP=1" "B200_AFF_SP=2" "B200_AFF_SP=3" "B200_AFF_SP=3 B200_AFF_MINB=3" \
   "B200_AFF_SP=5" "B200_AFF_SP=6" "B200_AFF_SP=7" "B200_AFF_SP=3 B200_AFF_MINB_FWD=6"
 if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
