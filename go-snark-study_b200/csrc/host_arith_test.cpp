@@ -87,10 +87,24 @@ void t_redc_wide(int field, int k, const uint32_t* t, uint32_t* out) {
 int t_geq(int field, const uint32_t* a) { return field == 0 ? load<Fq>(a).geq_modulus() : load<Fr>(a).geq_modulus(); }
 // pairing of AFFINE standard-form inputs: g1 = (x, y), g2 = (x.c0, x.c1, y.c0, y.c1); out = 12 field elements in
 // the reference's [2][3][2] order
-void t_pairing(const uint32_t* g1, const uint32_t* g2, uint32_t* out) {
+static void pairing_common(const uint32_t* g1, const uint32_t* g2, uint32_t* out, bool fast);
+void t_pairing(const uint32_t* g1, const uint32_t* g2, uint32_t* out) { pairing_common(g1, g2, out, false); }
+// same pairing with the fast final exponentiation (must give the same 12 field elements)
+void t_pairing_fast(const uint32_t* g1, const uint32_t* g2, uint32_t* out) { pairing_common(g1, g2, out, true); }
+// F_q^12 helpers of the fast path: op 0 inverse, 1..3 Frobenius^op, 4 x^u; in/out 12 standard-form field elements
+void t_f12_op(int op, const uint32_t* in, uint32_t* out) {
+  F12 x;
+  F2* xs[6] = {&x.a.a, &x.a.b, &x.a.c, &x.b.a, &x.b.b, &x.b.c};
+  for (int k = 0; k < 6; k++) *xs[k] = load<F2>(in + 16 * k).to_mont();
+  F12 r = op == 0 ? f12_inverse(x) : op == 1 ? f12_frobenius<1>(x) : op == 2 ? f12_frobenius<2>(x)
+          : op == 3 ? f12_frobenius<3>(x) : f12_exp_u(x);
+  const F2* parts[6] = {&r.a.a, &r.a.b, &r.a.c, &r.b.a, &r.b.b, &r.b.c};
+  for (int k = 0; k < 6; k++) store(out + 16 * k, parts[k]->from_mont());
+}
+static void pairing_common(const uint32_t* g1, const uint32_t* g2, uint32_t* out, bool fast) {
   F2::B px = load<F2::B>(g1).to_mont(), py = load<F2::B>(g1 + 8).to_mont();
   F2 qx = load<F2>(g2).to_mont(), qy = load<F2>(g2 + 16).to_mont();
-  F12 f = pairing_affine(px, py, qx, qy);
+  F12 f = pairing_affine(px, py, qx, qy, fast);
   const F2* parts[6] = {&f.a.a, &f.a.b, &f.a.c, &f.b.a, &f.b.b, &f.b.c};
   for (int k = 0; k < 6; k++) store(out + 16 * k, parts[k]->from_mont());
 }

@@ -15,6 +15,8 @@ timeout 400 tools/sweep_env.sh "B200_AFF_LR=1" "B200_AFF_LR=2" "B200_AFF_LR=3" "
   "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=5" "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=6"
 timeout 500 tools/sweep_env.sh "B200_X=0" "B200_AFF_SP=1" "B200_AFF_SP=2" "B200_AFF_SP=3" "B200_AFF_SP=3 B200_AFF_MINB=3" \
   "B200_AFF_SP=5" "B200_AFF_SP=6" "B200_AFF_SP=7" "B200_AFF_SP=3 B200_AFF_MINB_FWD=6"
+echo "== fast final exponentiation: parity on the goldens, then timing of the verify tests"
+B200_FAST_FINAL_EXP=1 timeout 200 python -m pytest tests/test_gpu_verify.py -x -q --durations=4 2>&1 | tail -8
 if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
   echo "== Karatsuba build variant: parity, then bench"
   B200_LIB_VARIANT=k timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py tests/test_gpu_poly.py -x -q 2>&1 | tail -2
