@@ -405,7 +405,17 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       ar.out = bufs[(r - 1) & 1];
       uint64_t npairs_max = nsl_bound << ar.q_log;
       static const int t_env = getenv("B200_AFF_T") ? atoi(getenv("B200_AFF_T")) : 32;  // tuning knob
-      const unsigned T = t_env == 16 ? 16 : 32;
+      unsigned T = t_env == 16 ? 16 : 32;
+      // experiment (off by default): the late rounds have too few pairs to fill the GPU with 32 pairs per thread (round 6
+      // of a 2^20 MSM: 64 CTAs for 148 SMs, and every thread still walks 32 dependent pairs) -> fewer pairs per thread
+      // when the round would launch fewer than B200_AFF_TSMALL CTAs.  (T = 8 only from round 2 on: the scratch arrays
+      // are sized for >= 16 pairs per thread in round 1.)
+      static const int tsmall_env = getenv("B200_AFF_TSMALL") ? atoi(getenv("B200_AFF_TSMALL")) : 0;
+      if (tsmall_env && T == 32) {
+        uint64_t nb32 = (npairs_max + kAffBlock * 32 - 1) / (kAffBlock * 32);
+        if (nb32 * 4 < (uint64_t)tsmall_env && r >= 2) T = 8;
+        else if (nb32 < (uint64_t)tsmall_env) T = 16;
+      }
       unsigned nb = (unsigned)((npairs_max + kAffBlock * T - 1) / (kAffBlock * T));
       // CTAs/SM bounds (register caps) of the backward / forward kernels; G2 variants above 4 spill (ptxas -v)
       static const int mb_g1 = getenv("B200_AFF_MINB") ? atoi(getenv("B200_AFF_MINB")) : 5;          // 20.8 -> 19.6 ms / 2^20 proof
@@ -427,7 +437,8 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
         } else if (mf_env >= 6) k_affine_forward_sp<FqH, 32, 6><<<nb, kAffBlock, 0, st>>>(arh);
         else k_affine_forward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
       } else
-      if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      if (T == 8) k_affine_forward<F, 8><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 1) {
         if (mf_env >= 8) k_affine_forward<F, 32, 8, true><<<nb, kAffBlock, 0, st>>>(ar);
         else k_affine_forward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
@@ -446,7 +457,8 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
           else k_affine_backward_sp<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
         } else if (mb_env >= 4) k_affine_backward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
         else k_affine_backward_sp<FqH, 32, 3><<<nb, kAffBlock, 0, st>>>(arh);
-      } else if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
+      } else if (T == 8) k_affine_backward<F, 8><<<nb, kAffBlock, 0, st>>>(ar);
+      else if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
       else if (pf_env & 2) {
         if (mb_env >= 5) k_affine_backward<F, 32, 5, true><<<nb, kAffBlock, 0, st>>>(ar);
         else k_affine_backward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);

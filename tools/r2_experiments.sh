@@ -15,6 +15,10 @@ timeout 400 tools/sweep_env.sh "B200_AFF_LR=1" "B200_AFF_LR=2" "B200_AFF_LR=3" "
   "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=5" "B200_AFF_LR=3 B200_AFF_MINB=6 B200_AFF_MINB_G2=6"
 timeout 500 tools/sweep_env.sh "B200_X=0" "B200_AFF_SP=1" "B200_AFF_SP=2" "B200_AFF_SP=3" "B200_AFF_SP=3 B200_AFF_MINB=3" \
   "B200_AFF_SP=5" "B200_AFF_SP=6" "B200_AFF_SP=7" "B200_AFF_SP=3 B200_AFF_MINB_FWD=6"
+echo "== fewer pairs per thread in the late rounds (B200_AFF_TSMALL = CTA threshold): parity, bench, stand-alone MSMs"
+B200_AFF_TSMALL=1184 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
+timeout 200 tools/sweep_env.sh "B200_AFF_TSMALL=600" "B200_AFF_TSMALL=1184" "B200_AFF_TSMALL=2400"
+for ts in 0 1184; do echo -n "G1 2^20 stand-alone, TSMALL=$ts: "; B200_AFF_TSMALL=$ts timeout 100 python tools/quick_msm_bench.py 1 20 16 2>&1 | tail -1; done
 echo "== fast final exponentiation: parity on the goldens, then timing of the verify tests"
 B200_FAST_FINAL_EXP=1 timeout 200 python -m pytest tests/test_gpu_verify.py -x -q --durations=4 2>&1 | tail -8
 if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
