@@ -34,3 +34,18 @@ def test_fails_loudly_without_gpu():
     rc = _lib.lib().b200_init(0)
     assert rc == -1
     assert b"no CPU fallback" in _lib.lib().b200_last_error()
+
+
+def test_go_binding_and_docs_name_only_declared_symbols():
+    """Every C.b200_* the cgo sketch (go/) and INTEGRATION.md call is declared in include/b200snark.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "b200snark.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header)) | {"b200_pk_t", "b200_bases_t"}
+    used = set()
+    for rel in ("INTEGRATION.md", os.path.join("go", "b200", "b200.go"), os.path.join("go", "groth16_generateproofs.go.txt")):
+        path = os.path.join(root, rel)
+        if os.path.exists(path):
+            used |= set(re.findall(r"\bC\.(b200_[a-z0-9_]+)", open(path).read()))
+    assert used, "no cgo calls found"
+    assert used <= declared, sorted(used - declared)
