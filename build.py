@@ -79,6 +79,18 @@ def build_host_arith(force=False):
     return target
 
 
+def build_host_kernels(force=False):
+    """g++ build of the per-thread bucket kernels over csrc/host_stub (CPU test vehicle, tests/test_host_kernels.py)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    target = os.path.join(LIBDIR, "libb200_host_kernels.so")
+    if not force and not _newer(target, _all_sources() + [os.path.join(CSRC, "host_stub", "cuda_runtime.h")]):
+        return target
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-x", "c++", "-shared", "-fPIC", "-Wno-psabi", "-I", os.path.join(CSRC, "host_stub"),
+           "-I", CSRC, "-o", target, os.path.join(CSRC, "host_kernel_test.cpp")]
+    _run(cmd)
+    return target
+
+
 def build_oracle(force=False):
     out = os.path.join(ORACLE, "_build")
     os.makedirs(out, exist_ok=True)

@@ -160,7 +160,13 @@ __device__ __forceinline__ PairIdx aff_pair_idx(const AffineRound<F>& a, uint32_
   }
   return r;
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 template <int BYTES>
 __device__ __forceinline__ void prefetch_span(const void* p) {
 #pragma unroll

@@ -1,0 +1,212 @@
+// CPU test vehicle for the per-thread bucket kernels of bucket_affine.cuh (g++, csrc/host_stub): the backward-pass
+// variants — the product kernel and the experiment kernels k_affine_backward_lr / _sp — are run one emulated thread at
+// a time over all rounds of a small slice forest, against a plain host restatement of the forward pass.  What this
+// checks is the kernels' own index logic (pair <-> slice <-> entry mapping, staging queues, fast/slow path split,
+// sign and infinity handling); the field arithmetic underneath is covered by host_arith_test.cpp.
+// Test infrastructure only: never linked into libb200snark.
+#include "host_stub/cuda_runtime.h"
+
+#include <pthread.h>
+
+#include <thread>
+#include <vector>
+
+#include "bucket_affine.cuh"
+
+using namespace b200;
+
+// ---- CTA-at-a-time emulation: one OS thread per CUDA thread, barriers for __syncthreads and the warp shuffles ------
+namespace {
+constexpr int kMaxWarps = 8;
+pthread_barrier_t g_block_bar, g_warp_bar[kMaxWarps];
+uint32_t g_xchg[kMaxWarps][32];
+bool g_cta_mode = false;
+}  // namespace
+void stub_syncthreads() {
+  if (!g_cta_mode) stub_abort("__syncthreads outside run_cta");
+  pthread_barrier_wait(&g_block_bar);
+}
+uint32_t stub_shfl(uint32_t v, int arg, int mode, int width) {
+  if (!g_cta_mode) stub_abort("warp shuffle outside run_cta");
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  g_xchg[warp][lane] = v;
+  pthread_barrier_wait(&g_warp_bar[warp]);
+  int seg = lane & ~(width - 1), pos = lane & (width - 1), src;
+  if (mode == 0) src = seg + (arg & (width - 1));
+  else if (mode == 1) src = pos - arg >= 0 ? lane - arg : lane;
+  else src = pos + arg < width ? lane + arg : lane;
+  uint32_t r = g_xchg[warp][src];
+  pthread_barrier_wait(&g_warp_bar[warp]);
+  return r;
+}
+namespace {
+// run `kernel()` for every thread of CTA `b` (nthreads a multiple of 32, <= 256)
+template <class K>
+void run_cta(unsigned b, unsigned nthreads, unsigned nblocks, K kernel) {
+  pthread_barrier_init(&g_block_bar, nullptr, nthreads);
+  for (unsigned w = 0; w < nthreads / 32; w++) pthread_barrier_init(&g_warp_bar[w], nullptr, 32);
+  g_cta_mode = true;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nthreads; t++)
+    th.emplace_back([=] {
+      threadIdx.x = t;
+      blockIdx.x = b;
+      blockDim.x = nthreads;
+      gridDim.x = nblocks;
+      kernel();
+    });
+  for (auto& x : th) x.join();
+  g_cta_mode = false;
+  pthread_barrier_destroy(&g_block_bar);
+  for (unsigned w = 0; w < nthreads / 32; w++) pthread_barrier_destroy(&g_warp_bar[w]);
+}
+
+template <class F>
+F load_std(const uint32_t* p) {
+  F v;
+  std::memcpy(&v, p, sizeof(F));
+  return v.to_mont();
+}
+template <class F>
+void store_std(uint32_t* p, const F& v) {
+  F s = v.from_mont();
+  std::memcpy(p, &s, sizeof(F));
+}
+
+// forward pass, restated: pre[p], others[thread], btot[block] exactly as k_affine_forward defines them
+template <class F, int T>
+void forward_reference(const AffineRound<F>& a, uint32_t npairs, unsigned nb) {
+  for (unsigned b = 0; b < nb; b++) {
+    uint32_t block_base = b * (kAffBlock * T);
+    if (block_base >= npairs) {
+      a.btot[b] = F::one();
+      continue;
+    }
+    std::vector<F> tot(kAffBlock, F::one());
+    for (unsigned t = 0; t < kAffBlock; t++) {
+      F run = F::one();
+      for (int k = 0; k < T; k++) {
+        uint32_t p = block_base + k * kAffBlock + t;
+        Affine<F> P, Q;
+        F d;
+        if (aff_operands(a, p, npairs, P, Q)) {
+          aff_denominator(P, Q, d);
+          F dx;                                   // the x-only forward path must agree with the full one
+          if (!aff_forward_denominator(a, p, npairs, dx) || !(dx == d)) std::abort();
+          a.pre[p] = run;
+          run = run * d;
+        }
+      }
+      tot[t] = run;
+    }
+    F all = F::one();
+    for (unsigned t = 0; t < kAffBlock; t++) all = all * tot[t];
+    for (unsigned t = 0; t < kAffBlock; t++) {
+      F o = F::one();
+      for (unsigned u = 0; u < kAffBlock; u++)
+        if (u != t) o = o * tot[u];
+      a.others[b * kAffBlock + t] = o;
+    }
+    a.btot[b] = all.inverse();                    // k_affine_invert
+  }
+}
+
+// the forward kernels themselves (block scan included), CTA by CTA: 0 product kernel, 1 L2-prefetch variant, 2 _sp
+template <class F, int T>
+void run_forward(int variant, const AffineRound<F>& a, unsigned nb) {
+  for (unsigned b = 0; b < nb; b++)
+    run_cta(b, kAffBlock, nb, [&] {
+      if (variant == 0) k_affine_forward<F, T, 1, false>(a);
+      else if (variant == 1) k_affine_forward<F, T, 1, true>(a);
+      else k_affine_forward_sp<F, T, 1>(a);
+    });
+  for (unsigned b = 0; b < nb; b++) a.btot[b] = a.btot[b].inverse();   // k_affine_invert
+}
+
+template <class F, int T>
+void run_backward(int variant, const AffineRound<F>& a, unsigned nb) {
+  blockDim.x = kAffBlock;
+  gridDim.x = nb;
+  for (unsigned b = 0; b < nb; b++)
+    for (unsigned t = 0; t < kAffBlock; t++) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      if (variant == 0) k_affine_backward<F, T, 1, false>(a);
+      else if (variant == 1) k_affine_backward_lr<F, T, 1>(a);
+      else if (variant == 2) k_affine_backward_sp<F, T, 1>(a);
+      else k_affine_backward<F, T, 1, true>(a);   // L2-prefetch variant (prefetches are no-ops here)
+    }
+}
+
+template <class F, int T>
+int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
+                  const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
+  constexpr int W = sizeof(F) / 4;
+  std::vector<Affine<F>> table(n_pts);
+  for (uint32_t i = 0; i < n_pts; i++) {
+    table[i].x = load_std<F>(table_std + (size_t)i * 2 * W);
+    table[i].y = load_std<F>(table_std + (size_t)i * 2 * W + W);
+  }
+  const uint32_t S = 1u << R;
+  std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
+  std::vector<F> pre((size_t)nslices * (S / 2));
+  unsigned nb_max = (nslices * (S / 2) + kAffBlock * T - 1) / (kAffBlock * T);
+  std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
+  AffineRound<F> ar{};
+  ar.table = table.data();
+  ar.entries = entries;
+  ar.slice_start = slice_start;
+  ar.slice_end = slice_end;
+  ar.nslices_ptr = &nslices;
+  ar.pre = pre.data();
+  ar.others = others.data();
+  ar.btot = btot.data();
+  const Affine<F>* prev = nullptr;
+  Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
+  for (uint32_t r = 1; r <= R; r++) {
+    ar.round = r;
+    ar.q_log = R - r;
+    ar.prev = prev;
+    ar.out = bufs[(r - 1) & 1];
+    uint32_t npairs = nslices << ar.q_log;
+    unsigned nb = (npairs + kAffBlock * T - 1) / (kAffBlock * T);
+    if (fwd_variant < 0) {
+      forward_reference<F, T>(ar, npairs, nb);
+    } else {
+      // kernel forward pass, checked against the restatement (pre, others, 1/btot) before it is consumed
+      run_forward<F, T>(fwd_variant, ar, nb);
+      std::vector<F> pre_k(pre), others_k(others), btot_k(btot);
+      forward_reference<F, T>(ar, npairs, nb);
+      for (uint32_t p = 0; p < npairs; p++)
+        if (!(pre_k[p] == pre[p])) return 10 + (int)r;
+      for (unsigned b = 0; b < nb; b++) {
+        if (!(btot_k[b] == btot[b])) return 20 + (int)r;
+        if (b * (kAffBlock * T) >= npairs) continue;
+        for (unsigned t = 0; t < kAffBlock; t++)
+          if (!(others_k[b * kAffBlock + t] == others[b * kAffBlock + t])) return 30 + (int)r;
+      }
+    }
+    run_backward<F, T>(variant, ar, nb);
+    prev = ar.out;
+  }
+  for (uint32_t s = 0; s < nslices; s++) {
+    store_std(out_std + (size_t)s * 2 * W, prev[s].x);
+    store_std(out_std + (size_t)s * 2 * W + W, prev[s].y);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+// group: 1 = G1 (F_q), 2 = G2 (F_q^2); variant: 0 product backward kernel, 1 _lr, 2 _sp, 3 prefetch variant; T in {8, 32}
+// fwd_variant: -1 = host restatement of the forward pass; 0 / 1 / 2 = run the forward KERNEL (product, prefetch, _sp)
+// CTA by CTA and compare its pre / others / btot with the restatement (return code 10+r, 20+r, 30+r on a mismatch in round r)
+int t_affine_rounds(int group, int variant, int fwd_variant, int T, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries,
+                    const uint32_t* slice_start, const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
+  if (group == 1 && T == 8) return affine_rounds<Fq, 8>(variant, fwd_variant, table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+  if (group == 1 && T == 32) return affine_rounds<Fq, 32>(variant, fwd_variant, table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+  if (group == 2 && T == 8) return affine_rounds<Fq2, 8>(variant, fwd_variant, table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+  return -1;
+}
+}

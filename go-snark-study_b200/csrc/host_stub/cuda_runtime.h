@@ -1,0 +1,43 @@
+// TEST VEHICLE ONLY (g++, no CUDA): just enough of the CUDA execution model to run the kernels of bucket_affine.cuh
+// on the CPU.  Per-thread kernels run one emulated thread at a time (the test sets threadIdx / blockIdx); kernels that
+// synchronise or shuffle run one CTA at a time with one OS thread per CUDA thread, __syncthreads and the warp shuffles
+// being barriers + an exchange buffer supplied by the test (stub_syncthreads / stub_shfl, host_kernel_test.cpp).
+// Nothing in the product build includes this file: nvcc resolves <cuda_runtime.h> to the real header.
+#pragma once
+#ifdef __CUDACC__
+#error "host_stub/cuda_runtime.h is for the g++ test build only"
+#endif
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct Dim3Stub { unsigned x = 0, y = 0, z = 0; };
+inline thread_local Dim3Stub threadIdx, blockIdx, blockDim, gridDim;
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+typedef void* cudaStream_t;
+
+[[noreturn]] inline void stub_abort(const char* what) { std::fprintf(stderr, "host stub: %s is not emulated\n", what); std::abort(); }
+// provided by the test translation unit (CTA-at-a-time emulation); mode 0 = idx, 1 = up, 2 = down
+void stub_syncthreads();
+uint32_t stub_shfl(uint32_t v, int arg, int mode, int width);
+inline void __syncthreads() { stub_syncthreads(); }
+inline uint32_t __shfl_sync(unsigned, uint32_t v, int lane, int width = 32) { return stub_shfl(v, lane, 0, width); }
+inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 1, width); }
+inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 2, width); }
+inline unsigned __ballot_sync(unsigned, int) { stub_abort("__ballot_sync"); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }

@@ -36,7 +36,12 @@ namespace b200 {
 // 256-bit global loads (sm_100+: LDG.E.ENL2.256) for 32 B-aligned field elements.
 __device__ __forceinline__ void ld256(const void* p, uint32_t* o) {
   uint64_t a, b, c, d;
+#ifdef __CUDA_ARCH__
   asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+#else  // g++ test vehicle (csrc/host_stub)
+  const uint64_t* q = static_cast<const uint64_t*>(p);
+  a = q[0]; b = q[1]; c = q[2]; d = q[3];
+#endif
   o[0] = (uint32_t)a; o[1] = (uint32_t)(a >> 32);
   o[2] = (uint32_t)b; o[3] = (uint32_t)(b >> 32);
   o[4] = (uint32_t)c; o[5] = (uint32_t)(c >> 32);
@@ -46,7 +51,12 @@ __device__ __forceinline__ void ld256(const void* p, uint32_t* o) {
 // the default pulls the whole 128-byte line from HBM (ncu: 2.1 GB read for 1.07 GB of points).
 __device__ __forceinline__ void ld256_g64(const void* p, uint32_t* o) {
   uint64_t a, b, c, d;
+#ifdef __CUDA_ARCH__
   asm volatile("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+#else
+  const uint64_t* q = static_cast<const uint64_t*>(p);
+  a = q[0]; b = q[1]; c = q[2]; d = q[3];
+#endif
   o[0] = (uint32_t)a; o[1] = (uint32_t)(a >> 32);
   o[2] = (uint32_t)b; o[3] = (uint32_t)(b >> 32);
   o[4] = (uint32_t)c; o[5] = (uint32_t)(c >> 32);

@@ -1,0 +1,118 @@
+"""CPU: the per-thread bucket kernels of csrc/bucket_affine.cuh — the product backward kernel and the experiment
+variants (_lr: short live ranges, _sp: three-deep staged fetches, prefetch) — run one emulated thread at a time over all
+rounds of a small slice forest (csrc/host_kernel_test.cpp over csrc/host_stub), against the oracle's group sums.
+Covers the kernels' index logic: pair <-> slice <-> entry mapping, signs, infinity operands, doublings, cancellations,
+ragged and empty slices, several CTAs, and that the x-only forward denominators equal the full ones."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import build as b200build
+from oracle import ref_py as o
+
+R_ = o.R
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return ctypes.CDLL(b200build.build_host_kernels())
+
+
+def _u32(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint32).copy()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _scenario(group, R, nslices, seed):
+    G = o.BN.G1 if group == 1 else o.BN.G2
+    rng = random.Random(seed)
+    npts = 40
+    pts = [G.affine(G.mul_scalar(G.G, rng.randrange(1, R_)))[:2] for _ in range(npts - 2)]
+    zero = (0, 0) if group == 1 else ((0, 0), (0, 0))
+    pts += [zero, pts[3]]                                   # an infinity point and a repeated point in the table
+    S = 1 << R
+    slices = [[], [(0, 0)], [(0, 0), (0, 0)], [(1, 0), (1, 1)], [(2, 0)] * 4, [(npts - 2, 0), (5, 1)], [(5, 0), (npts - 2, 1)],
+              [(3, 0), (npts - 1, 0)], [(3, 0), (npts - 1, 1), (7, 0)], [(i % npts, i & 1) for i in range(S)],
+              [(4, 0), (4, 0), (4, 1), (4, 1)], [(npts - 2, 0), (npts - 2, 1)]]
+    slices = [s[:S] for s in slices]
+    while len(slices) < nslices:
+        cnt = rng.choice([0, 1, 2, 3, S - 1, S, rng.randrange(S + 1)])
+        slices.append([(rng.randrange(npts), rng.randrange(2)) for _ in range(cnt)])
+    rng.shuffle(slices)
+    entries, starts, ends = [], [], []
+    for s in slices:
+        starts.append(len(entries))
+        entries += [(i << 1) | sg for i, sg in s]
+        ends.append(len(entries))
+    entries += [0] * 4
+    exp = []
+    for s in slices:
+        acc = G.zero3()
+        one = 1 if group == 1 else (1, 0)
+        for i, sg in s:
+            if pts[i] == zero:
+                continue
+            p = (pts[i][0], pts[i][1], one)
+            acc = G.add_or_double(acc, G.neg(p) if sg else p) if hasattr(G, "add_or_double") else _add(G, acc, G.neg(p) if sg else p)
+        exp.append(zero if G.is_zero(acc) else G.affine(acc)[:2])
+    flat = []
+    for p in pts:
+        for c in p:
+            flat.extend(c if isinstance(c, tuple) else (c,))
+    return _u32(flat), npts, np.array(entries, dtype=np.uint32), np.array(starts, dtype=np.uint32), np.array(ends, dtype=np.uint32), exp
+
+
+def _add(G, a, b):
+    """Group addition that also doubles (the reference's Add returns infinity for P + P)."""
+    if G.is_zero(a):
+        return b
+    if G.is_zero(b):
+        return a
+    if G.affine(a)[:2] == G.affine(b)[:2]:
+        return G.double(a)
+    return G.add(a, b)
+
+
+def _run(lib, group, variant, T, R, nslices, seed, fwd=-1):
+    table, npts, entries, starts, ends, exp = _scenario(group, R, nslices, seed)
+    w = 8 if group == 1 else 16
+    out = np.zeros(nslices * 2 * w, dtype=np.uint32)
+    rc = lib.t_affine_rounds(group, variant, fwd, T, _ptr(table), npts, _ptr(entries), _ptr(starts), _ptr(ends), nslices, R, _ptr(out))
+    assert rc == 0
+    raw = out.tobytes()
+    vals = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(len(raw) // 32)]
+    got = []
+    for s in range(nslices):
+        v = vals[s * (2 * w // 8):(s + 1) * (2 * w // 8)]
+        got.append((v[0], v[1]) if group == 1 else ((v[0], v[1]), (v[2], v[3])))
+    assert got == exp
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("T,R,nslices", [(8, 4, 300), (8, 3, 37), (32, 5, 520)])
+def test_g1_backward_variants(lib, variant, T, R, nslices):
+    _run(lib, 1, variant, T, R, nslices, seed=100 * T + R)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_g2_backward_variants(lib, variant):
+    _run(lib, 2, variant, 8, 3, 70, seed=9)
+
+
+@pytest.mark.parametrize("fwd", [0, 1, 2])
+@pytest.mark.parametrize("T,R,nslices", [(8, 4, 300), (32, 5, 520)])
+def test_g1_forward_kernels_cta_emulation(lib, fwd, T, R, nslices):
+    """The forward KERNELS (x-only denominators, per-thread prefix products, warp-shuffle + shared-memory block scan;
+    product / prefetch / _sp variants) run CTA by CTA with one OS thread per CUDA thread; their pre / others / btot equal
+    the host restatement in every round, and the proof-of-the-pudding sums come out right."""
+    _run(lib, 1, 0, T, R, nslices, seed=7 * T + R, fwd=fwd)
+
+
+def test_g2_forward_kernel_cta_emulation(lib):
+    _run(lib, 2, 0, 8, 3, 70, seed=11, fwd=0)
+    _run(lib, 2, 1, 8, 3, 70, seed=12, fwd=2)
