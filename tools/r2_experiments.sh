@@ -26,5 +26,5 @@ if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
   B200_LIB_VARIANT=k timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py tests/test_gpu_poly.py -x -q 2>&1 | tail -2
   timeout 200 tools/sweep_env.sh "B200_LIB_VARIANT=k" "B200_LIB_VARIANT=k B200_AFF_SP=3"
 else
-  echo "(build the variant first: python -c \"import build; build.build_cuda(variant='k')\")"
+  echo "(build the variant first, in the CPU container: python -c \"import build; build.build_cuda(variant='k')\")"
 fi
