@@ -39,6 +39,16 @@ uint32_t stub_shfl(uint32_t v, int arg, int mode, int width) {
   pthread_barrier_wait(&g_warp_bar[warp]);
   return r;
 }
+unsigned stub_ballot(int pred) {
+  if (!g_cta_mode) stub_abort("__ballot_sync outside run_cta");
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  g_xchg[warp][lane] = pred ? 1u : 0u;
+  pthread_barrier_wait(&g_warp_bar[warp]);
+  unsigned r = 0;
+  for (int l = 0; l < 32; l++) r |= g_xchg[warp][l] << l;
+  pthread_barrier_wait(&g_warp_bar[warp]);
+  return r;
+}
 namespace {
 // run `kernel()` for every thread of CTA `b` (nthreads a multiple of 32, <= 256)
 template <class K>
@@ -196,9 +206,45 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   return 0;
 }
 
+// Back end of an MSM after the accumulation: slices -> buckets (k_merge_slices_affine), sum_b b*S_b by segments
+// (k_bucket_reduce), tree sum (k_sum_points, one or two levels like launch_tree_sum), normalisation (k_finalize).
+template <class F>
+int msm_tail(const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t nbuckets, uint32_t seg, uint32_t* out_std) {
+  constexpr int W = sizeof(F) / 4;
+  uint32_t nsl = slice_off[nbuckets + 1];
+  std::vector<Affine<F>> pts(nsl ? nsl : 1);
+  for (uint32_t i = 0; i < nsl; i++) {
+    pts[i].x = load_std<F>(slice_pts_std + (size_t)i * 2 * W);
+    pts[i].y = load_std<F>(slice_pts_std + (size_t)i * 2 * W + W);
+  }
+  std::vector<XYZZ<F>> buckets(nbuckets);
+  SliceTables st{const_cast<uint32_t*>(slice_off), nullptr, nullptr};
+  unsigned nb = (nbuckets + 127) / 128;
+  for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_merge_slices_affine<F>(pts.data(), st, nbuckets, buckets.data()); });
+  uint32_t nseg = (nbuckets + seg - 1) / seg;
+  std::vector<XYZZ<F>> partials((size_t)nseg + 1024);
+  nb = (nseg + 127) / 128;
+  for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_bucket_reduce<F>(buckets.data(), nbuckets, seg, partials.data(), nseg); });
+  XYZZ<F> total;
+  if (nseg <= 64) {  // (the library switches at 1024; a low threshold here exercises the two-level path on small inputs)
+    run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data(), nseg, nseg, &total); });
+  } else {
+    uint32_t per = 32, nb2 = (nseg + per - 1) / per;
+    for (unsigned b = 0; b < nb2; b++) run_cta(b, 256, nb2, [&] { k_sum_points<F>(partials.data(), nseg, per, partials.data() + nseg); });
+    run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data() + nseg, nb2, nb2, &total); });
+  }
+  F out[3];
+  run_cta(0, 32, 1, [&] { k_finalize<F>(&total, out); });
+  std::memcpy(out_std, out, sizeof out);
+  return 0;
+}
 }  // namespace
 
 extern "C" {
+int t_msm_tail(int group, const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t nbuckets, uint32_t seg, uint32_t* out_std) {
+  return group == 1 ? msm_tail<Fq>(slice_pts_std, slice_off, nbuckets, seg, out_std)
+                    : msm_tail<Fq2>(slice_pts_std, slice_off, nbuckets, seg, out_std);
+}
 // group: 1 = G1 (F_q), 2 = G2 (F_q^2); variant: 0 product backward kernel, 1 _lr, 2 _sp, 3 prefetch variant; T in {8, 32}
 // fwd_variant: -1 = host restatement of the forward pass; 0 / 1 / 2 = run the forward KERNEL (product, prefetch, _sp)
 // CTA by CTA and compare its pre / others / btot with the restatement (return code 10+r, 20+r, 30+r on a mismatch in round r)

@@ -34,10 +34,15 @@ inline void __syncthreads() { stub_syncthreads(); }
 inline uint32_t __shfl_sync(unsigned, uint32_t v, int lane, int width = 32) { return stub_shfl(v, lane, 0, width); }
 inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 1, width); }
 inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 2, width); }
-inline unsigned __ballot_sync(unsigned, int) { stub_abort("__ballot_sync"); }
+unsigned stub_ballot(int pred);
+inline unsigned __ballot_sync(unsigned, int pred) { return stub_ballot(pred); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
-template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T atomicMax(T* p, T v) {
+  T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return o;
+}

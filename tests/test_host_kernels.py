@@ -116,3 +116,45 @@ def test_g1_forward_kernels_cta_emulation(lib, fwd, T, R, nslices):
 def test_g2_forward_kernel_cta_emulation(lib):
     _run(lib, 2, 0, 8, 3, 70, seed=11, fwd=0)
     _run(lib, 2, 1, 8, 3, 70, seed=12, fwd=2)
+
+
+@pytest.mark.parametrize("group,nbuckets,seg", [(1, 300, 4), (1, 37, 1), (1, 700, 4), (2, 90, 4)])
+def test_msm_tail_kernels(lib, group, nbuckets, seg):
+    """k_merge_slices_affine (thread-per-bucket path and the warp path for buckets with > 12 slices, ballot + shuffles),
+    k_bucket_reduce (running sums + small scalar multiple per segment), k_sum_points (one and two levels) and k_finalize:
+    sum_b b * (sum of the slices of bucket b) against the oracle."""
+    G = o.BN.G1 if group == 1 else o.BN.G2
+    rng = random.Random(50 + nbuckets)
+    zero = (0, 0) if group == 1 else ((0, 0), (0, 0))
+    one = 1 if group == 1 else (1, 0)
+    pool = [G.affine(G.mul_scalar(G.G, rng.randrange(1, R_)))[:2] for _ in range(24)] + [zero]
+    slice_off = [0, 0]                                # slice_off[b] for b = 0 (unused) and 1
+    pts = []
+    acc = G.zero3()
+    for b in range(1, nbuckets + 1):
+        cnt = rng.choice([0, 1, 1, 2, 3, 12, 13, 40]) if b % 7 else rng.choice([0, 33])
+        bsum = G.zero3()
+        for _ in range(cnt):
+            p = rng.choice(pool)
+            pts.append(p)
+            if p != zero:
+                bsum = _add(G, bsum, (p[0], p[1], one))
+        slice_off.append(slice_off[-1] + cnt)
+        if not G.is_zero(bsum):
+            acc = _add(G, acc, G.mul_scalar(bsum, b))
+    flat = []
+    for p in pts or [zero]:
+        for c in p:
+            flat.extend(c if isinstance(c, tuple) else (c,))
+    w = 8 if group == 1 else 16
+    out = np.zeros(3 * w, dtype=np.uint32)
+    so = np.array(slice_off, dtype=np.uint32)
+    assert lib.t_msm_tail(group, _ptr(_u32(flat)), _ptr(so), nbuckets, seg, _ptr(out)) == 0
+    raw = out.tobytes()
+    v = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(len(raw) // 32)]
+    if G.is_zero(acc):
+        assert all(x == 0 for x in v)
+    else:
+        e = G.affine(acc)
+        got = (v[0], v[1], v[2]) if group == 1 else ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
+        assert got == ((e[0], e[1], 1) if group == 1 else (e[0], e[1], (1, 0)))
