@@ -17,7 +17,7 @@ using namespace b200;
 
 // ---- CTA-at-a-time emulation: one OS thread per CUDA thread, barriers for __syncthreads and the warp shuffles ------
 namespace {
-constexpr int kMaxWarps = 8;
+constexpr int kMaxWarps = 32;
 pthread_barrier_t g_block_bar, g_warp_bar[kMaxWarps];
 uint32_t g_xchg[kMaxWarps][32];
 bool g_cta_mode = false;
@@ -238,9 +238,122 @@ int msm_tail(const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t 
   std::memcpy(out_std, out, sizeof out);
   return 0;
 }
+// ---- a whole MSM, kernel by kernel, in the order and with the parameters the library's msm_sort / msm_buckets /
+// bases_create use (capi.cu): window precompute, digit recode + counting sort + slice tables, bucket accumulation
+// (batched-affine rounds when S != 0, else the XYZZ kernel with LPB lanes per slice), slice merge, weighted bucket
+// reduction, tree sum, normalisation.
+template <class K>
+void run_threads(unsigned nblocks, unsigned nthreads, K kernel) {  // kernels without barriers: one thread at a time
+  blockDim.x = nthreads;
+  gridDim.x = nblocks;
+  for (unsigned b = 0; b < nblocks; b++)
+    for (unsigned t = 0; t < nthreads; t++) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      kernel();
+    }
+}
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <class F>
+int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, uint32_t c, uint32_t S, uint32_t* out_std) {
+  MsmShape sh{n, c, (255 + c - 1) / c, 1u << (c - 1), n};
+  int err = 0;
+  // --- bases_create: table[w][i] = 2^(c w) P_i
+  std::vector<F> staging((size_t)n * 3);
+  std::memcpy(staging.data(), jac_std, staging.size() * sizeof(F));
+  std::vector<Affine<F>> table((size_t)sh.nwin * n);
+  std::vector<XYZZ<F>> state(n);
+  run_threads(cdiv(n, 128), 128, [&] { k_load_bases<F>(staging.data(), n, table.data(), &err); });
+  run_threads(cdiv(n, 128), 128, [&] { k_affine_to_xyzz<F>(table.data(), state.data(), n); });
+  for (uint32_t w = 1; w < sh.nwin; w++) {
+    run_threads(cdiv(n, 128), 128, [&] { k_window_step<F>(state.data(), n, (int)c); });
+    run_threads(cdiv(cdiv(n, 8), 128), 128, [&] { k_batch_to_affine<F, 8>(state.data(), table.data() + (size_t)w * n, n); });
+  }
+  // --- msm_sort
+  uint32_t m = sh.nbuckets + 1;
+  uint64_t total = (uint64_t)sh.nwin * n;
+  uint64_t mean = (total + sh.nbuckets - 1) / sh.nbuckets;
+  const uint32_t kLPBh = 8;
+  uint32_t cap = (uint32_t)(2 * mean < 4 * kLPBh ? 4 * kLPBh : 2 * mean);
+  int fixed = 0;
+  if (S) {
+    cap = S;
+    fixed = 1;
+  }
+  size_t max_slices = sh.nbuckets + total / (S ? S : cap) + 8 + (S ? 0 : sh.nbuckets);
+  std::vector<Fr> scalars(n);
+  std::memcpy(scalars.data(), scalars_std, (size_t)n * sizeof(Fr));
+  std::vector<uint32_t> counts(m + 1, 0), offsets(m + 1, 0), cursor(m + 1, 0), entries(total + 8, 0);
+  std::vector<uint32_t> slice_off(m + 2, 0), slice_start(max_slices, 0), slice_end(max_slices, 0);
+  SliceTables stb{slice_off.data(), slice_start.data(), slice_end.data()};
+  run_threads(cdiv(n, 256), 256, [&] { k_digits_count(scalars.data(), sh, 0, counts.data(), &err); });
+  run_cta(0, 256, 1, [&] { k_scan(counts.data(), m, cap, fixed, offsets.data(), cursor.data(), stb); });
+  run_threads(cdiv(m, 256), 256, [&] { k_fill_slices(counts.data(), offsets.data(), m, cap, fixed, stb); });
+  run_threads(cdiv(n, 256), 256, [&] { k_digits_scatter(scalars.data(), sh, 0, cursor.data(), entries.data(), &err); });
+  if (err) return 100 + err;
+  uint32_t nslices = slice_off[m];
+  if (nslices > max_slices) return 99;
+  // --- msm_buckets
+  std::vector<XYZZ<F>> buckets(sh.nbuckets);
+  if (S) {
+    uint32_t R = 0;
+    while ((1u << R) < S) R++;
+    constexpr int T = 8;
+    std::vector<Affine<F>> bufA((size_t)nslices * (S / 2) + 1), bufB((size_t)nslices * (S / 2) + 1);
+    std::vector<F> pre((size_t)nslices * (S / 2) + 1);
+    unsigned nb_max = cdiv((size_t)nslices * (S / 2), kAffBlock * T) + 1;
+    std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
+    AffineRound<F> ar{};
+    ar.table = table.data();
+    ar.entries = entries.data();
+    ar.slice_start = slice_start.data();
+    ar.slice_end = slice_end.data();
+    ar.nslices_ptr = slice_off.data() + m;
+    ar.pre = pre.data();
+    ar.others = others.data();
+    ar.btot = btot.data();
+    const Affine<F>* prev = nullptr;
+    Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
+    for (uint32_t r = 1; r <= R; r++) {
+      ar.round = r;
+      ar.q_log = R - r;
+      ar.prev = prev;
+      ar.out = bufs[(r - 1) & 1];
+      unsigned nb = cdiv((size_t)nslices << ar.q_log, kAffBlock * T);
+      if (nb == 0) nb = 1;
+      for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_forward<F, T, 1, false>(ar); });
+      for (unsigned b = 0; b < cdiv((size_t)nb * 32, 128); b++) run_cta(b, 128, cdiv((size_t)nb * 32, 128), [&] { k_affine_invert<F>(ar.btot, nb); });
+      run_threads(nb, kAffBlock, [&] { k_affine_backward<F, T, 1, false>(ar); });
+      prev = ar.out;
+    }
+    for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)
+      run_cta(b, 128, cdiv(sh.nbuckets, 128), [&] { k_merge_slices_affine<F>(prev, stb, sh.nbuckets, buckets.data()); });
+  } else {
+    std::vector<XYZZ<F>> slice_out(max_slices);
+    unsigned nb = cdiv((size_t)max_slices * 4, 128);
+    for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_accumulate<F, 4>(table.data(), entries.data(), stb, m, slice_out.data()); });
+    for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)
+      run_cta(b, 128, cdiv(sh.nbuckets, 128), [&] { k_merge_slices<F>(slice_out.data(), stb, sh.nbuckets, buckets.data()); });
+  }
+  uint32_t seg = sh.nbuckets >= 256 ? 4 : 1, nseg = (sh.nbuckets + seg - 1) / seg;
+  std::vector<XYZZ<F>> partials((size_t)nseg + 1024);
+  for (unsigned b = 0; b < cdiv(nseg, 128); b++)
+    run_cta(b, 128, cdiv(nseg, 128), [&] { k_bucket_reduce<F>(buckets.data(), sh.nbuckets, seg, partials.data(), nseg); });
+  XYZZ<F> total_pt;
+  run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data(), nseg, nseg, &total_pt); });
+  F out[3];
+  run_cta(0, 32, 1, [&] { k_finalize<F>(&total_pt, out); });
+  std::memcpy(out_std, out, sizeof out);
+  return 0;
+}
 }  // namespace
 
 extern "C" {
+// sum_i scalars[i] * P_i through every kernel of the pipeline; S = 0: XYZZ accumulation, else batched-affine slices of S
+int t_msm_full(int group, const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, uint32_t c, uint32_t S, uint32_t* out_std) {
+  return group == 1 ? msm_full<Fq>(jac_std, scalars_std, n, c, S, out_std) : msm_full<Fq2>(jac_std, scalars_std, n, c, S, out_std);
+}
 int t_msm_tail(int group, const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t nbuckets, uint32_t seg, uint32_t* out_std) {
   return group == 1 ? msm_tail<Fq>(slice_pts_std, slice_off, nbuckets, seg, out_std)
                     : msm_tail<Fq2>(slice_pts_std, slice_off, nbuckets, seg, out_std);

@@ -158,3 +158,34 @@ def test_msm_tail_kernels(lib, group, nbuckets, seg):
         e = G.affine(acc)
         got = (v[0], v[1], v[2]) if group == 1 else ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
         assert got == ((e[0], e[1], 1) if group == 1 else (e[0], e[1], (1, 0)))
+
+
+@pytest.mark.parametrize("group,n,c,S", [(1, 150, 5, 0), (1, 150, 5, 16), (1, 97, 4, 64), (1, 40, 9, 0), (2, 48, 4, 8)])
+def test_whole_msm_pipeline_on_the_cpu(lib, group, n, c, S):
+    """Every kernel of an MSM in the library's order (window precompute, signed-digit recode, counting sort, slice tables,
+    bucket accumulation in both modes, slice merge, weighted bucket reduction, tree sum, normalisation) on the CPU
+    emulation == sum_i s_i * P_i by the oracle.  Scalars include 0, 1, r - 1, small values and repeated points."""
+    G = o.BN.G1 if group == 1 else o.BN.G2
+    rng = random.Random(1000 * group + n + c)
+    ks = [rng.randrange(1, R_) for _ in range(n)]
+    ks[5] = ks[6]                                           # a repeated point
+    pts = [G.mul_scalar(G.G, k) for k in ks]                # Jacobian, Z != 1: k_load_bases normalises
+    pts[7] = G.zero3()                                      # an infinity point in the CRS (SURVEY a11)
+    ks[7] = 0
+    sc = [rng.randrange(R_) for _ in range(n)]
+    sc[0], sc[1], sc[2], sc[3] = 0, 1, R_ - 1, (1 << 16) - 1
+    for i in range(10, 20):
+        sc[i] = rng.randrange(1 << 12)
+    flat = []
+    for p in pts:
+        for cc in p:
+            flat.extend(cc if isinstance(cc, tuple) else (cc,))
+    w = 8 if group == 1 else 16
+    out = np.zeros(3 * w, dtype=np.uint32)
+    rc = lib.t_msm_full(group, _ptr(_u32(flat)), _ptr(_u32(sc)), n, c, S, _ptr(out))
+    assert rc == 0
+    raw = out.tobytes()
+    v = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(len(raw) // 32)]
+    e = G.affine(G.mul_scalar(G.G, sum(k * s_ for k, s_ in zip(ks, sc)) % R_))
+    got = (v[0], v[1], v[2]) if group == 1 else ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
+    assert got == ((e[0], e[1], 1) if group == 1 else (e[0], e[1], (1, 0)))
