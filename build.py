@@ -56,7 +56,7 @@ VARIANTS = {"k": ["-DB200_KARATSUBA", "-DB200_NO_PAIRING"]}       # Karatsuba 51
 def build_cuda(force=False, variant=None):
     os.makedirs(LIBDIR, exist_ok=True)
     target = os.path.join(LIBDIR, "libb200snark.so" if not variant else f"libb200snark_{variant}.so")
-    if not force and not _newer(target, _all_sources()):
+    if not force and not _newer(target, _all_sources(exts=(".cu", ".cuh", ".h"))):   # the .cpp files are CPU test vehicles
         return target
     if not os.path.exists(NVCC):
         if os.path.exists(target):
