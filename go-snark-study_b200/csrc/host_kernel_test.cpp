@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bucket_affine.cuh"
+#include "ntt.cuh"
 
 using namespace b200;
 
@@ -347,9 +348,45 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
   std::memcpy(out_std, out, sizeof out);
   return 0;
 }
+// out = a * b over F_r with the NTT kernels, in the order of PolyCtx::forward / pointwise / inverse_unscaled
+// (poly_host.cuh): load + Montgomery, DIF stages, pointwise product scaled by 1/N, DIT stages, store.
+int poly_mul_kernels(const uint32_t* a_std, uint32_t la, const uint32_t* b_std, uint32_t lb, uint32_t* out_std) {
+  uint32_t lo = la + lb - 1;
+  int logn = 1;
+  while ((1u << logn) < lo) logn++;
+  uint32_t N = 1u << logn, n_half = N >> 1;
+  Fr root;
+  for (int i = 0; i < 8; i++) root.l[i] = FrParams::ROOT(i);
+  Fr w = root;
+  for (int i = 0; i < FrParams::TWO_ADICITY - logn; i++) w = w.sqr();
+  Fr w_inv = w.inverse();
+  Fr nf = Fr::zero();
+  nf.l[0] = N;
+  Fr n_inv = nf.to_mont().inverse();
+  std::vector<Fr> tw(n_half), tw_inv(n_half), A(N), B(N), src_a(la), src_b(lb), out(lo);
+  std::memcpy(src_a.data(), a_std, (size_t)la * sizeof(Fr));
+  std::memcpy(src_b.data(), b_std, (size_t)lb * sizeof(Fr));
+  int err = 0;
+  run_threads(cdiv(n_half, 256), 256, [&] { k_twiddles(tw.data(), n_half, w); });
+  run_threads(cdiv(n_half, 256), 256, [&] { k_twiddles(tw_inv.data(), n_half, w_inv); });
+  run_threads(cdiv(N, 256), 256, [&] { k_poly_load(src_a.data(), la, la, 0, 0, A.data(), N, &err); });
+  run_threads(cdiv(N, 256), 256, [&] { k_poly_load(src_b.data(), lb, lb, 0, 0, B.data(), N, &err); });
+  for (Fr* d : {A.data(), B.data()})
+    for (uint32_t half = n_half; half >= 1; half >>= 1)
+      run_threads(cdiv(n_half, 256), 256, [&] { k_ntt_dif_stage(d, tw.data(), n_half, half, n_half / half); });
+  run_threads(cdiv(N, 256), 256, [&] { k_pointwise_mul(A.data(), B.data(), N, n_inv, 1); });
+  for (uint32_t half = 1; half <= n_half; half <<= 1)
+    run_threads(cdiv(n_half, 256), 256, [&] { k_ntt_dit_stage(A.data(), tw_inv.data(), n_half, half, n_half / half); });
+  run_threads(cdiv(lo, 256), 256, [&] { k_poly_store(A.data(), lo, 0, 1, out.data()); });
+  std::memcpy(out_std, out.data(), (size_t)lo * sizeof(Fr));
+  return err;
+}
 }  // namespace
 
 extern "C" {
+int t_poly_mul_kernels(const uint32_t* a, uint32_t la, const uint32_t* b, uint32_t lb, uint32_t* out) {
+  return poly_mul_kernels(a, la, b, lb, out);
+}
 // sum_i scalars[i] * P_i through every kernel of the pipeline; S = 0: XYZZ accumulation, else batched-affine slices of S
 int t_msm_full(int group, const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, uint32_t c, uint32_t S, uint32_t* out_std) {
   return group == 1 ? msm_full<Fq>(jac_std, scalars_std, n, c, S, out_std) : msm_full<Fq2>(jac_std, scalars_std, n, c, S, out_std);

@@ -189,3 +189,18 @@ def test_whole_msm_pipeline_on_the_cpu(lib, group, n, c, S):
     e = G.affine(G.mul_scalar(G.G, sum(k * s_ for k, s_ in zip(ks, sc)) % R_))
     got = (v[0], v[1], v[2]) if group == 1 else ((v[0], v[1]), (v[2], v[3]), (v[4], v[5]))
     assert got == ((e[0], e[1], 1) if group == 1 else (e[0], e[1], (1, 0)))
+
+
+@pytest.mark.parametrize("la,lb", [(1, 1), (7, 13), (64, 64), (100, 29), (129, 128)])
+def test_ntt_kernels_polynomial_product(lib, la, lb):
+    """PolynomialField.Mul (r1csqap.go:57-67) through the NTT kernels on the CPU emulation (twiddles, DIF stages,
+    pointwise product, DIT stages; no bit-reversal pass) == the oracle's schoolbook product."""
+    rng = random.Random(la * 1000 + lb)
+    a = [rng.randrange(R_) for _ in range(la)]
+    b = [rng.randrange(R_) for _ in range(lb)]
+    a[0], b[-1] = R_ - 1, 1
+    out = np.zeros(8 * (la + lb - 1), dtype=np.uint32)
+    assert lib.t_poly_mul_kernels(_ptr(_u32(a)), la, _ptr(_u32(b)), lb, _ptr(out)) == 0
+    raw = out.tobytes()
+    got = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(la + lb - 1)]
+    assert got == o.PF.mul(a, b)
