@@ -383,7 +383,39 @@ int poly_mul_kernels(const uint32_t* a_std, uint32_t la, const uint32_t* b_std, 
 }
 }  // namespace
 
+namespace {
+// forward (dit = 0) or unscaled inverse (dit = 1) transform of 2^logn values: per-stage kernels vs the fused passes
+int ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* out_stage, uint32_t* out_fused) {
+  uint32_t N = 1u << logn, n_half = N >> 1;
+  Fr root;
+  for (int i = 0; i < 8; i++) root.l[i] = FrParams::ROOT(i);
+  Fr w = root;
+  for (int i = 0; i < FrParams::TWO_ADICITY - logn; i++) w = w.sqr();
+  if (dit) w = w.inverse();
+  std::vector<Fr> tw(n_half), A(N), B(N);
+  std::memcpy(A.data(), in_std, (size_t)N * sizeof(Fr));
+  B = A;
+  run_threads(cdiv(n_half, 256), 256, [&] { k_twiddles(tw.data(), n_half, w); });
+  if (!dit)
+    for (uint32_t half = n_half; half >= 1; half >>= 1)
+      run_threads(cdiv(n_half, 256), 256, [&] { k_ntt_dif_stage(A.data(), tw.data(), n_half, half, n_half / half); });
+  else
+    for (uint32_t half = 1; half <= n_half; half <<= 1)
+      run_threads(cdiv(n_half, 256), 256, [&] { k_ntt_dit_stage(A.data(), tw.data(), n_half, half, n_half / half); });
+  ntt_fused_passes(logn, dit, [&](uint32_t log_hbot, uint32_t k) {
+    unsigned nb = N / kNttTile;
+    for (unsigned b = 0; b < nb; b++) run_cta(b, 256, nb, [&] { k_ntt_fused(B.data(), tw.data(), n_half, log_hbot, k, dit); });
+  }, max_k);
+  std::memcpy(out_stage, A.data(), (size_t)N * sizeof(Fr));
+  std::memcpy(out_fused, B.data(), (size_t)N * sizeof(Fr));
+  return 0;
+}
+}  // namespace
+
 extern "C" {
+int t_ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* out_stage, uint32_t* out_fused) {
+  return ntt_compare(in_std, logn, dit, max_k, out_stage, out_fused);
+}
 int t_poly_mul_kernels(const uint32_t* a, uint32_t la, const uint32_t* b, uint32_t lb, uint32_t* out) {
   return poly_mul_kernels(a, la, b, lb, out);
 }

@@ -61,6 +61,81 @@ __global__ void k_ntt_dit_stage(Fr* __restrict__ a, const Fr* __restrict__ tw, u
   a[i + half] = u - v;
 }
 
+// ---- EXPERIMENT (off by default, B200_NTT_FUSED): several radix-2 stages per pass in shared memory ----------------
+// The per-stage kernels above read and write all N elements once per stage (21 passes over 64 MB for a 2^21-point
+// transform).  Here a CTA owns a tile of 1024 elements — R = 2^k rows spaced h_bot apart by C = 1024 / R adjacent
+// columns — and runs the k stages with halves h_bot * 2^(k-1) ... h_bot on it in shared memory (32 KB), so a 2^21-point
+// transform is 3 passes (8 + 3 strided stages, then the last 10 stages on contiguous 1024-element tiles: k = 10, C = 1).
+// Butterflies and twiddles are exactly those of k_ntt_dif_stage / k_ntt_dit_stage; the field results are identical.
+// dit = 0: DIF order (halves descending);  dit = 1: DIT order (halves ascending, twiddle applied before the butterfly).
+constexpr uint32_t kNttTile = 1024;
+__global__ void __launch_bounds__(256) k_ntt_fused(Fr* __restrict__ a, const Fr* __restrict__ tw, uint32_t n_half,
+                                                   uint32_t log_hbot, uint32_t k, int dit) {
+  __shared__ Fr tile[kNttTile];
+  const uint32_t logC = 10 - k, C = 1u << logC, R = 1u << k, h_bot = 1u << log_hbot;
+  const uint32_t tiles_per_group = h_bot >> logC;  // column tiles inside one group of R * h_bot elements
+  const uint32_t g = blockIdx.x / tiles_per_group, ct = blockIdx.x % tiles_per_group;
+  const size_t base = (size_t)g * ((size_t)R << log_hbot) + ((size_t)ct << logC);
+  const uint32_t col0 = ct << logC;
+  const uint32_t t = threadIdx.x;
+  for (uint32_t e = t; e < kNttTile; e += blockDim.x) {
+    uint32_t r = e >> logC, c = e & (C - 1);
+    tile[e] = a[base + ((size_t)r << log_hbot) + c];
+  }
+  __syncthreads();
+  for (uint32_t st = 0; st < k; st++) {
+    const uint32_t s = dit ? k - 1 - st : st;            // DIF: s = 0 is the largest half; DIT: smallest half first
+    const uint32_t lb = k - 1 - s;                        // log2 of the row distance of a butterfly pair
+    const uint32_t half = h_bot << lb;
+    const uint32_t tw_stride = n_half / half;
+    for (uint32_t bf = t; bf < kNttTile / 2; bf += blockDim.x) {
+      uint32_t c = bf & (C - 1), q = bf >> logC;
+      uint32_t low = q & ((1u << lb) - 1u), high = q >> lb;
+      uint32_t r = (high << (lb + 1)) | low;
+      uint32_t i0 = (r << logC) | c, i1 = i0 + ((1u << lb) << logC);
+      uint32_t j = (low << log_hbot) + col0 + c;          // position inside the half: the twiddle exponent
+      Fr u = tile[i0], v = tile[i1];
+      if (dit) {
+        if (j) v = v * tw[(size_t)j * tw_stride];
+        tile[i0] = u + v;
+        tile[i1] = u - v;
+      } else {
+        tile[i0] = u + v;
+        Fr d = u - v;
+        tile[i1] = j ? d * tw[(size_t)j * tw_stride] : d;
+      }
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = t; e < kNttTile; e += blockDim.x) {
+    uint32_t r = e >> logC, c = e & (C - 1);
+    a[base + ((size_t)r << log_hbot) + c] = tile[e];
+  }
+}
+// The passes of a fused 2^logn-point transform (logn >= 10): up to 8 strided stages per pass above the last ten, then one
+// contiguous pass.  Calls launch(log_hbot, k) in execution order (DIF: large halves first; DIT: the reverse).
+template <class Launch>
+inline void ntt_fused_passes(int logn, int dit, Launch&& launch, int max_k = 8) {
+  int upper = logn - 10;                 // stages with half >= 2^10
+  int ks[24], hb[24], np = 0;
+  int top = logn - 1;                    // log2 of the largest half still to do
+  while (upper > 0) {
+    int k = upper > max_k ? max_k : upper;   // max_k < 8 only in tests (several strided passes on small transforms)
+    ks[np] = k;
+    hb[np] = top - (k - 1);
+    np++;
+    top -= k;
+    upper -= k;
+  }
+  ks[np] = 10;
+  hb[np] = 0;
+  np++;
+  if (!dit)
+    for (int i = 0; i < np; i++) launch((uint32_t)hb[i], (uint32_t)ks[i]);
+  else
+    for (int i = np - 1; i >= 0; i--) launch((uint32_t)hb[i], (uint32_t)ks[i]);
+}
+
 // c[i] = a[i] * b[i] (* scale)
 __global__ void k_pointwise_mul(Fr* __restrict__ a, const Fr* __restrict__ b, uint32_t n, Fr scale, int use_scale) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,6 +52,12 @@ struct NttPlan {
 };
 
 struct PolyCtx {
+  // B200_NTT_FUSED=1: fused shared-memory passes instead of one launch per stage (bit-identical transform, checked on
+  // the CPU emulation in tests/test_host_kernels.py; off until it has been timed on a GPU)
+  static bool fused() {
+    static const bool v = getenv("B200_NTT_FUSED") && atoi(getenv("B200_NTT_FUSED")) != 0;
+    return v;
+  }
   unsigned long long* launch_counter = nullptr;
   void note(unsigned n) { if (launch_counter) *launch_counter += n; }
   std::map<int, std::unique_ptr<NttPlan>> plans;
@@ -88,6 +94,15 @@ struct PolyCtx {
     cudaError_t e = plan(logn, &pl, st);
     if (e != cudaSuccess) return e;
     uint32_t N = 1u << logn, n_half = N >> 1;
+    if (fused() && logn >= 10) {  // experiment: several stages per pass in shared memory (ntt.cuh: k_ntt_fused)
+      unsigned passes = 0;
+      ntt_fused_passes(logn, 0, [&](uint32_t log_hbot, uint32_t k) {
+        k_ntt_fused<<<N / kNttTile, 256, 0, st>>>(d, pl->tw.as<Fr>(), n_half, log_hbot, k, 0);
+        passes++;
+      });
+      note(passes);
+      return cudaGetLastError();
+    }
     for (uint32_t half = n_half; half >= 1; half >>= 1)
       k_ntt_dif_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw.as<Fr>(), n_half, half, n_half / half);
     note(logn);
@@ -99,6 +114,15 @@ struct PolyCtx {
     cudaError_t e = plan(logn, &pl, st);
     if (e != cudaSuccess) return e;
     uint32_t N = 1u << logn, n_half = N >> 1;
+    if (fused() && logn >= 10) {
+      unsigned passes = 0;
+      ntt_fused_passes(logn, 1, [&](uint32_t log_hbot, uint32_t k) {
+        k_ntt_fused<<<N / kNttTile, 256, 0, st>>>(d, pl->tw_inv.as<Fr>(), n_half, log_hbot, k, 1);
+        passes++;
+      });
+      note(passes);
+      return cudaGetLastError();
+    }
     for (uint32_t half = 1; half <= n_half; half <<= 1)
       k_ntt_dit_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw_inv.as<Fr>(), n_half, half, n_half / half);
     note(logn);

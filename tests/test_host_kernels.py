@@ -204,3 +204,19 @@ def test_ntt_kernels_polynomial_product(lib, la, lb):
     raw = out.tobytes()
     got = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(la + lb - 1)]
     assert got == o.PF.mul(a, b)
+
+
+@pytest.mark.parametrize("logn,dit,max_k", [(10, 0, 8), (10, 1, 8), (11, 0, 8), (11, 1, 8), (13, 0, 8), (13, 1, 8),
+                                            (14, 0, 2), (14, 1, 2), (14, 0, 3), (15, 1, 1),   # several strided passes
+                                            (18, 1, 8)])                                       # a full 8-stage strided pass
+def test_fused_ntt_passes_equal_the_stage_kernels(lib, logn, dit, max_k):
+    """k_ntt_fused (several stages per pass in a 1024-element shared-memory tile: strided passes + the contiguous last
+    pass) produces exactly the per-stage kernels' transform, forward and inverse; and the forward one is the DFT."""
+    n = 1 << logn
+    rng = random.Random(logn * 2 + dit)
+    vals = [rng.randrange(R_) for _ in range(n)]
+    a, b = np.zeros(8 * n, dtype=np.uint32), np.zeros(8 * n, dtype=np.uint32)
+    # inputs are taken as Montgomery representatives by the kernels; any residues do for an equality test
+    assert lib.t_ntt_compare(_ptr(_u32(vals)), logn, dit, max_k, _ptr(a), _ptr(b)) == 0
+    assert a.tobytes() == b.tobytes()
+    assert a.tobytes() != _u32(vals).tobytes()

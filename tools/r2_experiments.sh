@@ -19,6 +19,9 @@ echo "== fewer pairs per thread in the late rounds (B200_AFF_TSMALL = CTA thresh
 B200_AFF_TSMALL=1184 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
 timeout 200 tools/sweep_env.sh "B200_AFF_TSMALL=600" "B200_AFF_TSMALL=1184" "B200_AFF_TSMALL=2400"
 for ts in 0 1184; do echo -n "G1 2^20 stand-alone, TSMALL=$ts: "; B200_AFF_TSMALL=$ts timeout 100 python tools/quick_msm_bench.py 1 20 16 2>&1 | tail -1; done
+echo "== fused NTT passes (B200_NTT_FUSED=1): parity of the polynomial and prove tests, then bench"
+B200_NTT_FUSED=1 timeout 300 python -m pytest tests/test_gpu_poly.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
+timeout 120 tools/sweep_env.sh "B200_NTT_FUSED=1"
 echo "== fast final exponentiation: parity on the goldens, then timing of the verify tests"
 B200_FAST_FINAL_EXP=1 timeout 200 python -m pytest tests/test_gpu_verify.py -x -q --durations=4 2>&1 | tail -8
 if [ -f go-snark-study_b200/lib/libb200snark_k.so ]; then
