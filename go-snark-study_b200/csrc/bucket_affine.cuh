@@ -602,6 +602,226 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_lr(AffineRo
   }
 }
 
+// ---- EXPERIMENT (off by default, B200_AFF_TS): one thread per slice, rounds fused ----------------------------------
+// In the layout above a round's pairs are dealt out block-interleaved, so the forward pass of round r+1 has to re-read the
+// nodes round r just wrote, and the late rounds have too few pairs to fill the machine.  Here thread s owns slice s — the
+// whole subtree — in every round: the kernel of round r walks the slice's 2^(R-r) pairs of that level, does the backward
+// step (the addition) and, as soon as two sibling nodes exist, multiplies the denominator of THEIR addition into the
+// prefix product of round r+1.  Only round 1 needs a stand-alone forward pass; every later round is one kernel + the
+// inversion of the block totals, every thread is busy in every round (work per thread halves, the grid stays nslices / 128
+// CTAs), and the forward pass's operands are registers instead of gathers.  The walk direction alternates per round
+// (prefix products must be peeled off in the reverse order of their accumulation).  Node storage (slice-major, ping-pong)
+// is the same as above, so k_merge_slices_affine is unchanged.
+template <class F>
+struct AffineRoundTS {
+  const Affine<F>* table;
+  const uint32_t* entries;
+  const uint32_t* slice_start;
+  const uint32_t* slice_end;
+  const uint32_t* nslices_ptr;
+  const Affine<F>* prev;   // nodes of the previous round (round > 1)
+  Affine<F>* out;          // nodes of this round
+  const F* pre;            // prefix products of this round's pairs (slice-major: (s << q_log) + j)
+  const F* others;         // per thread: product of the other threads' totals of its CTA
+  const F* btot;           // per CTA: inverse of the product of all its denominators
+  F* pre_next;             // the same three for round + 1 (written unless `last`)
+  F* others_next;
+  F* btot_next;
+  uint32_t q_log;          // log2(pairs per slice in this round)
+  uint32_t round;          // 1-based
+  uint32_t last;           // no round + 1
+};
+
+// others[thread] = product of the OTHER threads' `run` in the CTA, btot[CTA] = product of all (as in k_affine_forward)
+template <class F>
+__device__ __forceinline__ void aff_block_scan(const F& run, F* others, F* btot, F* wtot) {
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  F incl = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    F up = shfl_up_fe(incl, off);
+    if ((int)lane >= off) incl = incl * up;
+  }
+  F sincl = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    F dn = shfl_down_fe(sincl, off);
+    if ((int)lane + off < 32) sincl = sincl * dn;
+  }
+  F pex = shfl_up_fe(incl, 1), sex = shfl_down_fe(sincl, 1);
+  if (lane == 0) pex = F::one();
+  if (lane == 31) sex = F::one();
+  F warp_total = shfl_idx_fe(incl, 31);
+  if (lane == 0) wtot[warp] = warp_total;
+  __syncthreads();
+  F other_warps = F::one();
+#pragma unroll
+  for (int w = 0; w < kAffBlock / 32; w++)
+    if (w != (int)warp) other_warps = other_warps * wtot[w];
+  others[blockIdx.x * kAffBlock + t] = pex * sex * other_warps;
+  if (t == 0) btot[blockIdx.x] = other_warps * wtot[0];
+}
+
+// operands of pair j of slice s in this round
+template <class F>
+__device__ __forceinline__ void aff_ts_operands(const AffineRoundTS<F>& a, uint32_t s, uint32_t j, uint32_t s0, uint32_t s1,
+                                                Affine<F>& P, Affine<F>& Q) {
+  if (a.round == 1) {
+    uint32_t i0 = s0 + 2 * j, i1 = i0 + 1;
+    P = Affine<F>::inf();
+    Q = Affine<F>::inf();
+    if (i0 < s1) {
+      uint32_t en = a.entries[i0];
+      P = ld_affine_gather(&a.table[en >> 1]);
+      if ((en & 1) && !P.is_inf()) P.y = P.y.neg();
+    }
+    if (i1 < s1) {
+      uint32_t en = a.entries[i1];
+      Q = ld_affine_gather(&a.table[en >> 1]);
+      if ((en & 1) && !Q.is_inf()) Q.y = Q.y.neg();
+    }
+  } else {
+    size_t base = ((size_t)s << (a.q_log + 1)) + 2 * j;
+    P = ld_affine(&a.prev[base]);
+    Q = ld_affine(&a.prev[base + 1]);
+  }
+}
+
+// Round 1 only: prefix products of the leaf-pair denominators of slice s (ascending j), then the block scan.
+template <class F, int MINB = 1>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_ts_forward1(AffineRoundTS<F> a) {
+  __shared__ F wtot[kAffBlock / 32];
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t s = blockIdx.x * kAffBlock + threadIdx.x;
+  F run = F::one();
+  if (s < nslices) {
+    const uint32_t q = 1u << a.q_log, s0 = a.slice_start[s], s1 = a.slice_end[s];
+    for (uint32_t j = 0; j < q; j++) {
+      Affine<F> P, Q;
+      aff_ts_operands(a, s, j, s0, s1, P, Q);
+      F d;
+      aff_denominator(P, Q, d);
+      a.pre_next[((size_t)s << a.q_log) + j] = run;
+      run = run * d;
+    }
+  }
+  aff_block_scan(run, a.others_next, a.btot_next, wtot);
+}
+
+// one pair with the full logic (absent / infinity operands, doubling, P = -Q), out of line: the rare cases
+template <class F>
+__device__ __noinline__ void aff_ts_pair_slow(const AffineRoundTS<F>& a, uint32_t s, uint32_t j, uint32_t s0, uint32_t s1,
+                                              F& inv_run, Affine<F>& Rr) {
+  Affine<F> P, Q;
+  aff_ts_operands(a, s, j, s0, s1, P, Q);
+  F d;
+  int kind = aff_denominator(P, Q, d);
+  F inv_d = inv_run * a.pre[((size_t)s << a.q_log) + j];
+  inv_run = inv_run * d;
+  if (kind == 1) {
+    F lam = (Q.y - P.y) * inv_d;
+    F x3 = lam.sqr() - P.x - Q.x;
+    Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+  } else if (kind == 2) {
+    F xx = P.x.sqr();
+    F lam = (xx.dbl() + xx) * inv_d;
+    F x3 = lam.sqr() - P.x.dbl();
+    Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+  } else {
+    Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
+  }
+}
+// denominator of the addition of two sibling nodes this thread has just written (rare cases: re-read them coherently)
+template <class F>
+__device__ __forceinline__ void aff_ts_sibling_slow(const Affine<F>* out, size_t p_even, F& d2) {
+  Affine<F> L = out[p_even], Rt = out[p_even + 1];
+  aff_denominator(L, Rt, d2);
+}
+
+template <class F, int MINB = 1>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_ts_round(AffineRoundTS<F> a) {
+  __shared__ F wtot[kAffBlock / 32];
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t s = blockIdx.x * kAffBlock + threadIdx.x;
+  F next_run = F::one();
+  if (s < nslices) {
+    const uint32_t q = 1u << a.q_log;
+    const bool desc = (a.round & 1u) != 0;        // round 1's stand-alone forward pass accumulated ascending
+    uint32_t s0 = 0, s1 = 0;
+    if (a.round == 1) {
+      s0 = a.slice_start[s];
+      s1 = a.slice_end[s];
+    }
+    F inv_run = a.btot[blockIdx.x] * a.others[blockIdx.x * kAffBlock + threadIdx.x];
+    F held_x = F::zero();                         // x of the sibling computed one step earlier (zero: infinity)
+#pragma unroll 1
+    for (uint32_t i = 0; i < q; i++) {
+      const uint32_t j = desc ? q - 1 - i : i;
+      const size_t p = ((size_t)s << a.q_log) + j;
+      // locate the operands; the generic case (both present, x's non-zero and distinct) runs with short live ranges
+      const Affine<F>*pp = nullptr, *qp = nullptr;
+      uint32_t neg1 = 0, neg2 = 0;
+      if (a.round == 1) {
+        uint32_t i0 = s0 + 2 * j;
+        if (i0 + 1 < s1) {
+          uint32_t e0 = a.entries[i0], e1 = a.entries[i0 + 1];
+          pp = &a.table[e0 >> 1];
+          qp = &a.table[e1 >> 1];
+          neg1 = e0 & 1u;
+          neg2 = e1 & 1u;
+        }
+      } else {
+        size_t base = ((size_t)s << (a.q_log + 1)) + 2 * j;
+        pp = &a.prev[base];
+        qp = &a.prev[base + 1];
+      }
+      bool fast = pp != nullptr;
+      F x1, x2, dx;
+      if (fast) {
+        x1 = a.round == 1 ? ld_x_gather(pp) : ld_fe(&pp->x);
+        x2 = a.round == 1 ? ld_x_gather(qp) : ld_fe(&qp->x);
+        dx = x2 - x1;
+        fast = !(x1.is_zero() || x2.is_zero() || dx.is_zero());
+      }
+      F rx;                                        // x of the node just produced (zero when it is the point at infinity)
+      if (fast) {
+        F lam;
+        {
+          F inv_d = inv_run * ld_fe(&a.pre[p]);
+          inv_run = inv_run * dx;
+          F y2 = ld_fe(&qp->y);
+          if (neg2) y2 = y2.neg();
+          F y1 = ld_fe(&pp->y);
+          if (neg1) y1 = y1.neg();
+          lam = (y2 - y1) * inv_d;
+        }
+        rx = lam.sqr() - x1 - x2;
+        F y1 = ld_fe(&pp->y);
+        if (neg1) y1 = y1.neg();
+        a.out[p] = Affine<F>{rx, lam * (x1 - rx) - y1};
+      } else {
+        Affine<F> Rr;
+        aff_ts_pair_slow(a, s, j, s0, s1, inv_run, Rr);
+        a.out[p] = Rr;
+        rx = Rr.x;                                 // a zero x sends the sibling step to its exact slow path
+      }
+      if (!a.last) {
+        const bool second = desc ? (j & 1u) == 0 : (j & 1u) == 1;   // both siblings of pair j >> 1 now exist
+        if (second) {
+          F xl = desc ? rx : held_x, xr = desc ? held_x : rx;
+          F d2 = xr - xl;
+          if (xl.is_zero() || xr.is_zero() || d2.is_zero()) aff_ts_sibling_slow(a.out, p & ~(size_t)1, d2);
+          a.pre_next[((size_t)s << (a.q_log - 1)) + (j >> 1)] = next_run;
+          next_run = next_run * d2;
+        } else {
+          held_x = rx;
+        }
+      }
+    }
+  }
+  if (!a.last) aff_block_scan(next_run, a.others_next, a.btot_next, wtot);
+}
+
 // Tail of the tree (tuning knob B200_AFF_ROUNDS): after fewer than log2(S) affine rounds every slice
 // still holds `q` nodes; LPB lanes per bucket add the (contiguous) nodes of all its slices with XYZZ mixed
 // adds and merge through a shuffle tree.

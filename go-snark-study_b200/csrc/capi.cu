@@ -148,7 +148,13 @@ struct Bases {
   // batched-affine accumulation (affine_S > 0): ping-pong node buffers, prefix products, per-thread / per-block products
   uint32_t affine_S = 0;
   DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot;
+  // experiment B200_AFF_TS (thread per slice, fused rounds): second prefix buffer, ping-pong per-thread / per-CTA products
+  DevBuf ts_pre2, ts_others[2], ts_btot[2];
 };
+static bool aff_ts_enabled() {
+  static const bool v = getenv("B200_AFF_TS") && atoi(getenv("B200_AFF_TS")) != 0;
+  return v;
+}
 
 int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
   ss.sh = sh;
@@ -233,6 +239,14 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
       size_t nblk_max = (nsl * (S / 2) + kAffBlock * 16 - 1) / (kAffBlock * 16);
       CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
       CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
+      if (aff_ts_enabled()) {
+        size_t nb_ts = (nsl + kAffBlock - 1) / kAffBlock;
+        CU(b->ts_pre2.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(F)));
+        for (int k = 0; k < 2; k++) {
+          CU(b->ts_others[k].alloc(nb_ts * kAffBlock * sizeof(F)));
+          CU(b->ts_btot[k].alloc(nb_ts * sizeof(F)));
+        }
+      }
     }
   }
   CU(b->slice_out.alloc((size_t)(b->affine_S ? 1 : b->sort.max_slices) * sizeof(XYZZ<F>)));
@@ -398,6 +412,50 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     // MSMs' streams (22.3 ms vs 25.5 ms with an XYZZ tail after round 3 at 2^20, profiles/r1_notes.md)
     uint32_t R_aff = rounds_env ? (uint32_t)rounds_env : R;
     if (R_aff > R) R_aff = R;
+    if (aff_ts_enabled() && b->ts_pre2.p && R_aff == R) {
+      // thread-per-slice fused rounds: forward pass of round 1, then one kernel + one inversion launch per round
+      AffineRoundTS<F> at{};
+      at.table = ar.table;
+      at.entries = ar.entries;
+      at.slice_start = ar.slice_start;
+      at.slice_end = ar.slice_end;
+      at.nslices_ptr = ar.nslices_ptr;
+      F* pres[2] = {b->aff_pre.as<F>(), b->ts_pre2.as<F>()};
+      F* oths[2] = {b->ts_others[0].as<F>(), b->ts_others[1].as<F>()};
+      F* bts[2] = {b->ts_btot[0].as<F>(), b->ts_btot[1].as<F>()};
+      unsigned nb = (unsigned)((nsl_bound + kAffBlock - 1) / kAffBlock);
+      static const int ts_mb = getenv("B200_AFF_TS_MINB") ? atoi(getenv("B200_AFF_TS_MINB")) : 4;
+      at.round = 1;
+      at.q_log = R - 1;
+      at.pre_next = pres[0];
+      at.others_next = oths[0];
+      at.btot_next = bts[0];
+      k_affine_ts_forward1<F, 4><<<nb, kAffBlock, 0, st>>>(at);
+      k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(bts[0], nb);
+      g_launches += 2;
+      for (uint32_t r = 1; r <= R; r++) {
+        at.round = r;
+        at.q_log = R - r;
+        at.prev = prev;
+        at.out = bufs[(r - 1) & 1];
+        at.pre = pres[(r - 1) & 1];
+        at.others = oths[(r - 1) & 1];
+        at.btot = bts[(r - 1) & 1];
+        at.pre_next = pres[r & 1];
+        at.others_next = oths[r & 1];
+        at.btot_next = bts[r & 1];
+        at.last = r == R;
+        if (ts_mb >= 5) k_affine_ts_round<F, 5><<<nb, kAffBlock, 0, st>>>(at);
+        else if (ts_mb >= 4) k_affine_ts_round<F, 4><<<nb, kAffBlock, 0, st>>>(at);
+        else k_affine_ts_round<F, 3><<<nb, kAffBlock, 0, st>>>(at);
+        g_launches += 1;
+        if (!at.last) {
+          k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(bts[r & 1], nb);
+          g_launches += 1;
+        }
+        prev = at.out;
+      }
+    } else
     for (uint32_t r = 1; r <= R_aff; r++) {
       ar.round = r;
       ar.q_log = R - r;

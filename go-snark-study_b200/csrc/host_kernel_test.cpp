@@ -207,6 +207,64 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   return 0;
 }
 
+// thread-per-slice fused rounds (k_affine_ts_forward1 / k_affine_ts_round), all rounds, CTA emulation throughout
+template <class F>
+int affine_rounds_ts(const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
+                     const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
+  constexpr int W = sizeof(F) / 4;
+  std::vector<Affine<F>> table(n_pts);
+  for (uint32_t i = 0; i < n_pts; i++) {
+    table[i].x = load_std<F>(table_std + (size_t)i * 2 * W);
+    table[i].y = load_std<F>(table_std + (size_t)i * 2 * W + W);
+  }
+  const uint32_t S = 1u << R;
+  unsigned nb = (nslices + kAffBlock - 1) / kAffBlock;
+  std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
+  std::vector<F> preA((size_t)nslices * (S / 2)), preB((size_t)nslices * (S / 2));
+  std::vector<F> othA((size_t)nb * kAffBlock), othB((size_t)nb * kAffBlock), btA(nb), btB(nb);
+  AffineRoundTS<F> ar{};
+  ar.table = table.data();
+  ar.entries = entries;
+  ar.slice_start = slice_start;
+  ar.slice_end = slice_end;
+  ar.nslices_ptr = &nslices;
+  F* pres[2] = {preA.data(), preB.data()};
+  F* oths[2] = {othA.data(), othB.data()};
+  F* bts[2] = {btA.data(), btB.data()};
+  Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
+  // round-1 forward pass
+  ar.round = 1;
+  ar.q_log = R - 1;
+  ar.pre_next = pres[0];
+  ar.others_next = oths[0];
+  ar.btot_next = bts[0];
+  for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_forward1<F>(ar); });
+  for (unsigned b = 0; b < nb; b++) bts[0][b] = bts[0][b].inverse();
+  const Affine<F>* prev = nullptr;
+  for (uint32_t r = 1; r <= R; r++) {
+    ar.round = r;
+    ar.q_log = R - r;
+    ar.prev = prev;
+    ar.out = bufs[(r - 1) & 1];
+    ar.pre = pres[(r - 1) & 1];
+    ar.others = oths[(r - 1) & 1];
+    ar.btot = bts[(r - 1) & 1];
+    ar.pre_next = pres[r & 1];
+    ar.others_next = oths[r & 1];
+    ar.btot_next = bts[r & 1];
+    ar.last = r == R;
+    for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_round<F>(ar); });
+    if (!ar.last)
+      for (unsigned b = 0; b < nb; b++) bts[r & 1][b] = bts[r & 1][b].inverse();
+    prev = ar.out;
+  }
+  for (uint32_t s = 0; s < nslices; s++) {
+    store_std(out_std + (size_t)s * 2 * W, prev[s].x);
+    store_std(out_std + (size_t)s * 2 * W + W, prev[s].y);
+  }
+  return 0;
+}
+
 // Back end of an MSM after the accumulation: slices -> buckets (k_merge_slices_affine), sum_b b*S_b by segments
 // (k_bucket_reduce), tree sum (k_sum_points, one or two levels like launch_tree_sum), normalisation (k_finalize).
 template <class F>
@@ -413,6 +471,11 @@ int ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* 
 }  // namespace
 
 extern "C" {
+int t_affine_rounds_ts(int group, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
+                       const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
+  return group == 1 ? affine_rounds_ts<Fq>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
+                    : affine_rounds_ts<Fq2>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+}
 int t_ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* out_stage, uint32_t* out_fused) {
   return ntt_compare(in_std, logn, dit, max_k, out_stage, out_fused);
 }

@@ -41,7 +41,7 @@ def _scenario(group, R, nslices, seed):
               [(4, 0), (4, 0), (4, 1), (4, 1)], [(npts - 2, 0), (npts - 2, 1)]]
     slices = [s[:S] for s in slices]
     while len(slices) < nslices:
-        cnt = rng.choice([0, 1, 2, 3, S - 1, S, rng.randrange(S + 1)])
+        cnt = min(S, rng.choice([0, 1, 2, 3, S - 1, S, rng.randrange(S + 1)]))
         slices.append([(rng.randrange(npts), rng.randrange(2)) for _ in range(cnt)])
     rng.shuffle(slices)
     entries, starts, ends = [], [], []
@@ -220,3 +220,20 @@ def test_fused_ntt_passes_equal_the_stage_kernels(lib, logn, dit, max_k):
     assert lib.t_ntt_compare(_ptr(_u32(vals)), logn, dit, max_k, _ptr(a), _ptr(b)) == 0
     assert a.tobytes() == b.tobytes()
     assert a.tobytes() != _u32(vals).tobytes()
+
+
+@pytest.mark.parametrize("group,R,nslices", [(1, 4, 300), (1, 1, 140), (1, 6, 130), (1, 3, 37), (2, 3, 70)])
+def test_thread_per_slice_fused_rounds(lib, group, R, nslices):
+    """k_affine_ts_forward1 + k_affine_ts_round (one thread per slice; the backward step of round r fused with the forward
+    pass of round r+1, walk direction alternating per round) over all rounds == the oracle's slice sums."""
+    table, npts, entries, starts, ends, exp = _scenario(group, R, nslices, seed=300 + 10 * R + group)
+    w = 8 if group == 1 else 16
+    out = np.zeros(nslices * 2 * w, dtype=np.uint32)
+    assert lib.t_affine_rounds_ts(group, _ptr(table), npts, _ptr(entries), _ptr(starts), _ptr(ends), nslices, R, _ptr(out)) == 0
+    raw = out.tobytes()
+    vals = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(len(raw) // 32)]
+    got = []
+    for s_ in range(nslices):
+        v = vals[s_ * (2 * w // 8):(s_ + 1) * (2 * w // 8)]
+        got.append((v[0], v[1]) if group == 1 else ((v[0], v[1]), (v[2], v[3])))
+    assert got == exp
