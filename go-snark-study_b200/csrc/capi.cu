@@ -151,8 +151,8 @@ struct Bases {
   // experiment B200_AFF_TS (thread per slice, fused rounds): second prefix buffer, ping-pong per-thread / per-CTA products
   DevBuf ts_pre2, ts_others[2], ts_btot[2];
 };
-static bool aff_ts_enabled() {
-  static const bool v = getenv("B200_AFF_TS") && atoi(getenv("B200_AFF_TS")) != 0;
+static int aff_ts_enabled() {  // bit 0: G1 base sets, bit 1: G2 base sets
+  static const int v = getenv("B200_AFF_TS") ? atoi(getenv("B200_AFF_TS")) : 0;
   return v;
 }
 
@@ -239,7 +239,7 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
       size_t nblk_max = (nsl * (S / 2) + kAffBlock * 16 - 1) / (kAffBlock * 16);
       CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
       CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
-      if (aff_ts_enabled()) {
+      if (aff_ts_enabled() & (sizeof(F) == 32 ? 1 : 2)) {
         size_t nb_ts = (nsl + kAffBlock - 1) / kAffBlock;
         CU(b->ts_pre2.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(F)));
         for (int k = 0; k < 2; k++) {
@@ -412,7 +412,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     // MSMs' streams (22.3 ms vs 25.5 ms with an XYZZ tail after round 3 at 2^20, profiles/r1_notes.md)
     uint32_t R_aff = rounds_env ? (uint32_t)rounds_env : R;
     if (R_aff > R) R_aff = R;
-    if (aff_ts_enabled() && b->ts_pre2.p && R_aff == R) {
+    if ((aff_ts_enabled() & (sizeof(F) == 32 ? 1 : 2)) && b->ts_pre2.p && R_aff == R) {
       // thread-per-slice fused rounds: forward pass of round 1, then one kernel + one inversion launch per round
       AffineRoundTS<F> at{};
       at.table = ar.table;
