@@ -738,12 +738,16 @@ __device__ __forceinline__ void aff_ts_sibling_slow(const Affine<F>* out, size_t
   aff_denominator(L, Rt, d2);
 }
 
-template <class F, int MINB = 1>
+// SMEM: keep the two values that live across iterations (the next round's running product and the held sibling x) in
+// shared memory instead of registers — for G2 they are 32 registers of a 128-register budget.
+template <class F, int MINB = 1, bool SMEM = false>
 __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_ts_round(AffineRoundTS<F> a) {
   __shared__ F wtot[kAffBlock / 32];
+  __shared__ F sm_state[SMEM ? 2 * kAffBlock : 1];
   const uint32_t nslices = *a.nslices_ptr;
   const uint32_t s = blockIdx.x * kAffBlock + threadIdx.x;
   F next_run = F::one();
+  if (SMEM) sm_state[threadIdx.x] = next_run;
   if (s < nslices) {
     const uint32_t q = 1u << a.q_log;
     const bool desc = (a.round & 1u) != 0;        // round 1's stand-alone forward pass accumulated ascending
@@ -754,6 +758,7 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_ts_round(AffineRound
     }
     F inv_run = a.btot[blockIdx.x] * a.others[blockIdx.x * kAffBlock + threadIdx.x];
     F held_x = F::zero();                         // x of the sibling computed one step earlier (zero: infinity)
+    if (SMEM) sm_state[kAffBlock + threadIdx.x] = held_x;
 #pragma unroll 1
     for (uint32_t i = 0; i < q; i++) {
       const uint32_t j = desc ? q - 1 - i : i;
@@ -808,17 +813,22 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_ts_round(AffineRound
       if (!a.last) {
         const bool second = desc ? (j & 1u) == 0 : (j & 1u) == 1;   // both siblings of pair j >> 1 now exist
         if (second) {
+          if (SMEM) held_x = sm_state[kAffBlock + threadIdx.x];
           F xl = desc ? rx : held_x, xr = desc ? held_x : rx;
           F d2 = xr - xl;
           if (xl.is_zero() || xr.is_zero() || d2.is_zero()) aff_ts_sibling_slow(a.out, p & ~(size_t)1, d2);
+          if (SMEM) next_run = sm_state[threadIdx.x];
           a.pre_next[((size_t)s << (a.q_log - 1)) + (j >> 1)] = next_run;
           next_run = next_run * d2;
+          if (SMEM) sm_state[threadIdx.x] = next_run;
         } else {
-          held_x = rx;
+          if (SMEM) sm_state[kAffBlock + threadIdx.x] = rx;
+          else held_x = rx;
         }
       }
     }
   }
+  if (SMEM) next_run = sm_state[threadIdx.x];
   if (!a.last) aff_block_scan(next_run, a.others_next, a.btot_next, wtot);
 }
 

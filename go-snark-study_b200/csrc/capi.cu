@@ -445,7 +445,11 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
         at.others_next = oths[r & 1];
         at.btot_next = bts[r & 1];
         at.last = r == R;
-        if (ts_mb >= 5) k_affine_ts_round<F, 5><<<nb, kAffBlock, 0, st>>>(at);
+        static const int ts_smem = getenv("B200_AFF_TS_SMEM") ? atoi(getenv("B200_AFF_TS_SMEM")) : 0;  // loop-carried state in smem
+        if (ts_smem) {
+          if (ts_mb >= 5) k_affine_ts_round<F, 5, true><<<nb, kAffBlock, 0, st>>>(at);
+          else k_affine_ts_round<F, 4, true><<<nb, kAffBlock, 0, st>>>(at);
+        } else if (ts_mb >= 5) k_affine_ts_round<F, 5><<<nb, kAffBlock, 0, st>>>(at);
         else if (ts_mb >= 4) k_affine_ts_round<F, 4><<<nb, kAffBlock, 0, st>>>(at);
         else k_affine_ts_round<F, 3><<<nb, kAffBlock, 0, st>>>(at);
         g_launches += 1;

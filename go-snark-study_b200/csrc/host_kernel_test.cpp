@@ -208,7 +208,7 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
 }
 
 // thread-per-slice fused rounds (k_affine_ts_forward1 / k_affine_ts_round), all rounds, CTA emulation throughout
-template <class F>
+template <class F, bool SMEM>
 int affine_rounds_ts(const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
                      const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
   constexpr int W = sizeof(F) / 4;
@@ -253,7 +253,7 @@ int affine_rounds_ts(const uint32_t* table_std, uint32_t n_pts, const uint32_t* 
     ar.others_next = oths[r & 1];
     ar.btot_next = bts[r & 1];
     ar.last = r == R;
-    for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_round<F>(ar); });
+    for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_round<F, 1, SMEM>(ar); });
     if (!ar.last)
       for (unsigned b = 0; b < nb; b++) bts[r & 1][b] = bts[r & 1][b].inverse();
     prev = ar.out;
@@ -471,10 +471,13 @@ int ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* 
 }  // namespace
 
 extern "C" {
-int t_affine_rounds_ts(int group, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
-                       const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
-  return group == 1 ? affine_rounds_ts<Fq>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
-                    : affine_rounds_ts<Fq2>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+int t_affine_rounds_ts(int group, int smem, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries,
+                       const uint32_t* slice_start, const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
+  if (group == 1)
+    return smem ? affine_rounds_ts<Fq, true>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
+                : affine_rounds_ts<Fq, false>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+  return smem ? affine_rounds_ts<Fq2, true>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
+              : affine_rounds_ts<Fq2, false>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
 }
 int t_ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* out_stage, uint32_t* out_fused) {
   return ntt_compare(in_std, logn, dit, max_k, out_stage, out_fused);

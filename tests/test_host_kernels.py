@@ -222,14 +222,15 @@ def test_fused_ntt_passes_equal_the_stage_kernels(lib, logn, dit, max_k):
     assert a.tobytes() != _u32(vals).tobytes()
 
 
+@pytest.mark.parametrize("smem", [0, 1])
 @pytest.mark.parametrize("group,R,nslices", [(1, 4, 300), (1, 1, 140), (1, 6, 130), (1, 3, 37), (2, 3, 70)])
-def test_thread_per_slice_fused_rounds(lib, group, R, nslices):
+def test_thread_per_slice_fused_rounds(lib, group, R, nslices, smem):
     """k_affine_ts_forward1 + k_affine_ts_round (one thread per slice; the backward step of round r fused with the forward
     pass of round r+1, walk direction alternating per round) over all rounds == the oracle's slice sums."""
     table, npts, entries, starts, ends, exp = _scenario(group, R, nslices, seed=300 + 10 * R + group)
     w = 8 if group == 1 else 16
     out = np.zeros(nslices * 2 * w, dtype=np.uint32)
-    assert lib.t_affine_rounds_ts(group, _ptr(table), npts, _ptr(entries), _ptr(starts), _ptr(ends), nslices, R, _ptr(out)) == 0
+    assert lib.t_affine_rounds_ts(group, smem, _ptr(table), npts, _ptr(entries), _ptr(starts), _ptr(ends), nslices, R, _ptr(out)) == 0
     raw = out.tobytes()
     vals = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(len(raw) // 32)]
     got = []

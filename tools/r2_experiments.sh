@@ -21,7 +21,7 @@ timeout 200 tools/sweep_env.sh "B200_AFF_TSMALL=600" "B200_AFF_TSMALL=1184" "B20
 for ts in 0 1184; do echo -n "G1 2^20 stand-alone, TSMALL=$ts: "; B200_AFF_TSMALL=$ts timeout 100 python tools/quick_msm_bench.py 1 20 16 2>&1 | tail -1; done
 echo "== thread-per-slice fused rounds (B200_AFF_TS: bit 0 G1, bit 1 G2): parity, bench, stand-alone MSMs"
 B200_AFF_TS=3 B200_ACC_MODE=affine timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prove.py tests/test_gpu_shard.py -x -q 2>&1 | tail -2
-timeout 300 tools/sweep_env.sh "B200_AFF_TS=1" "B200_AFF_TS=2" "B200_AFF_TS=3" "B200_AFF_TS=3 B200_AFF_TS_MINB=3" "B200_AFF_TS=1 B200_AFF_TS_MINB=5"
+timeout 300 tools/sweep_env.sh "B200_AFF_TS=1" "B200_AFF_TS=2" "B200_AFF_TS=3" "B200_AFF_TS=3 B200_AFF_TS_MINB=3" "B200_AFF_TS=3 B200_AFF_TS_SMEM=1" "B200_AFF_TS=3 B200_AFF_TS_SMEM=1 B200_AFF_TS_MINB=5"
 for g in 1 2; do echo -n "G$g 2^20 stand-alone, TS: "; B200_AFF_TS=3 timeout 100 python tools/quick_msm_bench.py $g 20 16 2>&1 | tail -1; done
 echo "== fused NTT passes (B200_NTT_FUSED=1): parity of the polynomial and prove tests, then bench"
 B200_NTT_FUSED=1 timeout 300 python -m pytest tests/test_gpu_poly.py tests/test_gpu_prove.py -x -q 2>&1 | tail -2
