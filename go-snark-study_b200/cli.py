@@ -51,7 +51,9 @@ def calculate_witness(circuit, private_inputs, public_inputs):
         elif op == "*":
             w[out] = a * b
         elif op == "/":
-            w[out] = int(a / b) if b else 0           # big.Int.Div is Euclidean; inputs are non-negative here
+            if b == 0:                                 # big.Int.Div panics "division by zero" (circuit.go:182)
+                raise ZeroDivisionError("calculate_witness: division by zero in constraint %r" % (c["Out"],))
+            w[out] = a // b if b > 0 else -(a // -b)   # big.Int.Div is Euclidean: remainder in [0, |b|)
     return w
 
 

@@ -546,7 +546,8 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
   CU(cudaMemcpyAsync(pk->w_stage.p, w, nw * sizeof(Fr), cudaMemcpyHostToDevice, st));
   // px is only needed by the division on side stream 3: copy it there so the transfer overlaps the sort of w
   // (same-stream order makes the division see it; the previous proof's use of pk->px finished before its combine)
-  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_side[2]));
+  // (measurement mode runs the division on `st`, so the copy goes there too)
+  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : g_side[2]));
   Fq* o = pk->out_std.as<Fq>();
   int rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, pk->px.as<Fr>(), npx, r, s, o, st);
   if (rc) return rc;

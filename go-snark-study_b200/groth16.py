@@ -21,6 +21,15 @@ def _attr(obj, name):
     return obj[name] if isinstance(obj, dict) else getattr(obj, name)
 
 
+def _n_signals(circuit, default):
+    """len(circuit.Signals) (groth16.go:164, snark.go:171) for dict- and object-style circuits; NVars if absent."""
+    if isinstance(circuit, dict):
+        sig = circuit.get("Signals")
+    else:
+        sig = getattr(circuit, "Signals", None)
+    return len(sig) if sig is not None else default
+
+
 def rand_fr():
     """Fq.Rand over r (fields/fq.go:116-132): bitlen/8-1 = 30 random bytes, mod r."""
     return int.from_bytes(secrets.token_bytes(30), "big") % R
@@ -61,14 +70,50 @@ class DeviceProvingKey:
             self.handle = 0
 
 
-_pk_cache = {}
+class KeyCache:
+    """Implicit proving-key cache of the drop-in ``GenerateProofs(circuit, pk, w, px)`` form (the reference takes the key
+    by value on every call, groth16.go:225; uploading 384·n bytes and precomputing window tables per call would
+    dominate).  An entry holds a STRONG reference to the caller's ``pk`` object and is matched by identity
+    (``entry.pk is pk``) plus the shape it was loaded with — never by ``id()`` alone: a freed dict's address can be
+    handed to a different key (round-1 bug: a proof under a stale key).  At most ``capacity`` keys stay resident;
+    evicting one frees its device tables.  A caller that mutates ``pk`` in place must call ``Forget(pk)``."""
+
+    def __init__(self, factory, capacity=2):
+        self.factory, self.capacity, self.entries = factory, capacity, []
+
+    def get(self, circuit, pk, window_bits=0):
+        shape = (_attr(circuit, "NVars"), _attr(circuit, "NPublic"), window_bits)
+        for k, (epk, eshape, dpk) in enumerate(self.entries):
+            if epk is pk and eshape == shape:
+                self.entries.append(self.entries.pop(k))          # most recently used last
+                return dpk
+        dpk = self.factory(pk, shape[0], shape[1], window_bits)
+        self.entries.append((pk, shape, dpk))
+        while len(self.entries) > self.capacity:
+            self.entries.pop(0)[2].free()
+        return dpk
+
+    def forget(self, pk=None):
+        keep = []
+        for e in self.entries:
+            if pk is None or e[0] is pk:
+                e[2].free()
+            else:
+                keep.append(e)
+        self.entries = keep
+
+
+_pk_cache = KeyCache(lambda pk, m, npub, c: DeviceProvingKey(pk, m, npub, c))
 
 
 def LoadProvingKey(circuit, pk, window_bits=0):
-    key = id(pk)
-    if key not in _pk_cache:
-        _pk_cache[key] = DeviceProvingKey(pk, _attr(circuit, "NVars"), _attr(circuit, "NPublic"), window_bits)
-    return _pk_cache[key]
+    """Explicit handle form: the returned DeviceProvingKey can be passed as ``pk`` to GenerateProofs."""
+    return _pk_cache.get(circuit, pk, window_bits)
+
+
+def Forget(pk=None):
+    """Free the device copy of ``pk`` (all cached keys when None)."""
+    _pk_cache.forget(pk)
 
 
 def GenerateProofs(circuit, pk, w, px, r=None, s=None):
@@ -92,9 +137,11 @@ def GenerateTrustedSetup(witnessLength, circuit, alphas, betas, gammas, toxic=No
     from . import bn128
     from ._lib import limbs_to_ints
     n_vars, n_public = _attr(circuit, "NVars"), _attr(circuit, "NPublic")
-    n_signals = len(_attr(circuit, "Signals")) if (isinstance(circuit, dict) and "Signals" in circuit) else n_vars
-    tox = toxic or {k: rand_fr() for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta")}
+    n_signals = _n_signals(circuit, n_vars)
+    tox = {k: rand_fr() for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta")} if toxic is None else toxic
     t, ka, kb, kg, kd = (int(tox[k]) % R for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta"))
+    if kg == 0 or kd == 0:
+        raise ValueError("GenerateTrustedSetup: Kgamma and Kdelta must be invertible mod r (groth16.go:151,201)")
     m = len(alphas)
     nz = m - 2                                                   # z pol: prod_{i=1}^{len(alphas)-2} (x - i), :122-132
     zl = np.zeros((nz + 1, 4), dtype=np.uint64)

@@ -9,7 +9,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, ints_to_limbs, lib, ptr
 from .bn128 import R, _flatten_g1, _flatten_g2, _unflatten_g1, _unflatten_g2, reduce_scalar
-from .groth16 import _attr
+from .groth16 import KeyCache, _attr, _n_signals
 
 _ORDER = ("PiA", "PiAp", "PiBp", "PiC", "PiCp", "PiH", "PiKp")
 
@@ -42,14 +42,15 @@ class DeviceProvingKey:
             self.handle = 0
 
 
-_pk_cache = {}
+_pk_cache = KeyCache(lambda pk, m, npub, c: DeviceProvingKey(pk, m, npub, c))       # see groth16.KeyCache (identity + strong ref)
 
 
 def LoadProvingKey(circuit, pk, window_bits=0):
-    key = id(pk)
-    if key not in _pk_cache:
-        _pk_cache[key] = DeviceProvingKey(pk, _attr(circuit, "NVars"), _attr(circuit, "NPublic"), window_bits)
-    return _pk_cache[key]
+    return _pk_cache.get(circuit, pk, window_bits)
+
+
+def Forget(pk=None):
+    _pk_cache.forget(pk)
 
 
 def GenerateProofs(circuit, pk, w, px):
@@ -70,8 +71,8 @@ def GenerateTrustedSetup(witnessLength, circuit, alphas, betas, gammas, toxic=No
     from ._lib import limbs_to_ints
     from .groth16 import rand_fr
     n_vars, n_public = _attr(circuit, "NVars"), _attr(circuit, "NPublic")
-    n_signals = len(_attr(circuit, "Signals")) if (isinstance(circuit, dict) and "Signals" in circuit) else n_vars
-    tox = dict(toxic) if toxic else {k: rand_fr() for k in ("T", "Ka", "Kb", "Kc", "Kbeta", "Kgamma", "RhoA", "RhoB")}
+    n_signals = _n_signals(circuit, n_vars)
+    tox = {k: rand_fr() for k in ("T", "Ka", "Kb", "Kc", "Kbeta", "Kgamma", "RhoA", "RhoB")} if toxic is None else dict(toxic)
     t, ka, kb, kc, kbeta, kgamma, rho_a, rho_b = (int(tox[k]) % R for k in
                                                   ("T", "Ka", "Kb", "Kc", "Kbeta", "Kgamma", "RhoA", "RhoB"))
     rho_c = rho_a * rho_b % R
