@@ -16,6 +16,7 @@ PKG = os.path.join(ROOT, "go-snark-study_b200")
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 ORACLE = os.path.join(ROOT, "oracle")
+HOSTTEST = os.path.join(ROOT, "tests", "host")     # CPU test vehicles for the kernel headers (g++, no CUDA)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_SOURCES = ["capi.cu"]
@@ -32,7 +33,7 @@ def _newer(target, sources):
 
 def _all_sources(exts=(".cu", ".cuh", ".cpp", ".h")):
     out = []
-    for d in (CSRC, os.path.join(ROOT, "include")):
+    for d in (CSRC, os.path.join(ROOT, "include"), HOSTTEST):
         if os.path.isdir(d):
             out += [os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts)]
     return out
@@ -49,22 +50,18 @@ def _run(cmd, log=None):
     return p
 
 
-# experiment builds, selected at run time with B200_LIB_VARIANT=<name> (go-snark-study_b200/_lib.py); never built by default
-VARIANTS = {"k": ["-DB200_KARATSUBA", "-DB200_NO_PAIRING"]}       # Karatsuba 512-bit products (fp.cuh: mul_full_k)
-
-
-def build_cuda(force=False, variant=None):
+def build_cuda(force=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    target = os.path.join(LIBDIR, "libb200snark.so" if not variant else f"libb200snark_{variant}.so")
+    target = os.path.join(LIBDIR, "libb200snark.so")
     if not force and not _newer(target, _all_sources(exts=(".cu", ".cuh", ".h"))):   # the .cpp files are CPU test vehicles
         return target
     if not os.path.exists(NVCC):
         if os.path.exists(target):
             return target          # GPU box without a toolchain change: use the shipped build
         raise RuntimeError("nvcc not found and no prebuilt libb200snark.so")
-    cmd = [NVCC, *NVCC_FLAGS, *(VARIANTS[variant] if variant else []), "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    cmd = [NVCC, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-o", target, *[os.path.join(CSRC, s) for s in CUDA_SOURCES]]
-    _run(cmd, log=os.path.join(LIBDIR, "nvcc_build.log" if not variant else f"nvcc_build_{variant}.log"))
+    _run(cmd, log=os.path.join(LIBDIR, "nvcc_build.log"))
     return target
 
 
@@ -74,7 +71,7 @@ def build_host_arith(force=False):
     if not force and not _newer(target, _all_sources()):
         return target
     cmd = ["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-Wno-psabi", "-I", CSRC,
-           "-o", target, os.path.join(CSRC, "host_arith_test.cpp")]
+           "-o", target, os.path.join(HOSTTEST, "host_arith_test.cpp")]
     _run(cmd)
     return target
 
@@ -83,10 +80,10 @@ def build_host_kernels(force=False):
     """g++ build of the per-thread bucket kernels over csrc/host_stub (CPU test vehicle, tests/test_host_kernels.py)."""
     os.makedirs(LIBDIR, exist_ok=True)
     target = os.path.join(LIBDIR, "libb200_host_kernels.so")
-    if not force and not _newer(target, _all_sources() + [os.path.join(CSRC, "host_stub", "cuda_runtime.h")]):
+    if not force and not _newer(target, _all_sources() + [os.path.join(HOSTTEST, "host_stub", "cuda_runtime.h")]):
         return target
-    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-x", "c++", "-shared", "-fPIC", "-Wno-psabi", "-I", os.path.join(CSRC, "host_stub"),
-           "-I", CSRC, "-o", target, os.path.join(CSRC, "host_kernel_test.cpp")]
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-x", "c++", "-shared", "-fPIC", "-Wno-psabi", "-I", os.path.join(HOSTTEST, "host_stub"),
+           "-I", HOSTTEST, "-I", CSRC, "-o", target, os.path.join(HOSTTEST, "host_kernel_test.cpp")]
     _run(cmd)
     return target
 

@@ -5,9 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200_LIB_VARIANT=<name> loads an experiment build (build.py VARIANTS) instead of the product library
-_VARIANT = os.environ.get("B200_LIB_VARIANT", "")
-LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so" if not _VARIANT else f"libb200snark_{_VARIANT}.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so")
+CFG_ACC_MODE, ACC_AUTO, ACC_AFFINE, ACC_XYZZ = 1, 0, 1, 2
 
 B200_OK = 0
 ERRORS = {-1: "ENODEVICE", -2: "ECUDA", -3: "EINVAL", -4: "ERANGE", -5: "EDIVZERO", -6: "ENOMEM"}
@@ -31,10 +30,12 @@ _SIGNATURES = {
     "b200_init": [_int],
     "b200_shutdown": [],
     "b200_version": [],
+    "b200_config": [_int, _int],
     "b200_g1_bases_load": [_vp, _sz, _int, ctypes.POINTER(_h)],
     "b200_g2_bases_load": [_vp, _sz, _int, ctypes.POINTER(_h)],
     "b200_bases_free": [_h],
     "b200_bases_info": [_h, ctypes.POINTER(_sz), ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int)],
+    "b200_bases_acc_mode": [_h, ctypes.POINTER(_int)],
     "b200_g1_msm": [_h, _vp, _sz, _vp],
     "b200_g2_msm": [_h, _vp, _sz, _vp],
     "b200_msm_device": [_h, _vp, _sz, _int, _vp, _vp],
@@ -72,6 +73,12 @@ _SIGNATURES = {
     "b200_g1_double_batch": [_vp, _sz, _vp], "b200_g2_double_batch": [_vp, _sz, _vp],
     "b200_g1_neg_batch": [_vp, _sz, _vp], "b200_g2_neg_batch": [_vp, _sz, _vp],
     "b200_g1_affine_batch": [_vp, _sz, _vp], "b200_g2_affine_batch": [_vp, _sz, _vp],
+    "b200_r1cs_load": [_sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_h)],
+    "b200_r1cs_free": [_h],
+    "b200_qap_px": [_h, _vp, _sz, _vp, _vp, _vp, _vp],
+    "b200_qap_eval_at": [_h, _vp, _sz, _vp, _vp, _vp, _vp],
+    "b200_interpolate": [_vp, _sz, _vp],
+    "b200_groth16_prove_witness": [_h, _h, _vp, _sz, _vp, _vp, _vp, _vp, _vp],
     "b200_profile": [_int],
     "b200_profile_read": [ctypes.POINTER(ctypes.c_double)],
 }

@@ -51,7 +51,8 @@ class BaseSet:
     """A CRS array (e.g. Pk.G1.At) uploaded once: normalised to affine Montgomery
     form and window-precomputed on the device (b200_g*_bases_load)."""
 
-    def __init__(self, group, points=None, limbs=None, window_bits=0):
+    def __init__(self, group, points=None, limbs=None, window_bits=0, acc_mode=0):
+        """acc_mode: 0 auto, 1 batched-affine, 2 XYZZ bucket accumulation (b200_config; same result)."""
         assert group in (1, 2)
         self.group = group
         if limbs is None:
@@ -62,8 +63,17 @@ class BaseSet:
         self.n = limbs.size // words
         h = _lib._h(0)
         fn = lib().b200_g1_bases_load if group == 1 else lib().b200_g2_bases_load
-        check(fn(ptr(limbs), self.n, window_bits, h))
+        check(lib().b200_config(_lib.CFG_ACC_MODE, acc_mode))
+        try:
+            check(fn(ptr(limbs), self.n, window_bits, h))
+        finally:
+            check(lib().b200_config(_lib.CFG_ACC_MODE, _lib.ACC_AUTO))
         self.handle = h.value
+
+    def acc_mode(self):
+        m = _lib._int(0)
+        check(lib().b200_bases_acc_mode(self.handle, m))
+        return m.value
 
     def info(self):
         n, g, c, nw = _lib._sz(0), _lib._int(0), _lib._int(0), _lib._int(0)

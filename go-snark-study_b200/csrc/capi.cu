@@ -18,6 +18,7 @@
 #include "bucket_affine.cuh"
 #include "poly_host.cuh"
 #include "qap.cuh"
+#include "qap_sparse.cuh"
 #ifndef B200_NO_PAIRING
 #include "pairing.cuh"
 #endif
@@ -34,6 +35,10 @@ cudaStream_t g_stream = nullptr;
 cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};  // side streams: independent MSMs of one proof overlap
 int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
 std::unique_ptr<PolyCtx> g_poly;
+
+// b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
+// (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
+int g_acc_mode = 0;
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
 // timing of the dominant kernel (k_accumulate), per group.
@@ -93,12 +98,6 @@ int init_locked(int device) {
   }
   if (device >= count) return fail(B200_EINVAL, "device %d out of range (%d devices)", device, count);
   CU(cudaSetDevice(device));
-  {
-    // random 64-byte point gathers: ask L2 for <= 64 B fetches (ncu showed 128 B per 64 B point otherwise)
-    const char* g = getenv("B200_L2_GRAN");   // tuning knob (no measurable effect on B200: left at the default)
-    size_t gran = g ? (size_t)atoi(g) : 0;
-    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-  }
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));  // (stream priorities: no measurable effect)
   CU(cudaMalloc(&g_d_err, sizeof(int)));
@@ -148,13 +147,7 @@ struct Bases {
   // batched-affine accumulation (affine_S > 0): ping-pong node buffers, prefix products, per-thread / per-block products
   uint32_t affine_S = 0;
   DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot;
-  // experiment B200_AFF_TS (thread per slice, fused rounds): second prefix buffer, ping-pong per-thread / per-CTA products
-  DevBuf ts_pre2, ts_others[2], ts_btot[2];
 };
-static int aff_ts_enabled() {  // bit 0: G1 base sets, bit 1: G2 base sets
-  static const int v = getenv("B200_AFF_TS") ? atoi(getenv("B200_AFF_TS")) : 0;
-  return v;
-}
 
 int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
   ss.sh = sh;
@@ -183,6 +176,7 @@ int check_err_flag(const char* what) {
   CU(cudaStreamSynchronize(g_stream));
   if (h) {
     CU(cudaMemset(g_d_err, 0, sizeof(int)));
+    if (h & 16) return fail(B200_EINVAL, "%s: tau is one of the interpolation points 1..n", what);
     if (h & 8) return fail(B200_EINVAL, "%s: q1[2] != Fq2.One() (G2 point at infinity; the reference panics, bn128.go:238-241)", what);
     if (h & 4) return fail(B200_EDIVZERO, "%s: divisor has a zero leading coefficient", what);
     return fail(B200_ERANGE, "%s: %s", what, (h & 1) ? "point coordinate >= q" : "scalar / coefficient >= r");
@@ -214,19 +208,15 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
   CU(b->scalars.alloc(n * sizeof(Fr)));
   CU(b->buckets.alloc((size_t)sh.nbuckets * sizeof(XYZZ<F>)));
   {
-    // accumulation mode: batched affine (default) or XYZZ mixed adds (B200_ACC_MODE=xyzz)
-    static const bool force_xyzz = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "xyzz");
-    static const bool force_affine = getenv("B200_ACC_MODE") && !strcmp(getenv("B200_ACC_MODE"), "affine");
-    const bool xyzz_mode = force_xyzz || (!prefer_affine && !force_affine);
+    // accumulation mode: batched affine (6.5 multiplies per add, 3 launches per round) where the buckets are populated
+    // enough to amortise the rounds, else XYZZ mixed adds (10 multiplies, one launch); b200_config forces either
+    const bool xyzz_mode = g_acc_mode == 2 || (g_acc_mode == 0 && !prefer_affine);
     uint32_t S = 0;
     uint64_t mean = ((uint64_t)sh.nwin * n) / sh.nbuckets;
-    static const int min_mean = getenv("B200_AFF_MIN_MEAN") ? atoi(getenv("B200_AFF_MIN_MEAN")) : 96;  // tuning knob
-    // small bucket populations: the per-round launch + inversion latency is not amortised -> XYZZ path
-    if (!xyzz_mode && mean >= (uint64_t)min_mean) {
+    const uint64_t min_mean = g_acc_mode == 1 ? 16 : 96;
+    if (!xyzz_mode && mean >= min_mean) {
       S = 8;
       while (S < 128 && (uint64_t)S * 2 * 6 <= mean) S *= 2;   // largest power of two <= mean/6, in [8, 128]
-      static const int s_env = getenv("B200_AFF_S") ? atoi(getenv("B200_AFF_S")) : 0;  // tuning knob
-      if (s_env) S = (uint32_t)s_env;
     }
     b->affine_S = S;
     int rc_ = sort_alloc(b->sort, sh, S);
@@ -236,17 +226,9 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
       CU(b->nodeA.alloc(nsl * (S / 2) * sizeof(Affine<F>)));
       CU(b->nodeB.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(Affine<F>)));
       CU(b->aff_pre.alloc(nsl * (S / 2) * sizeof(F)));
-      size_t nblk_max = (nsl * (S / 2) + kAffBlock * 16 - 1) / (kAffBlock * 16);
+      size_t nblk_max = (nsl * (S / 2) + kAffBlock * kAffPairs - 1) / (kAffBlock * kAffPairs);
       CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
       CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
-      if (aff_ts_enabled() & (sizeof(F) == 32 ? 1 : 2)) {
-        size_t nb_ts = (nsl + kAffBlock - 1) / kAffBlock;
-        CU(b->ts_pre2.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(F)));
-        for (int k = 0; k < 2; k++) {
-          CU(b->ts_others[k].alloc(nb_ts * kAffBlock * sizeof(F)));
-          CU(b->ts_btot[k].alloc(nb_ts * sizeof(F)));
-        }
-      }
     }
   }
   CU(b->slice_out.alloc((size_t)(b->affine_S ? 1 : b->sort.max_slices) * sizeof(XYZZ<F>)));
@@ -307,10 +289,7 @@ void launch_accumulate_l(const Affine<F>* table, const uint32_t* entries, SliceT
   if constexpr (sizeof(F) == sizeof(Fq)) {
     k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
   } else {
-    static const int minb = getenv("B200_ACC_MINB_G2") ? atoi(getenv("B200_ACC_MINB_G2")) : 1;  // tuning knob
-    if (minb >= 4) k_accumulate<F, LPB, 4><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
-    else if (minb >= 2) k_accumulate<F, LPB, 2><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
-    else k_accumulate<F, LPB, 1><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
+    k_accumulate<F, LPB, 1><<<grid, 128, 0, st>>>(table, entries, stb, m, out);
   }
 }
 template <class F>
@@ -378,7 +357,6 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
   uint32_t m = sh.nbuckets + 1;
   XYZZ<F>* buckets = b->buckets.as<XYZZ<F>>();
   XYZZ<F>* partials = b->partials.as<XYZZ<F>>();
-  static const int lpb_env = getenv("B200_LPB") ? atoi(getenv("B200_LPB")) : 0;  // tuning knob
   SliceTables stb = ss.tables();
   // The out-of-line F_q multiply wins here: the fully inlined madd body (~38 KB of SASS) thrashes the
   // instruction caches (measured 5.85 ms vs 4.80 ms at 2^20, profiles/r1_notes.md).
@@ -407,126 +385,25 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     ar.btot = b->aff_btot.as<F>();
     Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
     const Affine<F>* prev = nullptr;
-    static const int rounds_env = getenv("B200_AFF_ROUNDS") ? atoi(getenv("B200_AFF_ROUNDS")) : 0;  // tuning knob
-    // all rounds affine by default: inside a proof the per-round inversion latency is hidden by the other
-    // MSMs' streams (22.3 ms vs 25.5 ms with an XYZZ tail after round 3 at 2^20, profiles/r1_notes.md)
-    uint32_t R_aff = rounds_env ? (uint32_t)rounds_env : R;
-    if (R_aff > R) R_aff = R;
-    if ((aff_ts_enabled() & (sizeof(F) == 32 ? 1 : 2)) && b->ts_pre2.p && R_aff == R) {
-      // thread-per-slice fused rounds: forward pass of round 1, then one kernel + one inversion launch per round
-      AffineRoundTS<F> at{};
-      at.table = ar.table;
-      at.entries = ar.entries;
-      at.slice_start = ar.slice_start;
-      at.slice_end = ar.slice_end;
-      at.nslices_ptr = ar.nslices_ptr;
-      F* pres[2] = {b->aff_pre.as<F>(), b->ts_pre2.as<F>()};
-      F* oths[2] = {b->ts_others[0].as<F>(), b->ts_others[1].as<F>()};
-      F* bts[2] = {b->ts_btot[0].as<F>(), b->ts_btot[1].as<F>()};
-      unsigned nb = (unsigned)((nsl_bound + kAffBlock - 1) / kAffBlock);
-      static const int ts_mb = getenv("B200_AFF_TS_MINB") ? atoi(getenv("B200_AFF_TS_MINB")) : 4;
-      at.round = 1;
-      at.q_log = R - 1;
-      at.pre_next = pres[0];
-      at.others_next = oths[0];
-      at.btot_next = bts[0];
-      k_affine_ts_forward1<F, 4><<<nb, kAffBlock, 0, st>>>(at);
-      k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(bts[0], nb);
-      g_launches += 2;
-      for (uint32_t r = 1; r <= R; r++) {
-        at.round = r;
-        at.q_log = R - r;
-        at.prev = prev;
-        at.out = bufs[(r - 1) & 1];
-        at.pre = pres[(r - 1) & 1];
-        at.others = oths[(r - 1) & 1];
-        at.btot = bts[(r - 1) & 1];
-        at.pre_next = pres[r & 1];
-        at.others_next = oths[r & 1];
-        at.btot_next = bts[r & 1];
-        at.last = r == R;
-        static const int ts_smem = getenv("B200_AFF_TS_SMEM") ? atoi(getenv("B200_AFF_TS_SMEM")) : 0;  // loop-carried state in smem
-        if (ts_smem) {
-          if (ts_mb >= 5) k_affine_ts_round<F, 5, true><<<nb, kAffBlock, 0, st>>>(at);
-          else k_affine_ts_round<F, 4, true><<<nb, kAffBlock, 0, st>>>(at);
-        } else if (ts_mb >= 5) k_affine_ts_round<F, 5><<<nb, kAffBlock, 0, st>>>(at);
-        else if (ts_mb >= 4) k_affine_ts_round<F, 4><<<nb, kAffBlock, 0, st>>>(at);
-        else k_affine_ts_round<F, 3><<<nb, kAffBlock, 0, st>>>(at);
-        g_launches += 1;
-        if (!at.last) {
-          k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(bts[r & 1], nb);
-          g_launches += 1;
-        }
-        prev = at.out;
-      }
-    } else
-    for (uint32_t r = 1; r <= R_aff; r++) {
+    // all R rounds affine: inside a proof the per-round inversion latency is hidden by the other MSMs' streams
+    for (uint32_t r = 1; r <= R; r++) {
       ar.round = r;
       ar.q_log = R - r;
       ar.prev = prev;
       ar.out = bufs[(r - 1) & 1];
       uint64_t npairs_max = nsl_bound << ar.q_log;
-      static const int t_env = getenv("B200_AFF_T") ? atoi(getenv("B200_AFF_T")) : 32;  // tuning knob
-      unsigned T = t_env == 16 ? 16 : 32;
-      // experiment (off by default): the late rounds have too few pairs to fill the GPU with 32 pairs per thread (round 6
-      // of a 2^20 MSM: 64 CTAs for 148 SMs, and every thread still walks 32 dependent pairs) -> fewer pairs per thread
-      // when the round would launch fewer than B200_AFF_TSMALL CTAs.  (T = 8 only from round 2 on: the scratch arrays
-      // are sized for >= 16 pairs per thread in round 1.)
-      static const int tsmall_env = getenv("B200_AFF_TSMALL") ? atoi(getenv("B200_AFF_TSMALL")) : 0;
-      if (tsmall_env && T == 32) {
-        uint64_t nb32 = (npairs_max + kAffBlock * 32 - 1) / (kAffBlock * 32);
-        if (nb32 * 4 < (uint64_t)tsmall_env && r >= 2) T = 8;
-        else if (nb32 < (uint64_t)tsmall_env) T = 16;
+      unsigned nb = (unsigned)((npairs_max + kAffBlock * kAffPairs - 1) / (kAffBlock * kAffPairs));
+      // CTAs/SM bounds = register caps (ptxas -v: forward 64 / 128 registers, backward 96 / 128, G1 / G2; measured
+      // sweep in profiles/r1_notes.md: forward 8 + backward 5 CTAs/SM for G1, 4 + 4 for G2)
+      if (sizeof(F) == 32) {
+        k_affine_forward<F, kAffPairs, 8><<<nb, kAffBlock, 0, st>>>(ar);
+        k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
+        k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
+      } else {
+        k_affine_forward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
+        k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
+        k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
       }
-      unsigned nb = (unsigned)((npairs_max + kAffBlock * T - 1) / (kAffBlock * T));
-      // CTAs/SM bounds (register caps) of the backward / forward kernels; G2 variants above 4 spill (ptxas -v)
-      static const int mb_g1 = getenv("B200_AFF_MINB") ? atoi(getenv("B200_AFF_MINB")) : 5;          // 20.8 -> 19.6 ms / 2^20 proof
-      static const int mf_g1 = getenv("B200_AFF_MINB_FWD") ? atoi(getenv("B200_AFF_MINB_FWD")) : 8;  // together with the x-only forward
-      static const int mb_g2 = getenv("B200_AFF_MINB_G2") ? atoi(getenv("B200_AFF_MINB_G2")) : 4;
-      static const int mf_g2 = getenv("B200_AFF_MINB_FWD_G2") ? atoi(getenv("B200_AFF_MINB_FWD_G2")) : 4;
-      const int mb_env = sizeof(F) == 32 ? mb_g1 : mb_g2, mf_env = sizeof(F) == 32 ? mf_g1 : mf_g2;
-      static const int pf_env = getenv("B200_AFF_PF") ? atoi(getenv("B200_AFF_PF")) : 0;  // bit 0: forward, bit 1: backward L2 prefetch
-      // experiment: software-pipelined kernels (operand fetches staged three deep); bit 0 forward, bit 1 backward;
-      // bit 2: keep the out-of-line multiply (all groups) instead of the inlined one (G1 only)
-      static const int sp_env = getenv("B200_AFF_SP") ? atoi(getenv("B200_AFF_SP")) : 0;
-      const bool sp_inl = !(sp_env & 4);
-      const bool sp_ok = T == 32 && (sizeof(F) == 32 || !sp_inl);
-      const AffineRound<FqH>& arh = reinterpret_cast<const AffineRound<FqH>&>(ar);   // same layout, inlined multiply
-      if (sp_ok && (sp_env & 1)) {
-        if (!sp_inl) {
-          if (mf_env >= 6) k_affine_forward_sp<F, 32, 6><<<nb, kAffBlock, 0, st>>>(ar);
-          else k_affine_forward_sp<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-        } else if (mf_env >= 6) k_affine_forward_sp<FqH, 32, 6><<<nb, kAffBlock, 0, st>>>(arh);
-        else k_affine_forward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
-      } else
-      if (T == 8) k_affine_forward<F, 8><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (T == 16) k_affine_forward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (pf_env & 1) {
-        if (mf_env >= 8) k_affine_forward<F, 32, 8, true><<<nb, kAffBlock, 0, st>>>(ar);
-        else k_affine_forward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
-      } else if (mf_env >= 8) k_affine_forward<F, 32, 8><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (mf_env >= 4) k_affine_forward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-      else k_affine_forward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
-      k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-      static const int lr_env = getenv("B200_AFF_LR") ? atoi(getenv("B200_AFF_LR")) : 0;  // experiment: bit 0 G1, bit 1 G2
-      if (T == 32 && (lr_env & (sizeof(F) == 32 ? 1 : 2))) {
-        if (mb_env >= 6) k_affine_backward_lr<F, 32, 6><<<nb, kAffBlock, 0, st>>>(ar);
-        else if (mb_env >= 5) k_affine_backward_lr<F, 32, 5><<<nb, kAffBlock, 0, st>>>(ar);
-        else k_affine_backward_lr<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-      } else if (sp_ok && (sp_env & 2)) {
-        if (!sp_inl) {
-          if (mb_env >= 4) k_affine_backward_sp<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-          else k_affine_backward_sp<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
-        } else if (mb_env >= 4) k_affine_backward_sp<FqH, 32, 4><<<nb, kAffBlock, 0, st>>>(arh);
-        else k_affine_backward_sp<FqH, 32, 3><<<nb, kAffBlock, 0, st>>>(arh);
-      } else if (T == 8) k_affine_backward<F, 8><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (T == 16) k_affine_backward<F, 16><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (pf_env & 2) {
-        if (mb_env >= 5) k_affine_backward<F, 32, 5, true><<<nb, kAffBlock, 0, st>>>(ar);
-        else k_affine_backward<F, 32, 4, true><<<nb, kAffBlock, 0, st>>>(ar);
-      } else if (mb_env >= 5) k_affine_backward<F, 32, 5><<<nb, kAffBlock, 0, st>>>(ar);
-      else if (mb_env >= 4) k_affine_backward<F, 32, 4><<<nb, kAffBlock, 0, st>>>(ar);
-      else k_affine_backward<F, 32, 3><<<nb, kAffBlock, 0, st>>>(ar);
       prev = ar.out;
       g_launches += 3;
     }
@@ -534,10 +411,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       cudaEventRecord(pr.e1, st);
       g_prof_recs.push_back(pr);
     }
-    if (R_aff == R)
-      k_merge_slices_affine<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, buckets);
-    else
-      k_accumulate_nodes<F, 8><<<nblocks((size_t)sh.nbuckets * 8, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, R - R_aff, buckets);
+    k_merge_slices_affine<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, buckets);
     k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
     launch_tree_sum<F>(partials, b->nseg, d_out, st);
     g_launches += 2;
@@ -545,7 +419,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     return B200_OK;
   }
   uint64_t mean = ((uint64_t)sh.nwin * n_terms + sh.nbuckets - 1) / sh.nbuckets;
-  int lpb = lpb_env ? lpb_env : (mean >= 384 ? 8 : (mean >= 96 ? 4 : 2));
+  int lpb = mean >= 384 ? 8 : (mean >= 96 ? 4 : 2);
   launch_accumulate<F>(lpb, b->table.as<Affine<F>>(), ss.entries.as<uint32_t>(), stb, m,
                        b->slice_out.as<XYZZ<F>>(), ss.max_slices, st);
   if (g_prof) {
@@ -662,6 +536,36 @@ int poly_div_host(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 
 #include "prove_host.cuh"
 
+#include "qap_sparse_host.cuh"
+
+// groth16.GenerateProofs fed from the witness: px = CombinePolynomials(w, R1CSToQAP(a, b, c)) is computed on the device
+// from the resident sparse R1CS (never leaving HBM) and handed to the same prove pipeline.
+int groth16_prove_witness(b200_pk_t h, b200_r1cs_t hr, const uint64_t* w, size_t nw, const uint64_t* r, const uint64_t* s,
+                          uint64_t* pi_a, uint64_t* pi_b, uint64_t* pi_c) {
+  ProvingKey* pk = find_pk(h, 1);
+  R1cs* rc1 = find_r1cs(hr);
+  if (!pk || !rc1) return fail(B200_EINVAL, "groth16_prove_witness: bad handle");
+  if (!w || !r || !s || !pi_a || !pi_b || !pi_c) return fail(B200_EINVAL, "groth16_prove_witness: null pointer");
+  if (nw != pk->m || nw != rc1->m) return fail(B200_EINVAL, "groth16_prove_witness: witness length %zu, NVars %zu, R1CS columns %zu", nw, pk->m, rc1->m);
+  if (pk->world != 1) return fail(B200_EINVAL, "groth16_prove_witness: sharded key");
+  cudaStream_t st = g_stream;
+  CU(pk->w_stage.ensure(nw * sizeof(Fr)));
+  CU(cudaMemcpyAsync(pk->w_stage.p, w, nw * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  int rc = qap_px_enqueue(rc1, pk->w_stage.as<Fr>(), nullptr, nullptr, st);
+  if (rc) return rc;
+  Fq* o = pk->out_std.as<Fq>();
+  rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, rc1->px_mont.as<Fr>(), 2 * rc1->n - 1, r, s, o, st, /*px_mont=*/1);
+  if (rc) return rc;
+  uint64_t host_out[48];
+  CU(cudaMemcpyAsync(host_out, o, sizeof host_out, cudaMemcpyDeviceToHost, st));
+  rc = check_err_flag<Fr>("groth16_prove_witness");
+  if (rc) return rc;
+  memcpy(pi_a, host_out, 12 * 8);
+  memcpy(pi_c, host_out + 12, 12 * 8);
+  memcpy(pi_b, host_out + 24, 24 * 8);
+  return B200_OK;
+}
+
 // ---- dense QAP API (small n) -------------------------------------------------
 int r1cs_to_qap_host(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, size_t m, uint64_t* alphas,
                      uint64_t* betas, uint64_t* gammas, uint64_t* z) {
@@ -767,11 +671,16 @@ int poly_eval_batch_host(const uint64_t* polys, size_t m, size_t n, const uint64
 }
 
 int zero_poly_host(size_t n, uint64_t* out) {   // coefficients of prod_{i=1..n} (x - i), n + 1 of them
-  if (!out || n > 8191) return fail(B200_EINVAL, "zero_poly: bad arguments (n <= 8191)");
+  if (!out || n > ((size_t)1 << 26)) return fail(B200_EINVAL, "zero_poly: bad arguments (n <= 2^26)");
   DevBuf zn, zz;
-  CU(zn.alloc((n + 1) * sizeof(Fr)));
   CU(zz.alloc((n + 1) * sizeof(Fr)));
-  k_zero_poly<<<1, 1024, 0, g_stream>>>(zn.as<Fr>(), (uint32_t)n);
+  if (n <= 2048) {   // one-block schoolbook; above: Newton basis element n through the subproduct tree (qap_sparse.cuh)
+    CU(zn.alloc((n + 1) * sizeof(Fr)));
+    k_zero_poly<<<1, 1024, 0, g_stream>>>(zn.as<Fr>(), (uint32_t)n);
+  } else {
+    int rc = zero_poly_device(n, zn, g_stream);
+    if (rc) return rc;
+  }
   k_poly_store<<<nblk(n + 1, 256), 256, 0, g_stream>>>(zn.as<Fr>(), (uint32_t)(n + 1), 0, 1, zz.as<Fr>());
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, zz.p, (n + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, g_stream));
@@ -872,12 +781,11 @@ __global__ void k_ic_publ(const Fq* ic, const Fr* sig, size_t npub, Fq* out, int
   out[2] = acc.Z.from_mont();
 }
 
-// B200_FAST_FINAL_EXP=1: the Devegili-Scott-Dahab final exponentiation (same F_q^12 value, ~13x fewer operations;
-// bit-exact on the host emulation, tests/test_host_pairing.py).  Off until it has been run against the goldens on a GPU.
-static int fast_final_exp() {
-  static const int v = getenv("B200_FAST_FINAL_EXP") ? atoi(getenv("B200_FAST_FINAL_EXP")) : 0;
-  return v;
-}
+// Final exponentiation: Devegili-Scott-Dahab (easy part + hard part by the BN parameter), the SAME F_q^12 value as the
+// reference's plain f^((q^12-1)/r) square-and-multiply (bn128.go:400-421) with ~13x fewer operations: validated on the
+// GPU against the snarkjs golden vk_alfabeta_12 (K8), the bn128_test.go literal and the oracle (tests/test_gpu_verify.py,
+// profiles/r2_notes.md).  The plain routine stays in pairing.cuh as the step-by-step restatement used by the host tests.
+constexpr bool kFastFinalExp = true;
 int pairing_batch_host(const uint64_t* g1, const uint64_t* g2, size_t n, uint64_t* out) {
   if (!g1 || !g2 || !out) return fail(B200_EINVAL, "pairing_batch: null pointer");
   if (n == 0) return B200_OK;
@@ -887,8 +795,7 @@ int pairing_batch_host(const uint64_t* g1, const uint64_t* g2, size_t n, uint64_
   CU(dout.alloc(n * 6 * sizeof(Fq2)));
   CU(cudaMemcpyAsync(d1.p, g1, n * 3 * sizeof(Fq), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(d2.p, g2, n * 3 * sizeof(Fq2), cudaMemcpyHostToDevice, g_stream));
-  if (fast_final_exp()) k_pairing_batch<true><<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>(), g_d_err);
-  else k_pairing_batch<false><<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>(), g_d_err);
+  k_pairing_batch<kFastFinalExp><<<nblk(n, 32), 32, 0, g_stream>>>(d1.as<Fq>(), d2.as<Fq2>(), n, dout.as<Fq2>(), g_d_err);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, dout.p, n * 6 * sizeof(Fq2), cudaMemcpyDeviceToHost, g_stream));
   return check_err_flag<Fq>("pairing_batch");
@@ -935,8 +842,7 @@ int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1,
   CU(cudaMemcpyAsync(p2 + 6, gamma2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(p2 + 9, delta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   k_ic_publ<<<1, 32, 0, st>>>(dic.as<Fq>(), dsig.as<Fr>(), npub, p1 + 6, g_d_err);
-  if (fast_final_exp()) k_groth16_verify<true><<<1, 128, 0, st>>>(p1, p2, dok.as<int>(), g_d_err);
-  else k_groth16_verify<false><<<1, 128, 0, st>>>(p1, p2, dok.as<int>(), g_d_err);
+  k_groth16_verify<kFastFinalExp><<<1, 128, 0, st>>>(p1, p2, dok.as<int>(), g_d_err);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   return check_err_flag<Fq>("groth16_verify");
@@ -1104,6 +1010,30 @@ int b200_poly_sub(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t out[4]) { B200_API_BODY(poly_eval_host(v, n, x, out)) }
 int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out) { B200_API_BODY(poly_eval_batch_host(polys, m, n, x, out)) }
 int b200_zero_poly(size_t n, uint64_t* out) { B200_API_BODY(zero_poly_host(n, out)) }
+int b200_r1cs_load(size_t n, size_t m, const uint32_t* a_rowptr, const uint32_t* a_col, const uint64_t* a_val,
+                   const uint32_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val, const uint32_t* c_rowptr,
+                   const uint32_t* c_col, const uint64_t* c_val, b200_r1cs_t* out) {
+  const uint32_t* const rp[3] = {a_rowptr, b_rowptr, c_rowptr};
+  const uint32_t* const cl[3] = {a_col, b_col, c_col};
+  const uint64_t* const vl[3] = {a_val, b_val, c_val};
+  B200_API_BODY(r1cs_load(n, m, rp, cl, vl, out))
+}
+int b200_r1cs_free(b200_r1cs_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_r1cs.erase(h)) return fail(B200_EINVAL, "r1cs_free: bad handle");
+  return B200_OK;
+}
+int b200_qap_px(b200_r1cs_t h, const uint64_t* w, size_t nw, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px) {
+  B200_API_BODY(qap_px_host(h, w, nw, ax, bx, cx, px))
+}
+int b200_qap_eval_at(b200_r1cs_t h, const uint64_t tau[4], size_t nz, uint64_t* at, uint64_t* bt, uint64_t* ct, uint64_t zt[4]) {
+  B200_API_BODY(qap_eval_at_host(h, tau, nz, at, bt, ct, zt))
+}
+int b200_interpolate(const uint64_t* values, size_t n, uint64_t* coeffs) { B200_API_BODY(interpolate_host(values, n, coeffs)) }
+int b200_groth16_prove_witness(b200_pk_t pk, b200_r1cs_t r1cs, const uint64_t* w, size_t nw, const uint64_t r[4],
+                               const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24], uint64_t pi_c[12]) {
+  B200_API_BODY(groth16_prove_witness(pk, r1cs, w, nw, r, s, pi_a, pi_b, pi_c))
+}
 int b200_fq12_mul_batch(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) { B200_API_BODY(fq12_mul_batch_host(a, b, n, out)) }
 int b200_pairing_batch(const uint64_t* g1_jac, const uint64_t* g2_jac, size_t n, uint64_t* out) { B200_API_BODY(pairing_batch_host(g1_jac, g2_jac, n, out)) }
 int b200_groth16_verify(const uint64_t* ic, size_t n_ic, const uint64_t alpha1[12], const uint64_t beta2[24],
@@ -1133,7 +1063,15 @@ int b200_poly_div(const uint64_t* a, size_t na, const uint64_t* b, size_t nb, ui
 }
 
 
-int b200_version(void) { return 100; }
+int b200_version(void) { return 200; }
+int b200_config(int key, int value) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
+    g_acc_mode = value;
+    return B200_OK;
+  }
+  return fail(B200_EINVAL, "b200_config: unknown key %d or bad value %d", key, value);
+}
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 
@@ -1186,6 +1124,13 @@ int b200_bases_info(b200_bases_t h, size_t* n, int* group, int* window_bits, int
   return B200_OK;
 }
 
+int b200_bases_acc_mode(b200_bases_t h, int* mode) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Bases* b = find_bases(h, 0);
+  if (!b || !mode) return fail(B200_EINVAL, "bases_acc_mode: bad handle");
+  *mode = b->affine_S ? 1 : 2;
+  return B200_OK;
+}
 int b200_g1_msm(b200_bases_t h, const uint64_t* s, size_t n, uint64_t out[12]) {
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();

@@ -160,9 +160,6 @@ struct alignas(32) Fp {
   }
   static HD Fp mul_impl(const Fp& a, const Fp& b) {
     using namespace cc;
-#ifdef B200_KARATSUBA
-    return mul_impl_k(a, b);
-#else
     uint32_t even[8], odd[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
@@ -176,7 +173,6 @@ struct alignas(32) Fp {
     r.l[7] = addc(even[7], 0u);
     final_sub(r.l);
     return r;
-#endif
   }
   HD Fp sqr() const { return (*this) * (*this); }
 
@@ -187,9 +183,6 @@ struct alignas(32) Fp {
   // independent carry chains of fused IMAD.WIDE.U32.X, exactly as in mul_impl.
   static HD void mul_full(uint32_t* w, const uint32_t* a, const uint32_t* b) {
     using namespace cc;
-#ifdef B200_KARATSUBA
-    mul_full_k(w, a, b);
-#else
     uint32_t E[16], O[16];  // O[k] sits at column k + 1
 #pragma unroll
     for (int k = 0; k < 16; k++) E[k] = O[k] = 0;
@@ -240,170 +233,11 @@ struct alignas(32) Fp {
 #pragma unroll
     for (int k = 2; k < 15; k++) w[k] = addc_cc(E[k], O[k - 1]);
     w[15] = addc(E[15], O[14]);
-#endif
-  }
-
-  // ---- Karatsuba variant of the 512-bit product (EXPERIMENT, -DB200_KARATSUBA) -------------------------------
-  // The multiply pipe (IMAD.WIDE at a quarter of the issue rate) is what bounds the bucket kernels while the integer
-  // add pipe idles, so trading wide multiplies for additions can pay: one Karatsuba level over 128-bit halves turns the
-  // 64 wide multiplies of mul_full into 3 x 16 = 48 plus ~60 adds; with redc_wide a field multiply is 48 + 64 wide
-  // multiplies instead of 128.  Subtractive form: a0 b1 + a1 b0 = a0 b0 + a1 b1 - (a0 - a1)(b0 - b1).
-  // w[0..2N) = a * b for N-limb operands (N even): the even/odd two-chain scheme of mul_full, any width.
-  template <int N>
-  static HD void mul_n(uint32_t* w, const uint32_t* a, const uint32_t* b) {
-    using namespace cc;
-    uint32_t E[2 * N], O[2 * N];  // O[k] sits at column k + 1
-    // row 0 initialises the accumulators (no zero fill): a[even] * b0 -> E[j..j+1], a[odd] * b0 -> O[j-1..j]
-#pragma unroll
-    for (int j = 0; j < N; j += 2) {
-      mul_wide(a[j], b[0], E[j], E[j + 1]);
-      mul_wide(a[j + 1], b[0], O[j], O[j + 1]);
-    }
-#pragma unroll
-    for (int k = N; k < 2 * N; k++) E[k] = O[k] = 0;
-#pragma unroll
-    for (int i = 1; i < N; i++) {
-      uint32_t bi = b[i];
-      if ((i & 1) == 0) {
-        E[i] = mad_lo_cc(a[0], bi, E[i]);
-        E[i + 1] = madc_hi_cc(a[0], bi, E[i + 1]);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) {
-          E[i + j] = madc_lo_cc(a[j], bi, E[i + j]);
-          E[i + j + 1] = madc_hi_cc(a[j], bi, E[i + j + 1]);
-        }
-        if (i + N < 2 * N) E[i + N] = addc(E[i + N], 0u);
-        O[i] = mad_lo_cc(a[1], bi, O[i]);
-        O[i + 1] = madc_hi_cc(a[1], bi, O[i + 1]);
-#pragma unroll
-        for (int j = 3; j < N; j += 2) {
-          O[i + j - 1] = madc_lo_cc(a[j], bi, O[i + j - 1]);
-          O[i + j] = madc_hi_cc(a[j], bi, O[i + j]);
-        }
-        if (i + N < 2 * N) O[i + N] = addc(O[i + N], 0u);
-      } else {
-        O[i - 1] = mad_lo_cc(a[0], bi, O[i - 1]);
-        O[i] = madc_hi_cc(a[0], bi, O[i]);
-#pragma unroll
-        for (int j = 2; j < N; j += 2) {
-          O[i + j - 1] = madc_lo_cc(a[j], bi, O[i + j - 1]);
-          O[i + j] = madc_hi_cc(a[j], bi, O[i + j]);
-        }
-        if (i + N - 1 < 2 * N) O[i + N - 1] = addc(O[i + N - 1], 0u);
-        E[i + 1] = mad_lo_cc(a[1], bi, E[i + 1]);
-        E[i + 2] = madc_hi_cc(a[1], bi, E[i + 2]);
-#pragma unroll
-        for (int j = 3; j < N; j += 2) {
-          E[i + j] = madc_lo_cc(a[j], bi, E[i + j]);
-          E[i + j + 1] = madc_hi_cc(a[j], bi, E[i + j + 1]);
-        }
-        if (i + N + 1 < 2 * N) E[i + N + 1] = addc(E[i + N + 1], 0u);
-      }
-    }
-    w[0] = E[0];
-    w[1] = add_cc(E[1], O[0]);
-#pragma unroll
-    for (int k = 2; k < 2 * N - 1; k++) w[k] = addc_cc(E[k], O[k - 1]);
-    w[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
-  }
-  // d = |x - y| over 4 limbs; returns all-ones when x < y
-  static HD uint32_t abs_diff4(uint32_t* d, const uint32_t* x, const uint32_t* y) {
-    using namespace cc;
-    d[0] = sub_cc(x[0], y[0]);
-    d[1] = subc_cc(x[1], y[1]);
-    d[2] = subc_cc(x[2], y[2]);
-    d[3] = subc_cc(x[3], y[3]);
-    uint32_t neg = subc(0u, 0u);  // 0 or 0xffffffff
-    // two's complement when negative: (~d) + 1
-    d[0] = add_cc(d[0] ^ neg, neg & 1u);
-    d[1] = addc_cc(d[1] ^ neg, 0u);
-    d[2] = addc_cc(d[2] ^ neg, 0u);
-    d[3] = addc(d[3] ^ neg, 0u);
-    return neg;
-  }
-  static HD void mul_full_k(uint32_t* w, const uint32_t* a, const uint32_t* b) {
-    using namespace cc;
-    uint32_t z0[8], z2[8], m[8], da[4], db[4], t[9];
-    mul_n<4>(z0, a, b);
-    mul_n<4>(z2, a + 4, b + 4);
-    uint32_t sa = abs_diff4(da, a, a + 4), sb = abs_diff4(db, b, b + 4);
-    mul_n<4>(m, da, db);
-    // t = z0 + z2 -/+ m = a0 b1 + a1 b0  (>= 0, < 2^257): subtract when the two differences have the same sign
-    uint32_t sub = ~(sa ^ sb);  // all-ones: subtract m
-    t[0] = add_cc(z0[0], z2[0]);
-#pragma unroll
-    for (int k = 1; k < 8; k++) t[k] = addc_cc(z0[k], z2[k]);
-    t[8] = addc(0u, 0u);
-    add_cc(sub & 1u, 0xffffffffu);  // carry-in = 1 when subtracting (t + ~m + 1)
-#pragma unroll
-    for (int k = 0; k < 8; k++) t[k] = addc_cc(t[k], m[k] ^ sub);
-    t[8] = addc(t[8], sub);
-    // w = z0 + t * 2^128 + z2 * 2^256
-#pragma unroll
-    for (int k = 0; k < 4; k++) w[k] = z0[k];
-    w[4] = add_cc(z0[4], t[0]);
-    w[5] = addc_cc(z0[5], t[1]);
-    w[6] = addc_cc(z0[6], t[2]);
-    w[7] = addc_cc(z0[7], t[3]);
-    w[8] = addc_cc(z2[0], t[4]);
-    w[9] = addc_cc(z2[1], t[5]);
-    w[10] = addc_cc(z2[2], t[6]);
-    w[11] = addc_cc(z2[3], t[7]);
-    w[12] = addc_cc(z2[4], t[8]);
-    w[13] = addc_cc(z2[5], 0u);
-    w[14] = addc_cc(z2[6], 0u);
-    w[15] = addc(z2[7], 0u);
-  }
-  // redc_wide with the row carries deferred: the two carries of row i land at columns i + 8 and i + 9, which no later
-  // row reads (m_i only needs columns <= 7), so they are counted per column and folded in by ONE carry chain at the end
-  // instead of a ripple per row (60 -> ~30 additions).
-  static HD Fp redc_wide_dc(const uint32_t* t_in) {
-    using namespace cc;
-    uint32_t t[16], c[10];
-#pragma unroll
-    for (int k = 0; k < 16; k++) t[k] = t_in[k];
-#pragma unroll
-    for (int k = 0; k < 10; k++) c[k] = 0;  // c[k]: carries owed to column 8 + k
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      uint32_t m = mul_lo(t[i], P::INV);
-      t[i] = mad_lo_cc(P::MOD(0), m, t[i]);
-      t[i + 1] = madc_hi_cc(P::MOD(0), m, t[i + 1]);
-#pragma unroll
-      for (int j = 2; j < 8; j += 2) {
-        t[i + j] = madc_lo_cc(P::MOD(j), m, t[i + j]);
-        t[i + j + 1] = madc_hi_cc(P::MOD(j), m, t[i + j + 1]);
-      }
-      c[i] += addc(0u, 0u);
-      t[i + 1] = mad_lo_cc(P::MOD(1), m, t[i + 1]);
-      t[i + 2] = madc_hi_cc(P::MOD(1), m, t[i + 2]);
-#pragma unroll
-      for (int j = 3; j < 8; j += 2) {
-        t[i + j] = madc_lo_cc(P::MOD(j), m, t[i + j]);
-        t[i + j + 1] = madc_hi_cc(P::MOD(j), m, t[i + j + 1]);
-      }
-      c[i + 1] += addc(0u, 0u);  // column i + 9 (column 16, from the last row, is zero for t < p * 2^256 and dropped)
-    }
-    Fp r;
-    r.l[0] = add_cc(t[8], c[0]);
-#pragma unroll
-    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(t[8 + k], c[k]);
-    r.l[7] = addc(t[15], c[7]);
-    final_sub(r.l);
-    return r;
-  }
-  static HD Fp mul_impl_k(const Fp& a, const Fp& b) {
-    uint32_t w[16];
-    mul_full_k(w, a.l, b.l);
-    return redc_wide_dc(w);
   }
 
   // Montgomery reduction of a 512-bit value t < p * 2^256:  returns t / 2^256 mod p, canonical.
   static HD Fp redc_wide(const uint32_t* t_in) {
     using namespace cc;
-#ifdef B200_KARATSUBA
-    return redc_wide_dc(t_in);
-#else
     uint32_t t[17];
 #pragma unroll
     for (int k = 0; k < 16; k++) t[k] = t_in[k];
@@ -441,7 +275,6 @@ struct alignas(32) Fp {
     // t < p*2^256 + p*2^256  =>  result < 2p (t[16] is then 0 because 2p < 2^256)
     final_sub(r.l);
     return r;
-#endif
   }
 
   HD Fp to_mont() const { return (*this) * r2(); }

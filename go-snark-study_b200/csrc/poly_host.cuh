@@ -7,6 +7,14 @@
 
 #include "ntt.cuh"
 
+// Kernel launches of the polynomial orchestration go through these two macros so that the SAME host code (transform
+// plans, division, interpolation, subproduct trees) also runs in the CPU test vehicle (tests/host: the macros become
+// loops over emulated CTAs).  _CTA marks kernels that synchronise inside a block.
+#ifndef B200_LAUNCH
+#define B200_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define B200_LAUNCH_CTA(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace b200 {
 
 struct DevBuf {
@@ -52,12 +60,9 @@ struct NttPlan {
 };
 
 struct PolyCtx {
-  // B200_NTT_FUSED=1: fused shared-memory passes instead of one launch per stage (bit-identical transform, checked on
-  // the CPU emulation in tests/test_host_kernels.py; off until it has been timed on a GPU)
-  static bool fused() {
-    static const bool v = getenv("B200_NTT_FUSED") && atoi(getenv("B200_NTT_FUSED")) != 0;
-    return v;
-  }
+  // Transforms of >= 2^10 points run as fused shared-memory passes (ntt.cuh: k_ntt_fused; 3 passes instead of 21 stage
+  // launches at 2^21 points: 19.36 -> 18.88 ms per 2^20 proof, profiles/r2_notes.md); bit-identical to the stage kernels.
+  static constexpr bool fused() { return true; }
   unsigned long long* launch_counter = nullptr;
   void note(unsigned n) { if (launch_counter) *launch_counter += n; }
   std::map<int, std::unique_ptr<NttPlan>> plans;
@@ -81,8 +86,8 @@ struct PolyCtx {
     cudaError_t e;
     if ((e = p->tw.alloc(half * sizeof(Fr))) != cudaSuccess) return e;
     if ((e = p->tw_inv.alloc(half * sizeof(Fr))) != cudaSuccess) return e;
-    k_twiddles<<<nblk(half, 256), 256, 0, st>>>(p->tw.as<Fr>(), (uint32_t)half, w);
-    k_twiddles<<<nblk(half, 256), 256, 0, st>>>(p->tw_inv.as<Fr>(), (uint32_t)half, w_inv);
+    B200_LAUNCH(k_twiddles, nblk(half, 256), 256, st, p->tw.as<Fr>(), (uint32_t)half, w);
+    B200_LAUNCH(k_twiddles, nblk(half, 256), 256, st, p->tw_inv.as<Fr>(), (uint32_t)half, w_inv);
     *out = p.get();
     plans[logn] = std::move(p);
     return cudaGetLastError();
@@ -97,14 +102,14 @@ struct PolyCtx {
     if (fused() && logn >= 10) {  // experiment: several stages per pass in shared memory (ntt.cuh: k_ntt_fused)
       unsigned passes = 0;
       ntt_fused_passes(logn, 0, [&](uint32_t log_hbot, uint32_t k) {
-        k_ntt_fused<<<N / kNttTile, 256, 0, st>>>(d, pl->tw.as<Fr>(), n_half, log_hbot, k, 0);
+        B200_LAUNCH_CTA(k_ntt_fused, N / kNttTile, 256, st, d, pl->tw.as<Fr>(), n_half, log_hbot, k, 0);
         passes++;
       });
       note(passes);
       return cudaGetLastError();
     }
     for (uint32_t half = n_half; half >= 1; half >>= 1)
-      k_ntt_dif_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw.as<Fr>(), n_half, half, n_half / half);
+      B200_LAUNCH(k_ntt_dif_stage, nblk(n_half, 256), 256, st, d, pl->tw.as<Fr>(), n_half, half, n_half / half);
     note(logn);
     return cudaGetLastError();
   }
@@ -117,14 +122,14 @@ struct PolyCtx {
     if (fused() && logn >= 10) {
       unsigned passes = 0;
       ntt_fused_passes(logn, 1, [&](uint32_t log_hbot, uint32_t k) {
-        k_ntt_fused<<<N / kNttTile, 256, 0, st>>>(d, pl->tw_inv.as<Fr>(), n_half, log_hbot, k, 1);
+        B200_LAUNCH_CTA(k_ntt_fused, N / kNttTile, 256, st, d, pl->tw_inv.as<Fr>(), n_half, log_hbot, k, 1);
         passes++;
       });
       note(passes);
       return cudaGetLastError();
     }
     for (uint32_t half = 1; half <= n_half; half <<= 1)
-      k_ntt_dit_stage<<<nblk(n_half, 256), 256, 0, st>>>(d, pl->tw_inv.as<Fr>(), n_half, half, n_half / half);
+      B200_LAUNCH(k_ntt_dit_stage, nblk(n_half, 256), 256, st, d, pl->tw_inv.as<Fr>(), n_half, half, n_half / half);
     note(logn);
     return cudaGetLastError();
   }
@@ -135,7 +140,7 @@ struct PolyCtx {
     cudaError_t e = plan(logn, &pl, st);
     if (e != cudaSuccess) return e;
     uint32_t N = 1u << logn;
-    k_pointwise_mul<<<nblk(N, 256), 256, 0, st>>>(a, b, N, pl->n_inv, scale ? 1 : 0);
+    B200_LAUNCH(k_pointwise_mul, nblk(N, 256), 256, st, a, b, N, pl->n_inv, scale ? 1 : 0);
     note(1);
     return cudaGetLastError();
   }
@@ -170,19 +175,19 @@ inline cudaError_t series_inverse_rev(PolyCtx& pc, const Divisor& dv, size_t nq,
   const Fr* b = dv.b_mont.as<Fr>();
   uint32_t nb = (uint32_t)dv.nb;
   // f = rev(b): f[i] = b[nb-1-i]
-  k_poly_load<<<1, 32, 0, st>>>(b, nb, 1, 1, 1, A, 1, d_err);
-  k_series_inv0<<<1, 32, 0, st>>>(A, g, d_err);
+  B200_LAUNCH(k_poly_load, 1, 32, st, b, nb, 1, 1, 1, A, 1, d_err);
+  B200_LAUNCH(k_series_inv0, 1, 32, st, A, g, d_err);
   for (size_t P = 1; P < nq; P <<= 1) {
     int l4 = ceil_log2(4 * P);
     uint32_t N4 = 1u << l4;
     uint32_t take = (uint32_t)(2 * P < nb ? 2 * P : nb);
-    k_poly_load<<<nblk(N4, 256), 256, 0, st>>>(b, nb, take, 1, 1, A, N4, d_err);            // f mod x^2P
-    k_poly_load<<<nblk(N4, 256), 256, 0, st>>>(g, (uint32_t)P, (uint32_t)P, 0, 1, B, N4, d_err);  // g
+    B200_LAUNCH(k_poly_load, nblk(N4, 256), 256, st, b, nb, take, 1, 1, A, N4, d_err);            // f mod x^2P
+    B200_LAUNCH(k_poly_load, nblk(N4, 256), 256, st, g, (uint32_t)P, (uint32_t)P, 0, 1, B, N4, d_err);  // g
     PCU(pc.forward(A, l4, st));
     PCU(pc.forward(B, l4, st));
     PCU(pc.pointwise(A, B, l4, true, st));
     PCU(pc.inverse_unscaled(A, l4, st));                     // A = f*g
-    k_two_minus<<<nblk(N4, 256), 256, 0, st>>>(A, (uint32_t)(2 * P), N4);  // A = 2 - f*g mod x^2P
+    B200_LAUNCH(k_two_minus, nblk(N4, 256), 256, st, A, (uint32_t)(2 * P), N4);  // A = 2 - f*g mod x^2P
     PCU(pc.forward(A, l4, st));
     PCU(pc.pointwise(A, B, l4, true, st));
     PCU(pc.inverse_unscaled(A, l4, st));                     // A = g*(2 - f*g)
@@ -205,7 +210,7 @@ inline cudaError_t divisor_prepare(PolyCtx& pc, Divisor& dv, size_t nq, int* d_e
   NttPlan* pl;
   PCU(pc.plan(logn, &pl, st));
   // fold the 1/N of the inverse transform into the cached operand
-  k_scale<<<nblk(N, 256), 256, 0, st>>>(inv, (uint32_t)N, pl->n_inv);
+  B200_LAUNCH(k_scale, nblk(N, 256), 256, st, inv, (uint32_t)N, pl->n_inv);
   dv.nq = nq;
   dv.logn = logn;
   return cudaGetLastError();
@@ -225,12 +230,12 @@ inline cudaError_t poly_div_device(PolyCtx& pc, Divisor& dv, const Fr* d_a, size
   PCU(pc.bufA.ensure(N * sizeof(Fr)));
   Fr* X = pc.bufA.as<Fr>();
   // rev(a) mod x^nq, zero padded to N
-  k_poly_load<<<nblk(N, 256), 256, 0, st>>>(d_a, (uint32_t)na, (uint32_t)nq, 1, a_mont, X, (uint32_t)N, d_err);
+  B200_LAUNCH(k_poly_load, nblk(N, 256), 256, st, d_a, (uint32_t)na, (uint32_t)nq, 1, a_mont, X, (uint32_t)N, d_err);
   PCU(pc.forward(X, logn, st));
   PCU(pc.pointwise(X, dv.inv_ntt.as<Fr>(), logn, false, st));  // 1/N already folded into inv_ntt
   PCU(pc.inverse_unscaled(X, logn, st));
   // rev(q) = X[0..nq)  ->  q natural order, standard form
-  k_poly_store<<<nblk(nq, 256), 256, 0, st>>>(X, (uint32_t)nq, 1, 1, d_q_std);
+  B200_LAUNCH(k_poly_store, nblk(nq, 256), 256, st, X, (uint32_t)nq, 1, 1, d_q_std);
   pc.note(2);
   if (d_rem_std && nb > 1) {
     int lr = ceil_log2(na);
@@ -241,14 +246,14 @@ inline cudaError_t poly_div_device(PolyCtx& pc, Divisor& dv, const Fr* d_a, size
     Fr* Q = pc.bufA.as<Fr>();
     Fr* Bt = pc.bufB.as<Fr>();
     Fr* Am = pc.bufC.as<Fr>();
-    k_poly_load<<<nblk(Nr, 256), 256, 0, st>>>(d_q_std, (uint32_t)nq, (uint32_t)nq, 0, 0, Q, (uint32_t)Nr, d_err);
-    k_poly_load<<<nblk(Nr, 256), 256, 0, st>>>(dv.b_mont.as<Fr>(), (uint32_t)nb, (uint32_t)nb, 0, 1, Bt, (uint32_t)Nr, d_err);
-    k_poly_load<<<nblk(Nr, 256), 256, 0, st>>>(d_a, (uint32_t)na, (uint32_t)na, 0, a_mont, Am, (uint32_t)Nr, d_err);
+    B200_LAUNCH(k_poly_load, nblk(Nr, 256), 256, st, d_q_std, (uint32_t)nq, (uint32_t)nq, 0, 0, Q, (uint32_t)Nr, d_err);
+    B200_LAUNCH(k_poly_load, nblk(Nr, 256), 256, st, dv.b_mont.as<Fr>(), (uint32_t)nb, (uint32_t)nb, 0, 1, Bt, (uint32_t)Nr, d_err);
+    B200_LAUNCH(k_poly_load, nblk(Nr, 256), 256, st, d_a, (uint32_t)na, (uint32_t)na, 0, a_mont, Am, (uint32_t)Nr, d_err);
     PCU(pc.forward(Q, lr, st));
     PCU(pc.forward(Bt, lr, st));
     PCU(pc.pointwise(Q, Bt, lr, true, st));
     PCU(pc.inverse_unscaled(Q, lr, st));
-    k_poly_sub_store<<<nblk(nb - 1, 256), 256, 0, st>>>(Am, Q, (uint32_t)(nb - 1), d_rem_std);
+    B200_LAUNCH(k_poly_sub_store, nblk(nb - 1, 256), 256, st, Am, Q, (uint32_t)(nb - 1), d_rem_std);
   }
   return cudaGetLastError();
 }
@@ -263,13 +268,13 @@ inline cudaError_t poly_mul_device(PolyCtx& pc, const Fr* d_a, size_t la, int a_
   PCU(pc.bufB.ensure(N * sizeof(Fr)));
   Fr* A = pc.bufA.as<Fr>();
   Fr* B = pc.bufB.as<Fr>();
-  k_poly_load<<<nblk(N, 256), 256, 0, st>>>(d_a, (uint32_t)la, (uint32_t)la, 0, a_mont, A, (uint32_t)N, d_err);
-  k_poly_load<<<nblk(N, 256), 256, 0, st>>>(d_b, (uint32_t)lb, (uint32_t)lb, 0, b_mont, B, (uint32_t)N, d_err);
+  B200_LAUNCH(k_poly_load, nblk(N, 256), 256, st, d_a, (uint32_t)la, (uint32_t)la, 0, a_mont, A, (uint32_t)N, d_err);
+  B200_LAUNCH(k_poly_load, nblk(N, 256), 256, st, d_b, (uint32_t)lb, (uint32_t)lb, 0, b_mont, B, (uint32_t)N, d_err);
   PCU(pc.forward(A, logn, st));
   PCU(pc.forward(B, logn, st));
   PCU(pc.pointwise(A, B, logn, true, st));
   PCU(pc.inverse_unscaled(A, logn, st));
-  k_poly_store<<<nblk(lo, 256), 256, 0, st>>>(A, (uint32_t)lo, 0, 1, d_out_std);
+  B200_LAUNCH(k_poly_store, nblk(lo, 256), 256, st, A, (uint32_t)lo, 0, 1, d_out_std);
   return cudaGetLastError();
 }
 

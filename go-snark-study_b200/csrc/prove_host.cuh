@@ -188,7 +188,7 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   // N=2 14.5 vs 11.4 -- profiles/r1_notes.md); the threshold sits between the N=4 and N=8 shares.
   double weighted_terms = 0;
   for (int k = 0; k < 4; k++) weighted_terms += wgt[k] * (double)(pk->hi[k] - pk->lo[k]);
-  static const double min_terms = getenv("B200_AFF_MIN_TERMS") ? atof(getenv("B200_AFF_MIN_TERMS")) : 1.3e6;  // tuning knob
+  const double min_terms = 1.3e6;
   const bool affine_ok = weighted_terms >= min_terms;
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
@@ -409,7 +409,7 @@ inline int glv_decompose(const Fr& k_std, uint64_t out[4], uint32_t neg[2]) {
 // form).  d_out receives PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2) in standard form
 // (or, for a sharded key, the 1 KB partial record).  No host synchronisation.
 int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, size_t npx, const uint64_t* r,
-                    const uint64_t* s, Fq* d_out, cudaStream_t st) {
+                    const uint64_t* s, Fq* d_out, cudaStream_t st, int px_mont = 0) {
   size_t m = pk->m;
   if (nw != m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, m);
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "groth16_prove: len(px) < len(Z)");
@@ -464,7 +464,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
       bool direct = p_lo == 0 && nq <= n_p;
       Fr* h_dst = direct ? sCH + n_c : pk->h_full.as<Fr>();
       if (!direct && !pk->h_full.p) CU(pk->h_full.alloc((pk->m + pk->n_h_bases + 4) * sizeof(Fr)));
-      CU(poly_div_device(*g_poly, pk->Z, d_px, npx, 0, h_dst, nullptr, g_d_err, s3));
+      CU(poly_div_device(*g_poly, pk->Z, d_px, npx, px_mont, h_dst, nullptr, g_d_err, s3));
       size_t have = nq > p_lo ? (nq < p_hi ? nq - p_lo : n_p) : 0;   // valid h coefficients inside [p_lo, p_hi)
       if (!direct && have)
         CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + p_lo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));

@@ -112,3 +112,130 @@ class SyntheticGroth16:
         """96 B per G1 term, 160 B per G2 term, each MSM counted independently."""
         m, n = self.m, self.n
         return 96 * m + 96 * m + 160 * m + 96 * (m - 2) + 96 * (n - 1)
+
+
+class SyntheticCircuit:
+    """The synthetic R1CS of SURVEY §8d (configs 2 / 4): n constraints over m = n + 2 signals [one, pub, x_0 .. x_{n-1}],
+    a multiplication chain with full-width values:
+
+        (x_0 + 5) * x_0 = x_1;     x_k * x_{k-1} = x_{k+1}  (k = 1 .. n-2);     x_{n-1} * x_{n-2} = pub
+
+    1-2 non-zeros per row of A, one in B, one in C (coefficients 1 and the 5 of README.md:174).  CSR arrays are numpy;
+    the witness is the chain evaluated mod r from a seeded x_0 (NPublic = 1: the last product)."""
+
+    def __init__(self, n, seed=SEED_WITNESS):
+        assert n >= 2
+        self.n, self.m, self.npublic = n, n + 2, 1
+        j = np.arange(n, dtype=np.uint32)
+        # A: row 0 = {x_0: 1, one: 5}, row j = {x_j: 1}
+        a_rowptr = np.concatenate(([0, 2], 2 + np.arange(1, n, dtype=np.uint32))).astype(np.uint32)
+        a_col = np.concatenate(([0, 2], 2 + j[1:])).astype(np.uint32)          # columns sorted inside row 0: one, x_0
+        a_val = np.zeros((n + 1, 4), dtype=np.uint64)
+        a_val[:, 0] = 1
+        a_val[0, 0] = 5
+        b_rowptr = np.arange(n + 1, dtype=np.uint32)
+        b_col = np.concatenate(([2], 2 + j[1:] - 1)).astype(np.uint32)          # row 0: x_0; row j: x_{j-1}
+        c_col = np.concatenate((3 + j[:-1], [1])).astype(np.uint32)             # row j: x_{j+1}; last row: pub
+        ones = np.zeros((n, 4), dtype=np.uint64)
+        ones[:, 0] = 1
+        self.csr = [(a_rowptr, a_col, a_val), (b_rowptr, b_col, ones), (b_rowptr.copy(), c_col, ones.copy())]
+        x0 = limbs_to_ints(rand_limbs(1, seed))[0] % R
+        xs = [x0, (x0 + 5) * x0 % R]
+        for k in range(1, n - 1):
+            xs.append(xs[k] * xs[k - 1] % R)
+        pub = xs[n - 1] * xs[n - 2] % R
+        self.witness = [1, pub] + xs[:n]
+        self.public_signals = [pub]
+
+    def dense(self):
+        """The same R1CS as dense n x m matrices (small n only): the reference's a, b, c."""
+        out = []
+        for rowptr, col, val in self.csr:
+            vals = limbs_to_ints(val)
+            M = [[0] * self.m for _ in range(self.n)]
+            for r_ in range(self.n):
+                for k in range(int(rowptr[r_]), int(rowptr[r_ + 1])):
+                    M[r_][int(col[k])] = vals[k]
+            out.append(M)
+        return out
+
+
+class CircuitGroth16(SyntheticGroth16):
+    """A REAL Groth16 instance at benchmark sizes: SyntheticCircuit's R1CS, a satisfying witness, and the CRS that
+    groth16.GenerateTrustedSetup (groth16/groth16.go:94-222) yields for seeded toxic values — every point is still
+    k*G with a known k (k = Eval(alphas[i], tau) etc., obtained through the sparse A^T l(tau) of b200_qap_eval_at), so
+    the known-discrete-log parity check of SyntheticGroth16 keeps working AND the proof verifies under the real Vk.
+    px comes from the sparse QAP front end (b200_qap_px); the expected proof is computed in the exponent from the QAP
+    identity  h(tau) Z(tau) = A(tau) B(tau) - C(tau)  — independently of the GPU's px and h."""
+
+    def __init__(self, logn, mint=True):
+        from .r1csqap import SparseR1CS
+        self.logn = logn
+        n = self.n = 1 << logn
+        m = self.m = n + 2
+        self.npublic = 1
+        self.n_ptd = m - 1
+        self.circuit = SyntheticCircuit(n)
+        self.r1cs = SparseR1CS(n, m, self.circuit.csr)
+        tox = [x % R for x in limbs_to_ints(rand_limbs(5, SEED_TOXIC))]
+        self.toxic = dict(zip(("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta"), tox))
+        t, ka, kb, kg, kd = tox
+        at_l, bt_l, ct_l, zt = self.r1cs.EvalAt(t)
+        at, bt, ct = limbs_to_ints(at_l), limbs_to_ints(bt_l), limbs_to_ints(ct_l)
+        self.at_s, self.bt_s, self.ct_s, self.zt = at, bt, ct, zt
+        inv_d, inv_g = pow(kd, -1, R), pow(kg, -1, R)
+        l1 = self.npublic + 1
+        kc = [0] * l1 + [inv_d * ((at[i] * kb + bt[i] * ka + ct[i]) % R) % R for i in range(l1, m)]      # :181-200
+        self.k_ic = [inv_g * ((at[i] * kb + bt[i] * ka + ct[i]) % R) % R for i in range(l1)]               # :202-219
+        ptd, cur = [], zt * inv_d % R                                                                      # :139-149
+        for _ in range(self.n_ptd):
+            ptd.append(cur)
+            cur = cur * t % R
+        self.k_at, self.k_b, self.k_c, self.k_ptd = (ints_to_limbs(v) for v in (at, bt, kc, ptd))
+        self.k_alpha, self.k_beta, self.k_delta, self.k_gamma = (ints_to_limbs([v]) for v in (ka, kb, kd, kg))
+        self.w = ints_to_limbs(self.circuit.witness)
+        rs = limbs_to_ints(rand_limbs(2, SEED_RS))
+        self.r, self.s = rs[0] >> 13, rs[1] >> 13
+        self.z = np.zeros((n + 1, 4), dtype=np.uint64)
+        check(lib().b200_zero_poly(n, ptr(self.z)))                  # Z = prod_{i=1..m-2}(x - i), groth16.go:122-132
+        if mint:
+            self.mint()
+
+    def mint(self):
+        self.at = mint_points(1, self.k_at)
+        self.b1 = mint_points(1, self.k_b)
+        self.b2 = mint_points(2, self.k_b)
+        self.cd = mint_points(1, self.k_c)
+        self.ptd = mint_points(1, self.k_ptd)
+        self.alpha1, self.beta1, self.delta1 = (mint_points(1, k) for k in (self.k_alpha, self.k_beta, self.k_delta))
+        self.beta2, self.delta2, self.gamma2 = (mint_points(2, k) for k in (self.k_beta, self.k_delta, self.k_gamma))
+        self.ic = mint_points(1, ints_to_limbs(self.k_ic))
+        _, _, _, self.px = self.r1cs.combine_limbs(self.w, want_abc=False)
+
+    def expected_dlogs(self):
+        w = self.circuit.witness
+        dot = lambda ks: sum(a * b for a, b in zip(ks, w)) % R
+        t, ka, kb, kg, kd = (self.toxic[k] for k in ("T", "Kalpha", "Kbeta", "Kgamma", "Kdelta"))
+        A, B, C = dot(self.at_s), dot(self.bt_s), dot(self.ct_s)
+        r, s = self.r, self.s
+        a = (A + ka + r * kd) % R
+        b = (B + kb + s * kd) % R
+        l1 = self.npublic + 1
+        kc = limbs_to_ints(self.k_c)
+        c_msm = sum(x * y for x, y in zip(kc[l1:], w[l1:])) % R
+        h_msm = (A * B - C) * pow(kd, -1, R) % R                     # sum_i h_i tau^i Z(tau)/delta = (A B - C)(tau)/delta
+        c = (c_msm + h_msm + s * a + r * b - r * s * kd) % R
+        return a, b, c
+
+    def vk_limbs(self):
+        """(ic, alpha1, beta2, gamma2, delta2) as limb arrays for b200_groth16_verify."""
+        return self.ic, self.alpha1, self.beta2, self.gamma2, self.delta2
+
+    def verify(self, pi_a, pi_b, pi_c):
+        """groth16.VerifyProof (groth16.go:281-305) on the GPU against this instance's real verification key."""
+        import ctypes
+        ok = ctypes.c_int(0)
+        pub = ints_to_limbs(self.circuit.public_signals)
+        check(lib().b200_groth16_verify(ptr(self.ic), self.npublic + 1, ptr(self.alpha1), ptr(self.beta2), ptr(self.gamma2),
+                                        ptr(self.delta2), ptr(pi_a), ptr(pi_b), ptr(pi_c), ptr(pub), 1, ctypes.byref(ok)))
+        return bool(ok.value)

@@ -42,12 +42,18 @@ extern "C" {
 
 typedef uint64_t b200_bases_t; /* device-resident, window-precomputed base-point set */
 typedef uint64_t b200_pk_t;    /* device-resident proving key                        */
+typedef uint64_t b200_r1cs_t;  /* device-resident sparse R1CS (CSR + CSC)            */
 
 /* ---- context ------------------------------------------------------------ */
 int b200_init(int device);        /* idempotent; selects the CUDA device of this process */
 int b200_shutdown(void);
 const char* b200_last_error(void);
 int b200_version(void);
+/* Process-wide options for objects created AFTERWARDS.  B200_CFG_ACC_MODE: bucket-accumulation kernel of base sets and
+ * proving keys — 0 auto (batched affine where bucket population and shard size amortise its rounds, else XYZZ mixed
+ * adds), 1 batched affine, 2 XYZZ.  Same results either way; the parity tests run every MSM size under both.          */
+#define B200_CFG_ACC_MODE 1
+int b200_config(int key, int value);
 
 /* ---- base-point sets (the CRS arrays of groth16.Pk / snark.Pk) ---------- */
 /* Upload n Jacobian points, normalise to affine Montgomery form on the device
@@ -59,6 +65,8 @@ int b200_g1_bases_load(const uint64_t* points_jac, size_t n, int window_bits, b2
 int b200_g2_bases_load(const uint64_t* points_jac, size_t n, int window_bits, b200_bases_t* out);
 int b200_bases_free(b200_bases_t h);
 int b200_bases_info(b200_bases_t h, size_t* n, int* group, int* window_bits, int* n_windows);
+/* which bucket-accumulation kernel the set was built for: 1 batched affine, 2 XYZZ (see b200_config) */
+int b200_bases_acc_mode(b200_bases_t h, int* mode);
 
 /* ---- multi-scalar multiplication ---------------------------------------- */
 /* out = sum_i scalars[i] * P_i over the first n bases of the set.
@@ -178,7 +186,7 @@ int b200_poly_eval(const uint64_t* v, size_t n, const uint64_t x[4], uint64_t ou
 /* out[i] = Eval(polys[i], x) for m polynomials of n coefficients each (row-major): the At/Bt/Ct loops of
  * GenerateTrustedSetup (groth16/groth16.go:164-205, snark.go:181-218).                                        */
 int b200_poly_eval_batch(const uint64_t* polys, size_t m, size_t n, const uint64_t x[4], uint64_t* out);
-/* out[0..n] = coefficients of prod_{i=1}^{n} (x - i): the "z pol" of groth16.go:122-132 / snark.go:221-232.   */
+/* out[0..n] = coefficients of prod_{i=1}^{n} (x - i): the "z pol" of groth16.go:122-132 / snark.go:221-232; n <= 2^26. */
 int b200_zero_poly(size_t n, uint64_t* out);
 
 /* ---- verifier side ------------------------------------------------------------------ */
@@ -210,6 +218,35 @@ int b200_r1cs_to_qap(const uint64_t* a, const uint64_t* b, const uint64_t* c, si
  * each, ap/bp/cp m x n row-major) and px = ax*bx - cx (2n-1 coefficients).                                            */
 int b200_combine_polynomials(const uint64_t* r, size_t m, const uint64_t* ap, const uint64_t* bp, const uint64_t* cp,
                              size_t n, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px);
+
+/* ---- sparse QAP front end (any n): the same mathematics without the dense m x n polynomial matrices -------- */
+/* A sparse R1CS, n constraints x m signals, three CSR matrices (rowptr n+1 entries, col/val nnz entries; val = 4-limb
+ * coefficients reduced mod r, negative coefficients of circuitcompiler (circuit.go:78) sent as r - |v|).  Stays on
+ * the device; also stored transposed for the trusted setup.  Replaces the dense a, b, c [][]*big.Int arguments of
+ * PolynomialField.R1CSToQAP (r1csqap/r1csqap.go:161) where m*n coefficients cannot exist (137 GB per matrix at
+ * n = 2^16).                                                                                              */
+int b200_r1cs_load(size_t n, size_t m, const uint32_t* a_rowptr, const uint32_t* a_col, const uint64_t* a_val,
+                   const uint32_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val, const uint32_t* c_rowptr,
+                   const uint32_t* c_col, const uint64_t* c_val, b200_r1cs_t* out);
+int b200_r1cs_free(b200_r1cs_t h);
+/* CombinePolynomials(w, R1CSToQAP(a, b, c)) (r1csqap/r1csqap.go:161-210) fused: ax, bx, cx (n coefficients each, any
+ * may be NULL) and px = ax*bx - cx (2n-1 coefficients).  ax is the unique polynomial of degree < n with
+ * ax(j+1) = (A w)_j: one sparse mat-vec and one O(n log^2 n) interpolation over {1..n} per matrix.  Field-exact, so
+ * equal to the reference's coefficients wherever the reference can run (n <= 21).                          */
+int b200_qap_px(b200_r1cs_t h, const uint64_t* w, size_t nw, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px);
+/* at[i] = Eval(alphas[i], tau), bt[i], ct[i] for every signal i < m — the loops of GenerateTrustedSetup
+ * (groth16/groth16.go:164-205, snark.go:171-189) — as A^T l(tau) with l the Lagrange basis of {1..n} at tau, and
+ * zt = prod_{i=1..nz} (tau - i) (groth16.go:122-136 with nz = len(alphas) - 2).  tau must not be one of 1..n.          */
+int b200_qap_eval_at(b200_r1cs_t h, const uint64_t tau[4], size_t nz, uint64_t* at, uint64_t* bt, uint64_t* ct,
+                     uint64_t zt[4]);
+/* PolynomialField.LagrangeInterpolation over x = 1..n (r1csqap/r1csqap.go:150-158) at any n <= 2^26: n values ->
+ * n coefficients.                                                                                                    */
+int b200_interpolate(const uint64_t* values, size_t n, uint64_t* coeffs);
+/* groth16.GenerateProofs fed from the witness: px is computed on the device from the resident R1CS (b200_qap_px) and
+ * never leaves HBM; otherwise identical to b200_groth16_prove (groth16/groth16.go:225-278 after the caller's
+ * CombinePolynomials step, cli/main.go:339-349).                                                                     */
+int b200_groth16_prove_witness(b200_pk_t pk, b200_r1cs_t r1cs, const uint64_t* w, size_t nw, const uint64_t r[4],
+                               const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24], uint64_t pi_c[12]);
 
 /* ---- element-wise group operations, reference formulas (X,Y,Z-exact) ------------------- */
 /* bn128.G1.Add / Double / Neg / Affine (bn128/g1.go:32-170) and the G2 twins (bn128/g2.go:32-200), n independent

@@ -55,7 +55,6 @@ void t_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* 
       case 2: r = x * y; break;
       case 3: r = x.inverse(); break;
       case 6: r = x.inverse_vartime(); break;
-      case 7: r = F::mul_impl_k(x, y); break;   // Karatsuba product + wide reduction
       default: r = x.neg(); break;
     }
     store(out, r.from_mont());
@@ -75,14 +74,16 @@ void t_fq2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   }
   store(out, r.from_mont());
 }
-// w[0..16) = a * b as plain 512-bit integers (any 256-bit operands): schoolbook (k = 0) or Karatsuba (k = 1)
+// w[0..16) = a * b as plain 512-bit integers (any 256-bit operands)
 void t_mul_full(int k, const uint32_t* a, const uint32_t* b, uint32_t* w) {
-  if (k) Fq::mul_full_k(w, a, b); else Fq::mul_full(w, a, b);
+  (void)k;
+  Fq::mul_full(w, a, b);
 }
-// Montgomery reduction of a 512-bit value (t < p * 2^256): rippled (k = 0) or deferred-carry (k = 1) variant
+// Montgomery reduction of a 512-bit value (t < p * 2^256)
 void t_redc_wide(int field, int k, const uint32_t* t, uint32_t* out) {
-  if (field == 0) store(out, k ? Fq::redc_wide_dc(t) : Fq::redc_wide(t));
-  else store(out, k ? Fr::redc_wide_dc(t) : Fr::redc_wide(t));
+  (void)k;
+  if (field == 0) store(out, Fq::redc_wide(t));
+  else store(out, Fr::redc_wide(t));
 }
 int t_geq(int field, const uint32_t* a) { return field == 0 ? load<Fq>(a).geq_modulus() : load<Fr>(a).geq_modulus(); }
 // pairing of AFFINE standard-form inputs: g1 = (x, y), g2 = (x.c0, x.c1, y.c0, y.c1); out = 12 field elements in

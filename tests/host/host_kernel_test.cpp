@@ -14,6 +14,14 @@
 #include "bucket_affine.cuh"
 #include "ntt.cuh"
 
+// the polynomial orchestration (poly_host.cuh, qap_sparse.cuh) launches through these: sequential emulated threads for
+// plain kernels, one OS thread per CUDA thread for kernels that synchronise inside a CTA
+template <class K> void stub_launch_threads(unsigned nblocks, unsigned nthreads, K k);
+template <class K> void stub_launch_cta(unsigned nblocks, unsigned nthreads, K k);
+#define B200_LAUNCH(kernel, grid, block, stream, ...) stub_launch_threads((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#define B200_LAUNCH_CTA(kernel, grid, block, stream, ...) stub_launch_cta((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#include "qap_sparse.cuh"
+
 using namespace b200;
 
 // ---- CTA-at-a-time emulation: one OS thread per CUDA thread, barriers for __syncthreads and the warp shuffles ------
@@ -127,9 +135,8 @@ template <class F, int T>
 void run_forward(int variant, const AffineRound<F>& a, unsigned nb) {
   for (unsigned b = 0; b < nb; b++)
     run_cta(b, kAffBlock, nb, [&] {
-      if (variant == 0) k_affine_forward<F, T, 1, false>(a);
-      else if (variant == 1) k_affine_forward<F, T, 1, true>(a);
-      else k_affine_forward_sp<F, T, 1>(a);
+      (void)variant;
+      k_affine_forward<F, T, 1>(a);
     });
   for (unsigned b = 0; b < nb; b++) a.btot[b] = a.btot[b].inverse();   // k_affine_invert
 }
@@ -142,10 +149,8 @@ void run_backward(int variant, const AffineRound<F>& a, unsigned nb) {
     for (unsigned t = 0; t < kAffBlock; t++) {
       blockIdx.x = b;
       threadIdx.x = t;
-      if (variant == 0) k_affine_backward<F, T, 1, false>(a);
-      else if (variant == 1) k_affine_backward_lr<F, T, 1>(a);
-      else if (variant == 2) k_affine_backward_sp<F, T, 1>(a);
-      else k_affine_backward<F, T, 1, true>(a);   // L2-prefetch variant (prefetches are no-ops here)
+      (void)variant;
+      k_affine_backward<F, T, 1>(a);
     }
 }
 
@@ -198,64 +203,6 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
       }
     }
     run_backward<F, T>(variant, ar, nb);
-    prev = ar.out;
-  }
-  for (uint32_t s = 0; s < nslices; s++) {
-    store_std(out_std + (size_t)s * 2 * W, prev[s].x);
-    store_std(out_std + (size_t)s * 2 * W + W, prev[s].y);
-  }
-  return 0;
-}
-
-// thread-per-slice fused rounds (k_affine_ts_forward1 / k_affine_ts_round), all rounds, CTA emulation throughout
-template <class F, bool SMEM>
-int affine_rounds_ts(const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries, const uint32_t* slice_start,
-                     const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
-  constexpr int W = sizeof(F) / 4;
-  std::vector<Affine<F>> table(n_pts);
-  for (uint32_t i = 0; i < n_pts; i++) {
-    table[i].x = load_std<F>(table_std + (size_t)i * 2 * W);
-    table[i].y = load_std<F>(table_std + (size_t)i * 2 * W + W);
-  }
-  const uint32_t S = 1u << R;
-  unsigned nb = (nslices + kAffBlock - 1) / kAffBlock;
-  std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
-  std::vector<F> preA((size_t)nslices * (S / 2)), preB((size_t)nslices * (S / 2));
-  std::vector<F> othA((size_t)nb * kAffBlock), othB((size_t)nb * kAffBlock), btA(nb), btB(nb);
-  AffineRoundTS<F> ar{};
-  ar.table = table.data();
-  ar.entries = entries;
-  ar.slice_start = slice_start;
-  ar.slice_end = slice_end;
-  ar.nslices_ptr = &nslices;
-  F* pres[2] = {preA.data(), preB.data()};
-  F* oths[2] = {othA.data(), othB.data()};
-  F* bts[2] = {btA.data(), btB.data()};
-  Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
-  // round-1 forward pass
-  ar.round = 1;
-  ar.q_log = R - 1;
-  ar.pre_next = pres[0];
-  ar.others_next = oths[0];
-  ar.btot_next = bts[0];
-  for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_forward1<F>(ar); });
-  for (unsigned b = 0; b < nb; b++) bts[0][b] = bts[0][b].inverse();
-  const Affine<F>* prev = nullptr;
-  for (uint32_t r = 1; r <= R; r++) {
-    ar.round = r;
-    ar.q_log = R - r;
-    ar.prev = prev;
-    ar.out = bufs[(r - 1) & 1];
-    ar.pre = pres[(r - 1) & 1];
-    ar.others = oths[(r - 1) & 1];
-    ar.btot = bts[(r - 1) & 1];
-    ar.pre_next = pres[r & 1];
-    ar.others_next = oths[r & 1];
-    ar.btot_next = bts[r & 1];
-    ar.last = r == R;
-    for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_ts_round<F, 1, SMEM>(ar); });
-    if (!ar.last)
-      for (unsigned b = 0; b < nb; b++) bts[r & 1][b] = bts[r & 1][b].inverse();
     prev = ar.out;
   }
   for (uint32_t s = 0; s < nslices; s++) {
@@ -381,9 +328,9 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
       ar.out = bufs[(r - 1) & 1];
       unsigned nb = cdiv((size_t)nslices << ar.q_log, kAffBlock * T);
       if (nb == 0) nb = 1;
-      for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_forward<F, T, 1, false>(ar); });
+      for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_forward<F, T, 1>(ar); });
       for (unsigned b = 0; b < cdiv((size_t)nb * 32, 128); b++) run_cta(b, 128, cdiv((size_t)nb * 32, 128), [&] { k_affine_invert<F>(ar.btot, nb); });
-      run_threads(nb, kAffBlock, [&] { k_affine_backward<F, T, 1, false>(ar); });
+      run_threads(nb, kAffBlock, [&] { k_affine_backward<F, T, 1>(ar); });
       prev = ar.out;
     }
     for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)
@@ -470,14 +417,74 @@ int ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* 
 }
 }  // namespace
 
+template <class K> void stub_launch_threads(unsigned nblocks, unsigned nthreads, K k) { run_threads(nblocks, nthreads, k); }
+template <class K> void stub_launch_cta(unsigned nblocks, unsigned nthreads, K k) {
+  for (unsigned b = 0; b < nblocks; b++) run_cta(b, nthreads, nblocks, k);
+}
+
+namespace {
+// The library's OWN host orchestration (poly_host.cuh: transform plans, fused passes, division with the cached inverse
+// series; qap_sparse.cuh: subproduct tree, Newton coefficients, divide and conquer) on the emulated kernels.
+PolyCtx& poly_ctx() {
+  static PolyCtx pc;
+  return pc;
+}
+int qap_interpolate(const uint32_t* values_std, uint32_t n, uint32_t* coeffs_std) {
+  size_t N = 1;
+  while (N < n) N <<= 1;
+  static std::map<size_t, std::unique_ptr<QapDomain>> doms;
+  auto& dom = doms[N];
+  if (!dom) {
+    dom = std::make_unique<QapDomain>();
+    if (qap_domain_build(poly_ctx(), *dom, N, nullptr)) return 1;
+  }
+  std::vector<Fr> v(n), c(N), out(n);
+  std::memcpy(v.data(), values_std, (size_t)n * sizeof(Fr));
+  for (auto& x : v) x = x.to_mont();
+  QapWork wk;
+  if (interpolate_ap(poly_ctx(), *dom, wk, v.data(), n, n, 1, c.data(), nullptr)) return 2;
+  for (uint32_t i = 0; i < n; i++) out[i] = c[i].from_mont();
+  for (size_t i = n; i < N; i++)
+    if (!c[i].is_zero()) return 3;   // degree < n
+  std::memcpy(coeffs_std, out.data(), (size_t)n * sizeof(Fr));
+  return 0;
+}
+int qap_zero_poly(uint32_t n, uint32_t* out_std) {   // prod_{i=1..n}(x - i): Newton basis element n
+  size_t N = 1;
+  while (N < (size_t)n + 1) N <<= 1;
+  QapDomain dom;
+  if (qap_domain_build(poly_ctx(), dom, N, nullptr)) return 1;
+  std::vector<Fr> P(N, Fr::zero()), X(N);
+  P[n] = Fr::one();
+  if (newton_to_monomial(poly_ctx(), dom, P.data(), X.data(), 1, nullptr)) return 2;
+  for (uint32_t i = 0; i <= n; i++) {
+    Fr v = P[i].from_mont();
+    std::memcpy(out_std + 8 * (size_t)i, &v, sizeof(Fr));
+  }
+  return 0;
+}
+int poly_div_orch(const uint32_t* a_std, uint32_t na, const uint32_t* b_std, uint32_t nb, uint32_t* q_std, uint32_t* rem_std) {
+  Divisor dv;
+  std::vector<Fr> b(nb), a(na), q(na - nb + 1), rem(nb > 1 ? nb - 1 : 1);
+  std::memcpy(b.data(), b_std, (size_t)nb * sizeof(Fr));
+  std::memcpy(a.data(), a_std, (size_t)na * sizeof(Fr));
+  for (auto& x : b) x = x.to_mont();
+  if (dv.b_mont.alloc(nb * sizeof(Fr))) return 1;
+  std::memcpy(dv.b_mont.p, b.data(), nb * sizeof(Fr));
+  dv.nb = nb;
+  int err = 0;
+  if (poly_div_device(poly_ctx(), dv, a.data(), na, 0, q.data(), rem_std ? rem.data() : nullptr, &err, nullptr)) return 2;
+  std::memcpy(q_std, q.data(), q.size() * sizeof(Fr));
+  if (rem_std && nb > 1) std::memcpy(rem_std, rem.data(), (size_t)(nb - 1) * sizeof(Fr));
+  return err ? 100 + err : 0;
+}
+}  // namespace
+
 extern "C" {
-int t_affine_rounds_ts(int group, int smem, const uint32_t* table_std, uint32_t n_pts, const uint32_t* entries,
-                       const uint32_t* slice_start, const uint32_t* slice_end, uint32_t nslices, uint32_t R, uint32_t* out_std) {
-  if (group == 1)
-    return smem ? affine_rounds_ts<Fq, true>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
-                : affine_rounds_ts<Fq, false>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
-  return smem ? affine_rounds_ts<Fq2, true>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std)
-              : affine_rounds_ts<Fq2, false>(table_std, n_pts, entries, slice_start, slice_end, nslices, R, out_std);
+int t_qap_interpolate(const uint32_t* values_std, uint32_t n, uint32_t* coeffs_std) { return qap_interpolate(values_std, n, coeffs_std); }
+int t_qap_zero_poly(uint32_t n, uint32_t* out_std) { return qap_zero_poly(n, out_std); }
+int t_poly_div_orch(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* q, uint32_t* rem) {
+  return poly_div_orch(a, na, b, nb, q, rem);
 }
 int t_ntt_compare(const uint32_t* in_std, int logn, int dit, int max_k, uint32_t* out_stage, uint32_t* out_fused) {
   return ntt_compare(in_std, logn, dit, max_k, out_stage, out_fused);

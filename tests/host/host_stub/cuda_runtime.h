@@ -25,6 +25,18 @@ inline thread_local Dim3Stub threadIdx, blockIdx, blockDim, gridDim;
 struct uint2 { unsigned x, y; };
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 typedef void* cudaStream_t;
+// just enough of the runtime API for the host orchestration of poly_host.cuh / qap_sparse.cuh (device memory = heap)
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+inline cudaError_t cudaMalloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t b) { return cudaMalloc(reinterpret_cast<void**>(p), b); }
+inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t b, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, b); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t b, cudaMemcpyKind) { std::memmove(d, s, b); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t b, cudaStream_t) { std::memset(d, v, b); return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaGetLastError() { return 0; }
 
 [[noreturn]] inline void stub_abort(const char* what) { std::fprintf(stderr, "host stub: %s is not emulated\n", what); std::abort(); }
 // provided by the test translation unit (CTA-at-a-time emulation); mode 0 = idx, 1 = up, 2 = down

@@ -92,50 +92,3 @@ def test_cli_trustedsetup_prove_verify_with_go_in_the_loop(golden_dir, proto, ca
     finally:
         os.chdir(cwd)
         shutil.rmtree(d)
-
-
-@pytest.mark.timeout(900)
-@pytest.mark.parametrize("group,logn", [(1, 20), (2, 22)])
-def test_msm_full_size_known_discrete_logs(group, logn):
-    """BASELINE configs 3 and 5 (G1 MSM N = 2^20, G2 MSM N = 2^22) at full size: P_i = k_i*G minted on the GPU, so
-    sum s_i P_i = (sum s_i k_i mod r)*G — one CPU scalar multiplication gives the exact expected point.
-    Full-width scalars with 1 % zeros and a block of small (witness-like) values; linearity: msm(s) + msm(s') = msm(s+s')."""
-    import numpy as np
-    from gosnark_b200 import _lib, bn128
-    n = 1 << logn
-    G = G1 if group == 1 else G2
-    rng = np.random.default_rng(1000 + group)
-
-    def rand_limbs(count):
-        a = rng.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64) * np.uint64(2) + \
-            rng.integers(0, 2, size=(count, 4), dtype=np.uint64)
-        a[:, 3] &= np.uint64((1 << 61) - 1)                 # < 2^253 < r
-        return a
-
-    ks = rand_limbs(n)
-    ks[:, 0] |= np.uint64(1)                                # non-zero
-    words = 12 if group == 1 else 24
-    gen = bn128._flatten_g1([bn128.G1.G]) if group == 1 else bn128._flatten_g2([bn128.G2.G])
-    pts = np.zeros((n, words), dtype=np.uint64)
-    L = _lib.lib()
-    _lib.check((L.b200_g1_mul_batch_bcast if group == 1 else L.b200_g2_mul_batch_bcast)(_lib.ptr(gen), _lib.ptr(ks), n, _lib.ptr(pts)))
-    bs = bn128.BaseSet(group, limbs=pts)
-    try:
-        s1, s2 = rand_limbs(n), rand_limbs(n)
-        s1[rng.integers(0, n, size=n // 100)] = 0           # 1 % zero scalars
-        s1[: n // 8, 1:] = 0                                # an eighth of the vector: 64-bit values
-        kk = _lib.limbs_to_ints(ks)
-        exp = []
-        for s in (s1, s2):
-            sv = _lib.limbs_to_ints(s)
-            e = G.affine(G.mul_scalar(G.G, sum(a * b for a, b in zip(kk, sv)) % o.R))
-            exp.append(e)
-            got = bs.msm(limbs=s)
-            assert (got[0], got[1]) == (e[0], e[1])
-        ssum = _lib.ints_to_limbs([(a + b) % o.R for a, b in zip(_lib.limbs_to_ints(s1), _lib.limbs_to_ints(s2))])
-        got = bs.msm(limbs=ssum)
-        one = 1 if group == 1 else (1, 0)
-        esum = G.affine(G.add((exp[0][0], exp[0][1], one), (exp[1][0], exp[1][1], one)))
-        assert (got[0], got[1]) == (esum[0], esum[1])
-    finally:
-        bs.free()

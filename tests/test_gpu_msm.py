@@ -64,9 +64,10 @@ def test_k1_g1_kat_on_gpu(bn):
     assert out[2] == 1
 
 
-@pytest.mark.parametrize("g,n,c", [(1, 1, 0), (1, 7, 4), (1, 33, 0), (1, 200, 9), (1, 200, 16), (1, 64, 13),
-                                   (2, 1, 0), (2, 9, 5), (2, 40, 0), (2, 40, 16)])
-def test_msm_vs_reference_loop(bn, g, n, c):
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("g,n,c", [(1, 1, 0), (1, 7, 4), (1, 33, 0), (1, 200, 9), (1, 200, 16), (1, 64, 13), (1, 300, 5),
+                                   (2, 1, 0), (2, 9, 5), (2, 40, 0), (2, 40, 16), (2, 120, 4)])
+def test_msm_vs_reference_loop(bn, g, n, c, mode):
     """Same inputs as the reference loop (Jacobian CRS entries with Z != 1, some
     (0,0,0), full-width / zero / one scalars) -> same affine point."""
     G = OG[g]
@@ -79,8 +80,10 @@ def test_msm_vs_reference_loop(bn, g, n, c):
         scalars[3] = 0
         scalars[4] = 1
     exp = o.msm_reference_order(G, pts, scalars)
-    bs = bn.BaseSet(g, pts, window_bits=c)
+    bs = bn.BaseSet(g, pts, window_bits=c, acc_mode=mode)
     try:
+        if mode == 2:
+            assert bs.acc_mode() == 2
         assert bs.msm(scalars) == aff(g, exp)
         # a prefix of the base set with fewer scalars (PowersTauDelta[:len(hx)], groth16.go:269-271)
         if n > 4:
@@ -105,8 +108,9 @@ def test_msm_repeated_points_and_cancellation(bn, g):
     assert grp(bn, g).MSM([P, P], [R - 1, 1]) == aff(g, G.zero3())     # (r-1)P + P = rP = O
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("g,n", [(1, 1 << 14), (2, 1 << 11)])
-def test_msm_known_discrete_logs(bn, g, n):
+def test_msm_known_discrete_logs(bn, g, n, mode):
     """SURVEY §8(c) large-N parity: P_i = k_i*G, so sum s_i P_i = (sum s_i k_i mod r)*G."""
     G = OG[g]
     rng = random.Random(77 + g)
@@ -114,8 +118,9 @@ def test_msm_known_discrete_logs(bn, g, n):
     pts = grp(bn, g).MulScalarBatch([G.G], ks)
     for i in (0, n // 2, n - 1):
         assert pts[i] == G.mul_scalar(G.G, ks[i])
-    bs = bn.BaseSet(g, pts)
+    bs = bn.BaseSet(g, pts, acc_mode=mode)
     try:
+        assert bs.acc_mode() == mode               # both accumulation kernels are covered explicitly
         for dist in ("full", "small", "ones"):
             if dist == "full":
                 ss = [rng.randrange(R) for _ in range(n)]
@@ -145,3 +150,53 @@ def test_scalar_range_rejected(bn):
         bs.free()
     with pytest.raises(_lib.B200Error):
         bn.BaseSet(1, [(o.Q, 2, 1)])
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("group,logn", [(1, 20), (2, 22)])
+def test_msm_full_size_known_discrete_logs(bn, group, logn, mode):
+    """BASELINE configs 3 and 5 (G1 MSM N = 2^20, G2 MSM N = 2^22) at full size, under BOTH accumulation kernels:
+    P_i = k_i*G minted on the GPU, so sum s_i P_i = (sum s_i k_i mod r)*G — one CPU scalar multiplication gives the exact
+    expected point (SURVEY §8c).  Full-width scalars with 1 % zeros and a block of small (witness-like) values;
+    linearity: msm(s) + msm(s') = msm(s + s')."""
+    import numpy as np
+    from gosnark_b200 import _lib, bn128
+    n = 1 << logn
+    G = OG[group]
+    rng = np.random.default_rng(1000 + group)
+
+    def rand_limbs(count):
+        a = rng.integers(0, 1 << 63, size=(count, 4), dtype=np.uint64) * np.uint64(2) + \
+            rng.integers(0, 2, size=(count, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)                 # < 2^253 < r
+        return a
+
+    ks = rand_limbs(n)
+    ks[:, 0] |= np.uint64(1)                                # non-zero
+    words = 12 if group == 1 else 24
+    gen = bn128._flatten_g1([bn128.G1.G]) if group == 1 else bn128._flatten_g2([bn128.G2.G])
+    pts = np.zeros((n, words), dtype=np.uint64)
+    L = _lib.lib()
+    _lib.check((L.b200_g1_mul_batch_bcast if group == 1 else L.b200_g2_mul_batch_bcast)(_lib.ptr(gen), _lib.ptr(ks), n, _lib.ptr(pts)))
+    bs = bn128.BaseSet(group, limbs=pts, acc_mode=mode)
+    try:
+        assert bs.acc_mode() == mode
+        s1, s2 = rand_limbs(n), rand_limbs(n)
+        s1[rng.integers(0, n, size=n // 100)] = 0           # 1 % zero scalars
+        s1[: n // 8, 1:] = 0                                # an eighth of the vector: 64-bit values
+        kk = _lib.limbs_to_ints(ks)
+        exp = []
+        for s in (s1, s2):
+            sv = _lib.limbs_to_ints(s)
+            e = G.affine(G.mul_scalar(G.G, sum(a * b for a, b in zip(kk, sv)) % o.R))
+            exp.append(e)
+            got = bs.msm(limbs=s)
+            assert (got[0], got[1]) == (e[0], e[1])
+        ssum = _lib.ints_to_limbs([(a + b) % o.R for a, b in zip(_lib.limbs_to_ints(s1), _lib.limbs_to_ints(s2))])
+        got = bs.msm(limbs=ssum)
+        one = 1 if group == 1 else (1, 0)
+        esum = G.affine(G.add((exp[0][0], exp[0][1], one), (exp[1][0], exp[1][1], one)))
+        assert (got[0], got[1]) == (esum[0], esum[1])
+    finally:
+        bs.free()

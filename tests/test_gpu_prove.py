@@ -159,3 +159,33 @@ def test_prove_argument_errors(mods, golden_dir):
     ok = groth16.GenerateProofs(cc, pk, g["witness"], g["px"], r=0, s=0)       # r = s = 0: no blinding
     ref, _ = o.groth16_prove(cc["NVars"], cc["NPublic"], pk, g["witness"], g["px"], 0, 0)
     assert affeq(G1, ok["PiC"], ref["PiC"]) and affeq(G1, ok["PiA"], ref["PiA"])
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("logn", [12, 16])
+def test_groth16_prove_named_sizes_known_dlogs(mods, logn, mode):
+    """BASELINE config 2 (2^16 constraints, 1 GPU) through the host-pointer C ABI b200_groth16_prove, with the proving
+    key built for the batched-affine kernels (mode 1) and for the XYZZ kernels (mode 2): every proof element equals
+    (known scalar)*G — the exact output of groth16.GenerateProofs (groth16.go:225-278) on the same key, witness, px, r, s."""
+    import numpy as np
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+    from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+    from gosnark_b200.synthetic import SyntheticGroth16
+    syn = SyntheticGroth16(logn)
+    check(lib().b200_config(_lib.CFG_ACC_MODE, mode))
+    try:
+        pk = syn.load_pk()
+    finally:
+        check(lib().b200_config(_lib.CFG_ACC_MODE, _lib.ACC_AUTO))
+    pa, pb, pc = np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+    rr, ss = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
+    for _ in range(2):      # twice: scratch reuse across proofs
+        check(lib().b200_groth16_prove(pk, ptr(syn.w), syn.m, ptr(syn.px), syn.px.shape[0], ptr(rr), ptr(ss), ptr(pa), ptr(pb),
+                                       ptr(pc)))
+        ea, eb, ec = syn.expected_dlogs()
+        assert G1.affine(_unflatten_g1(pa)[0]) == G1.affine(G1.mul_scalar(G1.G, ea))
+        assert G2.affine(_unflatten_g2(pb)[0]) == G2.affine(G2.mul_scalar(G2.G, eb))
+        assert G1.affine(_unflatten_g1(pc)[0]) == G1.affine(G1.mul_scalar(G1.G, ec))
+    check(lib().b200_pk_free(pk))

@@ -75,9 +75,9 @@ def test_fp_ops(lib, field, p):
     assert lib.t_geq(field, ptr(to_u32([(1 << 256) - 1]))) == 1
 
 
-def test_karatsuba_product(lib):
-    """mul_full_k == mul_full == the integer product for arbitrary 256-bit operands (all sign combinations of the
-    half differences, carries at every limb boundary), and mul_impl_k == the field product."""
+def test_wide_product_and_reduction(lib):
+    """mul_full == the integer product for arbitrary 256-bit operands (carries at every limb boundary) and
+    redc_wide == t / 2^256 mod p: the two halves of the lazily reduced F_q^2 multiply."""
     rng = random.Random(2024)
     M = (1 << 256) - 1
     H = (1 << 128) - 1
@@ -87,22 +87,18 @@ def test_karatsuba_product(lib):
     for i, a in enumerate(vals):
         for b in (vals[(i * 7 + 3) % len(vals)], vals[(i * 13 + 5) % len(edge)], a):
             A, B = to_u32([a]), to_u32([b])
-            for k in (0, 1):
+            for k in (0,):
                 out = np.zeros(16, dtype=np.uint32)
                 lib.t_mul_full(k, ptr(A), ptr(B), ptr(out))
                 assert int.from_bytes(out.tobytes(), "little") == a * b, (k, hex(a), hex(b))
     for field, p in ((0, Q), (1, R)):
-        vs = samples(p, rng, 100)
-        for i, a in enumerate(vs):
-            b = vs[(i * 5 + 1) % len(vs)]
-            assert call(lib.t_fp_op, field, 7, ptr(to_u32([a])), ptr(to_u32([b])), nout=1)[0] == (a * b) % p
-        # wide reduction t -> t / 2^256 mod p for t < p * 2^256, both carry schemes (extremes: 0, p*2^256 - 1, all-ones low half)
+        # wide reduction t -> t / 2^256 mod p for t < p * 2^256 (extremes: 0, p*2^256 - 1, all-ones low half)
         rinv = pow(1 << 256, -1, p)
         ts = [0, 1, p * (1 << 256) - 1, (1 << 256) - 1, (p - 1) * (p - 1), ((1 << 256) - 1) * (p - 1), p << 255] + \
              [rng.randrange(p << 256) for _ in range(200)]
         for t in ts:
             T = np.frombuffer(int(t).to_bytes(64, "little"), dtype=np.uint32).copy()
-            for k in (0, 1):
+            for k in (0,):
                 out = np.zeros(8, dtype=np.uint32)
                 lib.t_redc_wide(field, k, ptr(T), ptr(out))
                 assert int.from_bytes(out.tobytes(), "little") == (t * rinv) % p, (field, k, hex(t))
