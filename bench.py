@@ -1,22 +1,29 @@
 #!/usr/bin/env python3
 """bench.py — Groth16 prove throughput on B200 (the driver's contract).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--logn 20]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload prove|g1msm|g2msm|verify]
+                    [--logn L] [--with-qap]
 
-A "step" is one groth16.GenerateProofs (groth16/groth16.go:225-278) on the synthetic
-R1CS shape of SURVEY §8(d): n = 2^logn constraints, m = n+2 signals, NPublic = 1,
-full-width witness, px = h0*Z.  Default workload: n = 2^20 — the size
-BASELINE.json's metric is quoted at; it fits one GPU.
+Default workload (BASELINE.json's metric): one step = one groth16.GenerateProofs (groth16/groth16.go:225-278) on the
+synthetic R1CS shape of SURVEY §8(d): n = 2^20 constraints, m = n+2 signals, NPublic = 1, full-width witness.
 
-  value   proofs/s with witness, px and CRS resident in HBM (CUDA events, max over ranks)
-  e2e     proofs/s through the host-pointer C ABI (b200_groth16_prove): pinned host
-          buffers, H2D of w and px and D2H of the proof inside the timed region
-  N > 1   the MSMs are sharded by index range, one 1 KB NCCL all-gather of partial
-          sums per proof, final adds on every rank (strong scaling)
+  value   proofs/s with witness, px and CRS resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e     proofs/s through the host-pointer C ABI b200_groth16_prove: pinned host buffers, H2D of the witness and px
+          and D2H of the proof inside the timed region — at N > 1 too (the NCCL all-gather of the 1 KB partial records
+          happens inside the library: b200_comm_init)
+  N > 1   the four MSMs are sharded by cost over the ranks (strong scaling), one all-gather per proof
 
-`--impl reference` times the reference's own algorithm (oracle/ref_c.c: per-term
-MSB-first double-and-add + add-2007-bl accumulate, exactly groth16.go:243-271) on the
-host cores, on a bounded sample of the same workload.
+Other workloads (BASELINE.json configs 3 and 5; never the default line):
+  --workload g1msm  BN128 G1 MSM, 2^20 random scalars/points, Mscalar-mul/s, roofline at 96 B/term
+  --workload g2msm  BN128 G2 MSM, 2^22, sharded over the ranks (partial records + point sums), 160 B/term
+  --workload verify batched bn128.Pairing (pairings/s) and groth16.VerifyProof calls
+  --with-qap        the prove step starts from the WITNESS: px = CombinePolynomials(w, R1CSToQAP(..)) is computed on
+                    the device from the sparse R1CS (b200_groth16_prove_witness), with a REAL CRS (trusted setup with
+                    seeded toxic values) — the proof is verified on the GPU and by the reference's Go binary.
+
+`--impl reference` times the reference's own algorithm (oracle/ref_c.c: per-term MSB-first double-and-add + add-2007-bl
+accumulate, exactly groth16.go:243-271) on the host cores, on a fixed-size sample of the same workload; nothing of the
+GPU library is loaded in that arm.
 """
 import argparse
 import ctypes
@@ -33,6 +40,13 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+G1_GEN = (1, 2, 1)
+G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531), (1, 0))   # bn128.go:57-83
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -40,8 +54,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--logn", type=int, default=20)
-    ap.add_argument("--no-extras", action="store_true", help="skip MSM-only / cpu_baseline side measurements")
+    ap.add_argument("--workload", default="prove", choices=["prove", "g1msm", "g2msm", "verify"])
+    ap.add_argument("--logn", type=int, default=None)
+    ap.add_argument("--with-qap", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / side measurements")
     return ap.parse_args()
 
 
@@ -88,212 +104,347 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU reference arm
-def cpu_reference(syn, budget_s=16.0):
-    """Time the reference algorithm (C restatement, oracle/ref_c.c) on a bounded sample of THIS
-    workload with every host core, and extrapolate linearly in the term count (the cost is exactly
-    linear for full-width scalars).  Returns (proofs_per_sec, info)."""
-    import build as b200build
-    oc = ctypes.CDLL(b200build.build_oracle())
-    threads = max(1, min(os.cpu_count() or 1, 256))
-    from gosnark_b200._lib import ptr
+def host_cores():
+    """Cores this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()
+            if q != "max":
+                quota = max(1, int(float(q) / float(per)))
+    except Exception:
+        pass
+    return (min(n, quota) if quota else n), {"affinity": n, "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
 
-    def run(group, pts, sc, k):
-        fn = oc.oc_g1_msm_loop if group == 1 else oc.oc_g2_msm_loop
+
+def _limbs(vals, words=4):
+    return np.frombuffer(b"".join(int(v).to_bytes(8 * words, "little") for v in vals), dtype=np.uint64).copy()
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CpuReference:
+    """The reference's hot loops (C restatement, oracle/ref_c.c) on a FIXED-SIZE sample of this workload: k1 G1 terms and
+    k2 G2 terms per run, sized from the usable core count so a run takes a few seconds on any lease; sample points
+    k_i*G are minted by the oracle itself (no GPU library in this arm); full-width scalars."""
+
+    def __init__(self):
+        import build as b200build
+        self.oc = ctypes.CDLL(b200build.build_oracle())
+        self.cores, self.core_info = host_cores()
+        self.threads = max(1, min(self.cores, 256))
+        rng = np.random.default_rng(0x5EED0006)
+
+        def rnd(n):
+            a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+            a[:, 3] &= np.uint64((1 << 61) - 1)
+            return np.ascontiguousarray(a)
+
+        pool = 1024
+        self.k1 = max(pool, 1536 * self.threads)
+        self.k2 = max(pool // 4, 384 * self.threads)
+        g1 = _limbs(G1_GEN)
+        g2 = _limbs([c for pt in G2_GEN for c in pt])
+        p1 = np.zeros((pool, 12), dtype=np.uint64)
+        p2 = np.zeros((pool // 4, 24), dtype=np.uint64)
+        self.oc.oc_g1_mul_batch_bcast(_p(g1), _p(rnd(pool)), ctypes.c_long(pool), self.threads, _p(p1))
+        self.oc.oc_g2_mul_batch_bcast(_p(g2), _p(rnd(pool // 4)), ctypes.c_long(pool // 4), self.threads, _p(p2))
+        self.pts1 = np.ascontiguousarray(np.tile(p1, (self.k1 // pool + 1, 1))[: self.k1])
+        self.pts2 = np.ascontiguousarray(np.tile(p2, (self.k2 // (pool // 4) + 1, 1))[: self.k2])
+        self.sc1, self.sc2 = rnd(self.k1), rnd(self.k2)
+        # one calibration probe: if the lease gives fewer effective cores than it reports, shrink the sample ONCE so a
+        # run stays near 3 s per group; the size is then fixed for every repeat (no time-budgeted sampling)
+        for grp in (1, 2):
+            probe = 32 * self.threads if grp == 1 else 8 * self.threads
+            t = self._run(grp, probe, self.threads) / probe
+            cap = max(probe, int(3.0 / t))
+            if grp == 1:
+                self.k1 = min(self.k1, cap)
+            else:
+                self.k2 = min(self.k2, cap)
+
+    def _run(self, group, k, threads):
+        fn = self.oc.oc_g1_msm_loop if group == 1 else self.oc.oc_g2_msm_loop
+        pts, sc = (self.pts1, self.sc1) if group == 1 else (self.pts2, self.sc2)
         out = np.zeros(24, dtype=np.uint64)
         t0 = time.perf_counter()
-        fn(ptr(pts), ptr(sc), ctypes.c_long(k), threads, ptr(out))
+        fn(_p(pts), _p(sc), ctypes.c_long(k), threads, _p(out))
         return time.perf_counter() - t0
 
-    m, n = syn.m, syn.n
-    at = np.ascontiguousarray(syn.at[2:])       # skip the (0,0,0)/tiny entries at the front
-    b2 = np.ascontiguousarray(syn.b2[2:])
-    w = np.ascontiguousarray(syn.w[2:])
-    avail = min(at.shape[0], b2.shape[0], w.shape[0])
-    probe = min(avail, 8 * threads)
-    t1 = run(1, at, w, probe) / probe           # seconds per G1 term (all threads busy)
-    t2 = run(2, b2, w, probe) / probe
-    k1 = int(max(probe, min(avail, budget_s * 0.5 / t1)))
-    k2 = int(max(probe, min(avail, budget_s * 0.5 / t2)))
-    t1 = run(1, at, w, k1) / k1
-    t2 = run(2, b2, w, k2) / k2
-    g1_terms = m + m + (m - 2) + (n - 1)        # A, B1, C, H loops (groth16.go:243-250,269-271)
-    g2_terms = m
-    secs = t1 * g1_terms + t2 * g2_terms
-    info = {"kind": "port", "cores": threads,
-            "sample": f"reference double-and-add loops on {k1} G1 + {k2} G2 terms of this workload, "
-                      f"{threads} threads, extrapolated linearly to {g1_terms} G1 + {g2_terms} G2 terms; "
-                      "h=px/Z (O(n^3) in the reference, r1csqap.go:70-84) excluded in the CPU's favour",
-            "g1_us_per_term": t1 * 1e6, "g2_us_per_term": t2 * 1e6}
-    return 1.0 / secs, info
+    def per_term(self, threads=None):
+        """(seconds per G1 term, seconds per G2 term) with `threads` threads (all usable cores by default)."""
+        th = self.threads if threads is None else threads
+        k1 = self.k1 if threads is None else max(64, self.k1 // self.threads)
+        k2 = self.k2 if threads is None else max(16, self.k2 // self.threads)
+        return self._run(1, k1, th) / k1, self._run(2, k2, th) / k2
+
+    def single_thread(self):
+        t1, t2 = self.per_term(threads=1)
+        return {"g1_us_per_term": t1 * 1e6, "g2_us_per_term": t2 * 1e6}
+
+
+def workload_terms(workload, n):
+    """(G1 terms, G2 terms) of the reference's loops for one unit of the workload."""
+    if workload == "prove":
+        m = n + 2
+        return m + m + (m - 2) + (n - 1), m          # A, B1, C, H loops (groth16.go:243-250,269-271); B2
+    if workload == "g1msm":
+        return n, 0
+    if workload == "g2msm":
+        return 0, n
+    return 0, 0
+
+
+def reference_value(ref, workload, n, repeats):
+    """Median over `repeats` fixed-size samples, extrapolated linearly in the term count (exact for full-width scalars)."""
+    g1_terms, g2_terms = workload_terms(workload, n)
+    vals, t1s, t2s = [], [], []
+    for _ in range(repeats):
+        t1, t2 = ref.per_term()
+        t1s.append(t1); t2s.append(t2)
+        vals.append(1.0 / (t1 * g1_terms + t2 * g2_terms))
+    info = {"kind": "port", "cores": ref.threads, "core_detection": ref.core_info,
+            "sample": f"reference double-and-add loops on a fixed sample of {ref.k1} G1 + {ref.k2} G2 terms of this workload per "
+                      f"run (median of {repeats}), {ref.threads} threads, extrapolated linearly to {g1_terms} G1 + {g2_terms} G2 "
+                      "terms; h = px/Z (O(n^3) in the reference, r1csqap.go:70-84) excluded in the CPU's favour",
+            "g1_us_per_term": statistics.median(t1s) * 1e6, "g2_us_per_term": statistics.median(t2s) * 1e6,
+            "spread": {"min": min(vals), "max": max(vals)}}
+    return statistics.median(vals), info
+
+
+def metric_of(workload):
+    return {"prove": ("groth16_proofs_per_sec", "proofs/s"), "g1msm": ("g1_msm_mscalar_mul_per_sec", "Mscalar-mul/s"),
+            "g2msm": ("g2_msm_mscalar_mul_per_sec", "Mscalar-mul/s"), "verify": ("bn128_pairings_per_sec", "pairings/s")}[workload]
+
+
+def default_logn(workload):
+    return {"prove": 20, "g1msm": 20, "g2msm": 22, "verify": 12}[workload]
+
+
+def make_config(args, logn, world):
+    n = 1 << logn
+    if args.workload == "prove":
+        src = ("REAL CRS from the sparse trusted setup of the chain circuit, px computed on the device from the witness "
+               "(b200_groth16_prove_witness)") if args.with_qap else "px = h0*Z, CRS points k_i*G with known discrete logs"
+        wl = f"synthetic R1CS 2^{logn} constraints Groth16 prove (m=n+2 signals, NPublic=1, full-width witness), {src}"
+    elif args.workload in ("g1msm", "g2msm"):
+        wl = f"BN128 {'G1' if args.workload == 'g1msm' else 'G2'} MSM 2^{logn} random scalars/points (P_i = k_i*G), device-resident"
+    else:
+        wl = f"bn128.Pairing batch of 2^{logn} (Miller loop + final exponentiation) and groth16.VerifyProof"
+    return {"workload": wl, "constraints" if args.workload == "prove" else "n": n,
+            "parallelism": (f"msm-cost-shard x{world}, all-gather inside libb200snark" if args.workload == "prove" else
+                            f"index-shard x{world}") if world > 1 else "single-gpu",
+            "l2": "inputs larger than L2 (>= 1 GB of precomputed CRS tables gathered per MSM)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    logn = args.logn if args.logn is not None else default_logn(args.workload)
+    n = 1 << logn
+    metric, unit = metric_of(args.workload)
+    config = make_config(args, logn, args.gpus)
+    if args.workload == "verify":
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU port of the pairing loop is timed (oracle/ref_py is pure Python)"}))
+        return 0
+    ref = CpuReference()
+    for _ in range(args.warmup):
+        ref.per_term()
+    v, info = reference_value(ref, args.workload, n, max(args.steps, 5))
+    if args.workload != "prove":
+        v = v * n / 1e6                      # MSMs per second -> Mscalar-mul/s
+    info["value"], info["unit"] = v, unit
+    info["single_thread"] = ref.single_thread()
+    print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit,
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": (1e3 / v) if args.workload == "prove" else (n / (v * 1e6) * 1e3),
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)",
+                      "data": "synthetic", "config": config, "cpu_baseline": info,
+                      "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+# --------------------------------------------------------------------------- GPU arm
+class Ctx:
+    pass
+
+
+def setup_dist(args):
+    import torch
+    import torch.distributed as dist
+    from gosnark_b200 import _lib
+    c = Ctx()
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    c.torch, c.dist = torch, dist
+    torch.cuda.set_device(c.local)
+    if c.world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
+    _lib.init(c.local)
+    c.L = _lib.lib()
+    c.stream = torch.cuda.Stream()
+    torch.cuda.set_stream(c.stream)
+    c.st = c.stream.cuda_stream
+    if c.world > 1:            # NCCL communicator INSIDE the library; torch.distributed only carries the 128-byte id
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if c.rank == 0:
+            buf = np.zeros(128, dtype=np.uint8)
+            _lib.check(c.L.b200_comm_unique_id(buf.ctypes.data_as(ctypes.c_void_p)))
+            uid.copy_(torch.from_numpy(buf))
+        dist.broadcast(uid, 0)
+        ub = uid.cpu().numpy()
+        _lib.check(c.L.b200_comm_init(ub.ctypes.data_as(ctypes.c_void_p), c.rank, c.world))
+    return c
+
+
+def barrier(c):
+    c.torch.cuda.synchronize()
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+
+
+def timed(c, fn, steps, wall=False):
+    """Device time of `steps` calls bracketed by barrier + synchronize, MAX over ranks.  wall=True for calls that
+    synchronise internally on the library's own stream (the host-pointer C ABI)."""
+    torch = c.torch
+    barrier(c)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(c.stream)
+    for _ in range(steps):
+        fn()
+    e1.record(c.stream)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 if wall else e0.elapsed_time(e1)
+    if c.world > 1:
+        t = torch.tensor([ms], device="cuda")
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier(c)
+    return ms
+
+
+def peaks_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (of fallback)"
+
+
+def measured_traffic():
+    """Per-term DRAM bytes of the G1 accumulation phase from this round's ncu --set full capture (profiles/traffic.json,
+    regenerated by tools/ncu_traffic.py from profiles/r2_ncu_*.csv); None when that capture does not exist."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# measured on B200 with ncu (profiles/r2_notes.md): an IMAD.WIDE.U32 warp instruction occupies the fmaheavy pipe for 4
+# cycles per SM sub-partition => 32 wide multiply-accumulates / clk / SM; 148 SMs at 1.965 GHz.
+IMAD_WIDE_PEAK = 148 * 32 * 1.965e9
 
 
 def _nwin(n):
     """Windows per scalar the library uses for an n-term base set (mirror of pick_window_bits, csrc/capi.cu)."""
     best, best_cost = 8, float("inf")
-    for c in range(8, 19):
-        cost = ((255 + c - 1) // c) * float(n) * 10.0 + 2.0 * float(1 << (c - 1)) * 14.0 * 4.0
+    for cbits in range(8, 19):
+        cost = ((255 + cbits - 1) // cbits) * float(n) * 10.0 + 2.0 * float(1 << (cbits - 1)) * 14.0 * 4.0
         if cost < best_cost:
-            best, best_cost = c, cost
+            best, best_cost = cbits, cost
     return (255 + best - 1) // best
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    logn = args.logn
-    n = 1 << logn
-    config = {"workload": f"synthetic R1CS 2^{logn} constraints Groth16 prove (m=n+2 signals, NPublic=1, full-width "
-                          "witness, px=h0*Z), CRS points k_i*G with known discrete logs",
-              "constraints": n, "parallelism": f"msm-index-shard x{world}" if world > 1 else "single-gpu",
-              "l2": "inputs larger than L2 (>= 1 GB of precomputed CRS tables gathered per MSM)"}
+def alu_model(terms_per_launch, ms_per_launch, fq_mults_per_add, wide_per_mult=123 + 8):
+    macs = fq_mults_per_add * wide_per_mult * _nwin(terms_per_launch) * terms_per_launch / (ms_per_launch * 1e-3)
+    return {"achieved": macs, "peak": IMAD_WIDE_PEAK, "unit": "32x32+64 multiply-accumulates/s", "frac": macs / IMAD_WIDE_PEAK,
+            "windows_per_term": _nwin(terms_per_launch),
+            "note": f"one bucket add per term and window; {fq_mults_per_add} F_q multiplies per batched-affine add x {wide_per_mult} "
+                    "IMAD.WIDE-class fmaheavy slots each (SASS of fp_mul_outlined, profiles/r2_sass_fp_mul.txt); peak = 32 "
+                    "IMAD.WIDE / clk / SM (ncu: sm__pipe_fmaheavy_cycles_active, profiles/r2_notes.md) x 148 SMs x 1.965 GHz"}
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from gosnark_b200.synthetic import SyntheticGroth16
-        # the reference arm needs CRS points; mint a bounded slice with the C oracle-free GPU minting if a
-        # GPU is present, else with the Python oracle (tiny)
-        import torch
-        sample_log = min(logn, 14)
-        syn_small = SyntheticGroth16(sample_log, mint=False)
-        if torch.cuda.is_available():
-            from gosnark_b200 import _lib
-            _lib.init(local)
-            syn_small.mint()
-        else:
-            raise SystemExit("reference arm needs the GPU box only to mint sample CRS points")
-        # extrapolate to the full workload size
-        syn_small.m, syn_small.n = n + 2, n
-        vals, info = [], None
-        for i in range(args.warmup + args.steps):
-            v, info = cpu_reference(syn_small, budget_s=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
-            if i >= args.warmup:
-                vals.append(v)
-        v = statistics.median(vals)
-        info["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "groth16_proofs_per_sec", "value": v, "unit": "proofs/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)",
-                          "data": "synthetic", "config": config, "cpu_baseline": info,
-                          "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return 0
 
-    import torch
-    import torch.distributed as dist
+def run_prove(args, c):
+    torch, dist, L = c.torch, c.dist, c.L
     from gosnark_b200 import _lib
-    from gosnark_b200.synthetic import SyntheticGroth16
-    from gosnark_b200._lib import check, ints_to_limbs, lib, limbs_to_ints, ptr
-
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.init(local)
-    L = lib()
-    syn = SyntheticGroth16(logn)
+    from gosnark_b200._lib import check, ints_to_limbs, ptr
+    from gosnark_b200.synthetic import CircuitGroth16, SyntheticGroth16
+    rank, world, st = c.rank, c.world, c.st
+    logn = args.logn if args.logn is not None else 20
+    n = 1 << logn
+    syn = CircuitGroth16(logn) if args.with_qap else SyntheticGroth16(logn)
     pk = syn.load_pk(rank, world)
-    m = syn.m
-    npx = 2 * n - 1
+    m, npx = syn.m, 2 * n - 1
     r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
-
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    st = stream.cuda_stream
     d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
     d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
-    d_part = torch.zeros(128, dtype=torch.int64, device="cuda")          # 1 KB partial record
-    d_gather = torch.zeros(128 * world, dtype=torch.int64, device="cuda")
     d_out = torch.zeros(48, dtype=torch.int64, device="cuda")
     h_w = torch.from_numpy(syn.w.view(np.int64)).pin_memory()
     h_px = torch.from_numpy(syn.px.view(np.int64)).pin_memory()
-
-    def step_device():
-        if world == 1:
-            check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
-                                              d_out.data_ptr(), st))
-        else:
-            check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
-                                              d_part.data_ptr(), st))
-            dist.all_gather_into_tensor(d_gather, d_part)
-            check(L.b200_groth16_finalize_device(pk, d_gather.data_ptr(), world, ptr(r_l), ptr(s_l),
-                                                 d_out.data_ptr(), st))
-
     host_out = (np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64))
+    qap = args.with_qap and world == 1
 
-    # sharded ranks stage only what they read: their witness index ranges, and px only if they hold PTD points
+    def step_device():      # with a communicator the all-gather + finalize run inside the call (csrc/prove_host.cuh)
+        check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l), d_out.data_ptr(), st))
+
+    def step_e2e():          # the reference-facing call: host pointers in, proof out — on every rank
+        if qap:
+            check(L.b200_groth16_prove_witness(pk, syn.r1cs.handle, h_w.data_ptr(), m, ptr(r_l), ptr(s_l), ptr(host_out[0]),
+                                               ptr(host_out[1]), ptr(host_out[2])))
+        else:
+            check(L.b200_groth16_prove(pk, h_w.data_ptr(), m, h_px.data_ptr(), npx, ptr(r_l), ptr(s_l), ptr(host_out[0]),
+                                       ptr(host_out[1]), ptr(host_out[2])))
+
     info = np.zeros(12, dtype=np.uint64)
     check(L.b200_groth16_shard_info(pk, ptr(info)))
-    w_ranges, needs_px = [], bool(info[8])
+    ranges = []
     for lo, hi in sorted({(int(info[2 * k]), int(info[2 * k + 1])) for k in range(4)}):
         if lo < hi:
-            if w_ranges and lo <= w_ranges[-1][1]:
-                w_ranges[-1] = (w_ranges[-1][0], max(w_ranges[-1][1], hi))
+            if ranges and lo <= ranges[-1][1]:
+                ranges[-1] = (ranges[-1][0], max(ranges[-1][1], hi))
             else:
-                w_ranges.append((lo, hi))
-    h2d_bytes = (32 * m + 32 * npx) if world == 1 else (sum(32 * (hi - lo) for lo, hi in w_ranges) + (32 * npx if needs_px else 0))
-    d_w2, h_w2 = d_w.view(-1, 4), h_w.view(-1, 4)
+                ranges.append((lo, hi))
+    needs_px = bool(info[8])
+    h2d_bytes = (32 * m + (0 if qap else 32 * npx)) if world == 1 else (sum(32 * (hi - lo) for lo, hi in ranges) + (32 * npx if needs_px else 0))
 
-    def step_e2e():
-        if world == 1:      # the reference-facing call: host pointers in, proof out
-            check(L.b200_groth16_prove(pk, h_w.data_ptr(), m, h_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
-                                       ptr(host_out[0]), ptr(host_out[1]), ptr(host_out[2])))
-            return None
-        for lo, hi in w_ranges:
-            d_w2[lo:hi].copy_(h_w2[lo:hi], non_blocking=True)
-        if needs_px:
-            d_px.copy_(h_px, non_blocking=True)
-        step_device()
-        return d_out.cpu()
+    # ---- correctness of what we time (every step function): proof == the known-discrete-log expectation
+    from oracle import ref_py as o          # checker only
+    from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+    G1o, G2o = o.BN.G1, o.BN.G2
+    ea, eb, ec = syn.expected_dlogs() if rank == 0 else (0, 0, 0)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def matches(pa, pb, pc):
+        return (G1o.affine(pa) == G1o.affine(G1o.mul_scalar(G1o.G, ea)) and G2o.affine(pb) == G2o.affine(G2o.mul_scalar(G2o.G, eb))
+                and G1o.affine(pc) == G1o.affine(G1o.mul_scalar(G1o.G, ec)))
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        ms = e0.elapsed_time(e1)
-        if fn is step_e2e and world == 1:
-            ms = wall      # the host-pointer call synchronises internally on the library's own stream
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
-        return ms
-
-    # ---- correctness of what we time: proof == the known-discrete-log expectation (rank 0)
-    for _ in range(1):
-        step_device()
+    step_device()
     torch.cuda.synchronize()
-    parity = None
+    step_e2e()
+    parity, verified = None, None
     if rank == 0:
-        from oracle import ref_py as o          # checker only
         out = d_out.cpu().numpy().view(np.uint64)
-        from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
         pa, pc = _unflatten_g1(out[:24])
-        pb = _unflatten_g2(out[24:])[0]
-        ea, eb, ec = syn.expected_dlogs()
-        G1o, G2o = o.BN.G1, o.BN.G2
-        parity = (G1o.affine(pa) == G1o.affine(G1o.mul_scalar(G1o.G, ea))
-                  and G2o.affine(pb) == G2o.affine(G2o.mul_scalar(G2o.G, eb))
-                  and G1o.affine(pc) == G1o.affine(G1o.mul_scalar(G1o.G, ec)))
+        parity = matches(pa, _unflatten_g2(out[24:])[0], pc) and \
+            matches(_unflatten_g1(host_out[0])[0], _unflatten_g2(host_out[1])[0], _unflatten_g1(host_out[2])[0])
         if not parity:
             print(json.dumps({"error": "proof does not match the known-discrete-log expectation"}))
             return 1
+        if args.with_qap:
+            verified = bool(syn.verify(host_out[0], host_out[1], host_out[2]))       # groth16.VerifyProof on the GPU, real Vk
+            if not verified:
+                print(json.dumps({"error": "proof does not verify under the real verification key"}))
+                return 1
 
     # ---- timed region: device-resident
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(c.local)
     if rank == 0:
         clocks.start()                         # sampled across warm-up + timed region (the region can be < 100 ms)
     for _ in range(args.warmup):
@@ -301,7 +452,7 @@ def main():
     check(L.b200_profile(1))
     prof0 = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof0))          # reset counters
-    ms_total = timed(step_device, args.steps)
+    ms_total = timed(c, step_device, args.steps)
     prof = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof))
     check(L.b200_profile(0))
@@ -310,123 +461,277 @@ def main():
     value = 1e3 / ms_step
 
     # ---- exclusive timing of the dominant kernels: the same step with the MSMs serialised on one stream
-    # (in the overlapped step above the four bucket phases share the SMs, so their event times overlap)
+    # (in the overlapped step above the bucket phases of the four MSMs share the SMs, so their event times overlap)
     check(L.b200_profile(3))
     check(L.b200_profile_read(prof0))
     for _ in range(2):
         step_device()
     torch.cuda.synchronize()
     check(L.b200_profile_read(prof0))
-    ms_serial = timed(step_device, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    ser_steps = max(2, args.steps // 2)
+    ms_serial = timed(c, step_device, ser_steps) / ser_steps
     prof_x = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof_x))
     check(L.b200_profile(0))
 
-    # ---- e2e through the host-pointer API
+    # ---- e2e through the host-pointer API (wall clock around the calls: they synchronise internally)
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_ms = timed(c, step_e2e, args.steps, wall=True) / args.steps
 
-    # ---- side measurement: stand-alone G1 MSM at 2^20 (BASELINE.json's second metric), device-resident
-    msm_extra = None
-    if rank == 0 and world == 1 and not args.no_extras:
-        try:
-            from gosnark_b200.synthetic import rand_limbs
-            nm = 1 << 20
-            hb = _lib._h(0)
-            pts = syn.at[:nm] if syn.at.shape[0] >= nm else None
-            if pts is not None:
-                check(L.b200_g1_bases_load(ptr(np.ascontiguousarray(pts)), nm, 16, hb))
-                d_s = torch.from_numpy(rand_limbs(nm, 0x5EED0005).view(np.int64)).cuda()
-                d_r = torch.zeros(32, dtype=torch.int64, device="cuda")
-                for _ in range(3):
-                    check(L.b200_msm_device(hb.value, d_s.data_ptr(), nm, 0, d_r.data_ptr(), st))
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(10):
-                    check(L.b200_msm_device(hb.value, d_s.data_ptr(), nm, 0, d_r.data_ptr(), st))
-                e1.record(stream)
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 10
-                msm_extra = {"metric": "g1_msm_mscalar_mul_per_sec", "n": nm, "window_bits": 16, "ms": ms,
-                             "value": nm / ms / 1e3, "unit": "Mscalar-mul/s",
-                             "hbm_algorithmic_GBps": 96.0 * nm / (ms * 1e-3) / 1e9}
-                check(L.b200_bases_free(hb.value))
-        except Exception as e:
-            msm_extra = {"error": str(e)}
-
+    # ---- per-rank phase times (exclusive, ms per proof) so the limiter of the 1 -> N curve is visible
+    mine = {"rank": rank, "g1_acc_ms": prof_x[0] / ser_steps, "g1_phases": prof_x[1] / ser_steps, "g1_terms": prof_x[2] / ser_steps,
+            "g2_acc_ms": prof_x[3] / ser_steps, "g2_terms": prof_x[5] / ser_steps, "launches": prof_x[6] / ser_steps,
+            "witness_ranges": ranges, "holds_px_division": needs_px}
+    per_rank = [mine]
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
         dist.barrier()
+        check(L.b200_comm_destroy())
         dist.destroy_process_group()
     if rank != 0:
         return 0
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    g1_ms, g1_l, g1_terms = prof_x[0], max(prof_x[1], 1), prof_x[2]      # exclusive (serialised) timings
+    peak, peak_src = peaks_hbm()
+    g1_ms, g1_l, g1_terms = prof_x[0], max(prof_x[1], 1), prof_x[2]      # exclusive (serialised) timings, this rank
+    g2_ms, g2_l, g2_terms = prof_x[3], max(prof_x[4], 1), prof_x[5]
     ach = 96.0 * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3) / 1e9 if g1_ms > 0 else None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_accumulate_g1_dram_bytes_per_term", None)
-            if traffic is not None:
-                traffic = traffic * (g1_terms / g1_l)
-    except Exception:
-        pass
+    tr = measured_traffic()
+    traffic = tr["g1_accumulation_dram_bytes_per_term"] * (g1_terms / g1_l) if tr and g1_ms > 0 else None
+    metric, unit = metric_of("prove")
     line = {
-        "metric": "groth16_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)", "data": "synthetic", "config": config,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)", "data": "synthetic",
+        "config": make_config(args, logn, world),
         "constraints_per_sec": value * n, "parity_vs_known_dlog": parity,
-        "e2e": {"value": 1e3 / e2e_ms, "unit": "proofs/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 384,
-                "note": "N=1: the host-pointer C ABI call b200_groth16_prove; N>1: per rank, pinned->device copies of the "
-                        "witness ranges it reads (+ px on ranks holding PowersTauDelta), partial prove, NCCL all-gather, "
-                        "finalize, device->host read of the proof; h2d bytes are rank 0's"},
+                "note": ("b200_groth16_prove_witness: pinned witness in, px computed on the device, proof out" if qap else
+                         "the host-pointer C ABI call b200_groth16_prove on every rank (pinned witness and px in, proof out); at N > 1 "
+                         "each rank stages only the witness ranges it reads (+ px on ranks holding PowersTauDelta) and the NCCL "
+                         "all-gather of the 1 KB partial records runs inside the library; h2d bytes are rank 0's")},
         "gpu_launches": int(prof[6]),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "G1 bucket accumulation phase (k_affine_forward/invert/backward<Fq> rounds; "
-                                               "k_accumulate<Fq> below the affine threshold)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                     "traffic": traffic,
-                     "launches_per_step": 3, "avg_launch_ms": g1_ms / g1_l,
-                     "timing": "CUDA events around each phase, measured with the proof's MSMs serialised on one stream "
-                               f"(b200_profile(3)); serialised step = {ms_serial:.3f} ms, overlapped step = {ms_step:.3f} ms",
-                     "share_of_serial_step": (g1_ms / g1_l * 3) / ms_serial if ms_serial else None,
-                     "note": "bound by the integer multiply pipe (IMAD.WIDE at quarter rate, DESIGN.md §4), not by HBM: "
-                             "the HBM fraction is reported because the contract asks for it",
-                     "g2": {"avg_launch_ms": prof_x[3] / max(prof_x[4], 1),
-                            "share_of_serial_step": (prof_x[3] / max(prof_x[4], 1)) / ms_serial if ms_serial else None,
-                            "achieved": 160.0 * (prof_x[5] / max(prof_x[4], 1)) / (prof_x[3] / max(prof_x[4], 1) * 1e-3) / 1e9
-                            if prof_x[3] > 0 else None},
-                     "alu": (lambda macs: {"achieved": macs, "peak": 9.3e12, "unit": "32x32+64 multiply-accumulates/s",
-                                           "windows_per_term": _nwin(g1_terms / g1_l),
-                                           "frac": macs / 9.3e12,
-                                           "note": "one bucket add per term and window; 6 Montgomery multiplies per batched-affine add x 136 "
-                                                   "IMAD.WIDE-equivalent slots each (SASS of fp_mul_outlined); peak = IMAD.WIDE carry-chain rate measured "
-                                                   "by tools/micro/imad_bench.cu on this GPU class (29.6 / clk / SM)"})(
-                         6 * 136 * _nwin(g1_terms / g1_l) * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3)) if g1_ms > 0 else None,
-                     "overlapped": {"g1_avg_ms": prof[0] / max(prof[1], 1), "g2_avg_ms": prof[3] / max(prof[4], 1)}},
+        "roofline": {
+            "bound": "hbm", "kernel": "G1 bucket accumulation phase (k_affine_forward / k_affine_invert / k_affine_backward<Fq> rounds; "
+                                      "k_accumulate<Fq> below the affine threshold)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
+            "traffic": traffic,
+            "traffic_source": (tr or {}).get("source", "not measured in this run: no profiles/traffic.json from this round's ncu capture"),
+            "launches_per_step": prof_x[1] / ser_steps, "avg_launch_ms": g1_ms / g1_l,
+            "timing": "CUDA events around each phase on its stream, measured with the proof's MSMs serialised on one stream "
+                      f"(b200_profile(3)); serialised step = {ms_serial:.3f} ms, overlapped step = {ms_step:.3f} ms",
+            "share_of_serial_step": (g1_ms / ser_steps) / ms_serial if ms_serial else None,
+            "note": "bound by the integer multiply pipe (fmaheavy: IMAD.WIDE occupies it 4 cycles per warp; ncu on the dominant "
+                    "kernel: sm__pipe_fmaheavy_cycles_active 76.7 %, DRAM 25 %), not by HBM: the HBM fraction is reported "
+                    "because the contract asks for it (SURVEY H8)",
+            "g2": {"avg_launch_ms": g2_ms / g2_l, "share_of_serial_step": (g2_ms / ser_steps) / ms_serial if ms_serial else None,
+                   "achieved": 160.0 * (g2_terms / g2_l) / (g2_ms / g2_l * 1e-3) / 1e9 if g2_ms > 0 else None},
+            "alu": alu_model(g1_terms / g1_l, g1_ms / g1_l, 6) if g1_ms > 0 else None,
+            "overlapped": {"g1_avg_ms": prof[0] / max(prof[1], 1), "g2_avg_ms": prof[3] / max(prof[4], 1)}},
         "algorithmic_bytes_per_proof": syn.algorithmic_bytes(),
-        "g1_msm_2p20": msm_extra,
+        "per_rank": per_rank,
     }
+    if args.with_qap:
+        line["verified_under_real_vk"] = verified
     if not args.no_extras and world == 1:
         try:
-            v, info = cpu_reference(syn, budget_s=16.0)
-            info["value"] = v
-            info["unit"] = "proofs/s"
-            line["cpu_baseline"] = info
+            ref = CpuReference()
+            v, cinfo = reference_value(ref, "prove", n, 5)
+            cinfo["value"], cinfo["unit"] = v, unit
+            cinfo["single_thread"] = ref.single_thread()
+            line["cpu_baseline"] = cinfo
         except Exception as e:   # the checker must never take the bench line down
             line["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(line))
     return 0
+
+
+def run_msm(args, c):
+    """Configs 3 / 5: stand-alone MSM, scalars and points device-resident, index range sharded over the ranks."""
+    torch, dist, L = c.torch, c.dist, c.L
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ptr
+    from gosnark_b200.bn128 import _flatten_g1, _flatten_g2, _unflatten_g1, _unflatten_g2
+    from gosnark_b200.synthetic import SEED_POINTS, SEED_SCALARS, rand_limbs
+    rank, world, st = c.rank, c.world, c.st
+    group = 1 if args.workload == "g1msm" else 2
+    logn = args.logn if args.logn is not None else default_logn(args.workload)
+    n = 1 << logn
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    ks = rand_limbs(n, SEED_POINTS)[lo:hi]
+    ks[:, 0] |= np.uint64(1)
+    ss = rand_limbs(n, SEED_SCALARS)[lo:hi]
+    words = 12 if group == 1 else 24
+    gen = _flatten_g1([G1_GEN]) if group == 1 else _flatten_g2([G2_GEN])
+    pts = np.zeros((hi - lo, words), dtype=np.uint64)
+    check((L.b200_g1_mul_batch_bcast if group == 1 else L.b200_g2_mul_batch_bcast)(ptr(gen), ptr(ks), hi - lo, ptr(pts)))
+    hb = _lib._h(0)
+    check((L.b200_g1_bases_load if group == 1 else L.b200_g2_bases_load)(ptr(pts), hi - lo, 0, hb))
+    del pts
+    rec = 128 if group == 1 else 256                                     # XYZZ partial record bytes
+    d_s = torch.from_numpy(ss.view(np.int64)).cuda()
+    d_part = torch.zeros(rec // 8, dtype=torch.int64, device="cuda")
+    d_all = torch.zeros(rec // 8 * world, dtype=torch.int64, device="cuda")
+    h_s = torch.from_numpy(ss.view(np.int64)).pin_memory()
+    out = np.zeros(words, dtype=np.uint64)
+
+    def step_device():
+        check(L.b200_msm_device(hb.value, d_s.data_ptr(), hi - lo, 0, d_part.data_ptr(), st))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+
+    def finish():
+        src = d_all if world > 1 else d_part
+        check((L.b200_g1_sum_partials if group == 1 else L.b200_g2_sum_partials)(src.data_ptr(), world, ptr(out), st))
+
+    def step_e2e():
+        d_s.copy_(h_s, non_blocking=True)
+        step_device()
+        finish()
+
+    step_e2e()
+    parity = None
+    if True:
+        part = sum(int(a) * int(b) for a, b in zip(_lib.limbs_to_ints(ks), _lib.limbs_to_ints(ss))) % R_MOD
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+            part = sum(parts) % R_MOD
+        if rank == 0:
+            from oracle import ref_py as o
+            G = o.BN.G1 if group == 1 else o.BN.G2
+            got = (_unflatten_g1(out) if group == 1 else _unflatten_g2(out))[0]
+            parity = G.affine(got) == G.affine(G.mul_scalar(G.G, part))
+            if not parity:
+                print(json.dumps({"error": "MSM does not match the known-discrete-log expectation"}))
+                return 1
+    clocks = ClockSampler(c.local)
+    if rank == 0:
+        clocks.start()
+    for _ in range(args.warmup):
+        step_device()
+    check(L.b200_profile(1))
+    prof = (ctypes.c_double * 8)()
+    check(L.b200_profile_read(prof))
+    ms = timed(c, step_device, args.steps) / args.steps
+    check(L.b200_profile_read(prof))
+    check(L.b200_profile(0))
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(c, step_e2e, args.steps, wall=True) / args.steps
+    mode = ctypes.c_int(0)
+    check(L.b200_bases_acc_mode(hb.value, ctypes.byref(mode)))
+    if world > 1:
+        dist.barrier()
+        check(L.b200_comm_destroy())
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    peak, peak_src = peaks_hbm()
+    bpt = 96.0 if group == 1 else 160.0
+    k = 0 if group == 1 else 3
+    acc_ms, acc_l, acc_terms = prof[k], max(prof[k + 1], 1), prof[k + 2]
+    ach = bpt * (acc_terms / acc_l) / (acc_ms / acc_l * 1e-3) / 1e9 if acc_ms > 0 else None
+    metric, unit = metric_of(args.workload)
+    line = {"metric": metric, "value": n / ms / 1e3, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q)",
+            "data": "synthetic", "config": make_config(args, logn, world), "parity_vs_known_dlog": parity,
+            "e2e": {"value": n / e2e_ms / 1e3, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 32 * (hi - lo),
+                    "d2h_bytes_per_step": 8 * words,
+                    "note": "pinned scalars -> device, b200_msm_device, all-gather of the XYZZ partial records, b200_g*_sum_partials "
+                            "to host; the points are the resident CRS"},
+            "gpu_launches": int(prof[6]), "clocks": clk, "accumulation_kernel": {1: "batched affine", 2: "xyzz"}[mode.value],
+            "whole_msm_hbm_algorithmic_GBps": bpt * n / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": f"G{group} bucket accumulation phase of this rank's shard", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src, "traffic": None,
+                         "avg_launch_ms": acc_ms / acc_l,
+                         "alu": alu_model(acc_terms / acc_l, acc_ms / acc_l, 6 if group == 1 else 6 * 320 / 131.0) if acc_ms > 0 else None}}
+    if not args.no_extras and world == 1:
+        try:
+            ref = CpuReference()
+            v, cinfo = reference_value(ref, args.workload, n, 5)
+            cinfo["value"], cinfo["unit"] = v * n / 1e6, unit
+            cinfo["single_thread"] = ref.single_thread()
+            line["cpu_baseline"] = cinfo
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line))
+    return 0
+
+
+def run_verify(args, c):
+    """Config 5's verifier side: throughput of bn128.Pairing batches (bn128/bn128.go:179-421) and of groth16.VerifyProof."""
+    torch, L = c.torch, c.L
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, ptr
+    from gosnark_b200.bn128 import _flatten_g1, _flatten_g2
+    from gosnark_b200.synthetic import CircuitGroth16, rand_limbs
+    if c.world > 1:
+        raise SystemExit("--workload verify is a single-GPU measurement")
+    logn = args.logn if args.logn is not None else default_logn("verify")
+    n = 1 << logn
+    k1, k2 = rand_limbs(n, 11), rand_limbs(n, 12)
+    p1 = np.zeros((n, 12), dtype=np.uint64)
+    p2 = np.zeros((n, 24), dtype=np.uint64)
+    check(L.b200_g1_mul_batch_bcast(ptr(_flatten_g1([G1_GEN])), ptr(k1), n, ptr(p1)))
+    check(L.b200_g2_mul_batch_bcast(ptr(_flatten_g2([G2_GEN])), ptr(k2), n, ptr(p2)))
+    out = np.zeros((n, 48), dtype=np.uint64)
+
+    def step():
+        check(L.b200_pairing_batch(ptr(p1), ptr(p2), n, ptr(out)))
+
+    step()
+    # bilinearity spot check of what we time: e(aG, bH) == e(abG, H)
+    from oracle import ref_py as o
+    ab = _lib.limbs_to_ints(k1[:1])[0] * _lib.limbs_to_ints(k2[:1])[0] % R_MOD
+    q1, q2, o2 = np.zeros((1, 12), dtype=np.uint64), _flatten_g2([G2_GEN]), np.zeros((1, 48), dtype=np.uint64)
+    check(L.b200_g1_mul_batch_bcast(ptr(_flatten_g1([G1_GEN])), ptr(ints_to_limbs([ab])), 1, ptr(q1)))
+    check(L.b200_pairing_batch(ptr(q1), ptr(q2), 1, ptr(o2)))
+    parity = bool((o2[0] == out[0]).all())
+    clocks = ClockSampler(c.local)
+    clocks.start()
+    for _ in range(args.warmup):
+        step()
+    ms = timed(c, step, args.steps, wall=True) / args.steps
+    clk = clocks.stop()
+    # groth16.VerifyProof latency on a real instance
+    syn = CircuitGroth16(6)
+    pk = syn.load_pk()
+    pa, pb, pc = np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+    check(L.b200_groth16_prove(pk, ptr(syn.w), syn.m, ptr(syn.px), syn.px.shape[0], ptr(ints_to_limbs([syn.r])), ptr(ints_to_limbs([syn.s])),
+                               ptr(pa), ptr(pb), ptr(pc)))
+    ok = syn.verify(pa, pb, pc)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        ok = ok and syn.verify(pa, pb, pc)
+    verify_ms = (time.perf_counter() - t0) * 1e3 / reps
+    metric, unit = metric_of("verify")
+    print(json.dumps({"metric": metric, "value": n / ms * 1e3, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q), F_q^12",
+                      "data": "synthetic", "config": make_config(args, logn, 1), "parity_bilinearity": parity,
+                      "e2e": {"value": n / ms * 1e3, "unit": unit, "h2d_bytes_per_step": n * 288, "d2h_bytes_per_step": n * 384,
+                              "note": "b200_pairing_batch is a host-pointer call: value and e2e are the same measurement"},
+                      "groth16_verify": {"ms_per_call": verify_ms, "accepted": bool(ok)}, "clocks": clk,
+                      "gpu_launches": args.steps}))
+    return 0 if parity and ok else 1
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    c = setup_dist(args)
+    if args.workload == "prove":
+        return run_prove(args, c)
+    if args.workload in ("g1msm", "g2msm"):
+        return run_msm(args, c)
+    return run_verify(args, c)
 
 
 if __name__ == "__main__":

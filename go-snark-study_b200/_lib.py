@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so")
 CFG_ACC_MODE, ACC_AUTO, ACC_AFFINE, ACC_XYZZ = 1, 0, 1, 2
 
 B200_OK = 0
-ERRORS = {-1: "ENODEVICE", -2: "ECUDA", -3: "EINVAL", -4: "ERANGE", -5: "EDIVZERO", -6: "ENOMEM"}
+ERRORS = {-1: "ENODEVICE", -2: "ECUDA", -3: "EINVAL", -4: "ERANGE", -5: "EDIVZERO", -6: "ENOMEM", -7: "ECOMM"}
 
 
 class B200Error(RuntimeError):
@@ -59,6 +59,9 @@ _SIGNATURES = {
                                    _int, _int, ctypes.POINTER(_h)],
     "b200_groth16_finalize_device": [_h, _vp, _int, _vp, _vp, _vp, _vp],
     "b200_groth16_shard_info": [_h, _vp],
+    "b200_comm_unique_id": [_vp],
+    "b200_comm_init": [_vp, _int, _int],
+    "b200_comm_destroy": [],
     "b200_poly_add": [_vp, _sz, _vp, _sz, _vp],
     "b200_poly_sub": [_vp, _sz, _vp, _sz, _vp],
     "b200_poly_eval": [_vp, _sz, _vp, _vp],

@@ -19,6 +19,7 @@
 #include "poly_host.cuh"
 #include "qap.cuh"
 #include "qap_sparse.cuh"
+#include "comm.cuh"
 #ifndef B200_NO_PAIRING
 #include "pairing.cuh"
 #endif
@@ -35,6 +36,8 @@ cudaStream_t g_stream = nullptr;
 cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};  // side streams: independent MSMs of one proof overlap
 int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
 std::unique_ptr<PolyCtx> g_poly;
+
+Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = none
 
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
@@ -942,6 +945,44 @@ int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const vo
   return groth16_enqueue(p, (const Fr*)d_w, nw, (const Fr*)d_px, npx, r, s, (Fq*)d_out,
                          stream ? (cudaStream_t)stream : g_stream);
 }
+int b200_comm_unique_id(uint8_t out[128]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return fail(B200_EINVAL, "comm_unique_id: null pointer");
+  if (const char* e = g_comm.api.load()) return fail(B200_ECOMM, "comm_unique_id: %s", e);
+  ncclUniqueId id;
+  ncclResult_t rc = g_comm.api.GetUniqueId(&id);
+  if (rc != ncclSuccess) return fail(B200_ECOMM, "ncclGetUniqueId: %s", g_comm.api.GetErrorString(rc));
+  memcpy(out, &id, 128);
+  return B200_OK;
+}
+int b200_comm_init(const uint8_t id[128], int rank, int world) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  if (!id || world < 1 || rank < 0 || rank >= world) return fail(B200_EINVAL, "comm_init: bad arguments");
+  if (g_comm.active()) return fail(B200_EINVAL, "comm_init: communicator already initialised (rank %d/%d)", g_comm.rank, g_comm.world);
+  if (const char* e = g_comm.api.load()) return fail(B200_ECOMM, "comm_init: %s", e);
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t rc = g_comm.api.CommInitRank(&g_comm.comm, world, uid, rank);
+  if (rc != ncclSuccess) {
+    g_comm.comm = nullptr;
+    return fail(B200_ECOMM, "ncclCommInitRank: %s", g_comm.api.GetErrorString(rc));
+  }
+  g_comm.rank = rank;
+  g_comm.world = world;
+  return B200_OK;
+}
+int b200_comm_destroy(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_comm.active()) return B200_OK;
+  cudaSetDevice(g_device);
+  cudaDeviceSynchronize();
+  g_comm.api.CommDestroy(g_comm.comm);
+  g_comm.comm = nullptr;
+  g_comm.world = 1;
+  g_comm.rank = 0;
+  return B200_OK;
+}
 int b200_groth16_shard_info(b200_pk_t pk, uint64_t out[12]) {
   std::lock_guard<std::mutex> lk(g_mu);
   ProvingKey* p = find_pk(pk, 1);
@@ -1084,8 +1125,16 @@ int b200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g_init) return B200_OK;
   cudaSetDevice(g_device);
+  if (g_comm.active()) {
+    cudaDeviceSynchronize();
+    g_comm.api.CommDestroy(g_comm.comm);
+    g_comm.comm = nullptr;
+    g_comm.world = 1;
+  }
   g_bases.clear();
   g_pks.clear();
+  g_r1cs.clear();
+  g_domains.clear();
   g_poly.reset();
   if (g_d_err) cudaFree(g_d_err);
   if (g_stream) cudaStreamDestroy(g_stream);

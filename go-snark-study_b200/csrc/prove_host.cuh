@@ -38,6 +38,7 @@ struct ProvingKey {
   int sort_src[3] = {0, 1, 2};                        // set k reuses the digit sort of set sort_src[k] (same scalars)
   DevBuf s4;                                          // extra scalar vector (non-shared case)
   DevBuf h_full;              // full quotient (sharded mode)
+  DevBuf gather;              // all-gathered partial records (world x 1 KB), when a communicator is active
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ~ProvingKey() { for (auto e : ev) if (e) cudaEventDestroy(e); }
   std::unique_ptr<Bases> g[8];  // Groth16: A, B1, B2(G2), CH   Pinocchio: A, Ap, B(G2), Bp, C, Cp, Kp, H
@@ -512,9 +513,18 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   EV_WAIT(st, e_ch);
   if (pk->world == 1) {
     k_groth16_combine<<<1, 96, 0, st>>>(res, prod, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
-  } else {  // fold the products into this rank's C part and hand the 1 KB partial record to the all-gather
+  } else {  // fold the products into this rank's C part; the 1 KB partial record goes to the all-gather
     k_groth16_fold_products<<<1, 32, 0, st>>>(res, prod);
-    CU(cudaMemcpyAsync(d_out, res, kPartialBytes, cudaMemcpyDeviceToDevice, st));
+    if (g_comm.active() && g_comm.world == pk->world) {
+      if (g_comm.rank != pk->rank) return fail(B200_EINVAL, "groth16_prove: key shard %d on communicator rank %d", pk->rank, g_comm.rank);
+      CU(pk->gather.ensure(kPartialBytes * (size_t)pk->world));
+      ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPartialBytes, ncclUint8, g_comm.comm, st);
+      if (nrc != ncclSuccess) return fail(B200_ECOMM, "ncclAllGather: %s", g_comm.api.GetErrorString(nrc));
+      k_groth16_finalize<<<1, 96, 0, st>>>(pk->gather.as<uint8_t>(), pk->world, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
+      g_launches += 2;
+    } else {
+      CU(cudaMemcpyAsync(d_out, res, kPartialBytes, cudaMemcpyDeviceToDevice, st));
+    }
   }
   g_launches += 3;
   CU(cudaGetLastError());
@@ -537,17 +547,38 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
   if (!pk) return fail(B200_EINVAL, "groth16_prove: bad proving-key handle");
   if (!w || !px || !r || !s || !pi_a || !pi_b || !pi_c) return fail(B200_EINVAL, "groth16_prove: null pointer");
   if (nw != pk->m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, pk->m);
-  if (pk->world != 1)
-    return fail(B200_EINVAL, "groth16_prove: sharded key (rank %d/%d): use b200_groth16_prove_device + "
-                             "b200_groth16_finalize_device around the all-gather", pk->rank, pk->world);
+  const bool sharded = pk->world != 1;
+  if (sharded && !(g_comm.active() && g_comm.world == pk->world))
+    return fail(B200_EINVAL, "groth16_prove: sharded key (rank %d/%d) without a matching communicator: call b200_comm_init, "
+                             "or use b200_groth16_prove_device + b200_groth16_finalize_device around your own all-gather",
+                pk->rank, pk->world);
   cudaStream_t st = g_stream;
   CU(pk->px.ensure(npx * sizeof(Fr)));
   CU(pk->w_stage.ensure(nw * sizeof(Fr)));
-  CU(cudaMemcpyAsync(pk->w_stage.p, w, nw * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  bool need_px = true;
+  if (!sharded) {
+    CU(cudaMemcpyAsync(pk->w_stage.p, w, nw * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  } else {   // stage only what this rank reads: its witness index ranges, and px only if it holds PowersTauDelta points
+    const size_t l1 = pk->npublic + 1, ncf = pk->n_c_full;
+    size_t lo[4], hi[4];
+    for (int k = 0; k < 3; k++) { lo[k] = pk->lo[k]; hi[k] = pk->hi[k]; }
+    size_t c_lo = pk->lo[3] < ncf ? pk->lo[3] : ncf, c_hi = pk->hi[3] < ncf ? pk->hi[3] : ncf;
+    lo[3] = l1 + c_lo;
+    hi[3] = l1 + c_hi;
+    need_px = pk->hi[3] > ncf;
+    for (int k = 0; k < 4; k++) {
+      if (lo[k] >= hi[k]) continue;
+      bool dup = false;
+      for (int j = 0; j < k; j++) dup = dup || (lo[j] <= lo[k] && hi[k] <= hi[j] && lo[j] < hi[j]);
+      if (dup) continue;
+      CU(cudaMemcpyAsync(pk->w_stage.as<Fr>() + lo[k], reinterpret_cast<const Fr*>(w) + lo[k], (hi[k] - lo[k]) * sizeof(Fr),
+                         cudaMemcpyHostToDevice, st));
+    }
+  }
   // px is only needed by the division on side stream 3: copy it there so the transfer overlaps the sort of w
   // (same-stream order makes the division see it; the previous proof's use of pk->px finished before its combine)
   // (measurement mode runs the division on `st`, so the copy goes there too)
-  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : g_side[2]));
+  if (need_px) CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : g_side[2]));
   Fq* o = pk->out_std.as<Fq>();
   int rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, pk->px.as<Fr>(), npx, r, s, o, st);
   if (rc) return rc;

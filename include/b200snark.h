@@ -39,6 +39,7 @@ extern "C" {
 #define B200_ERANGE (-4)    /* a field element >= modulus or a scalar >= r           */
 #define B200_EDIVZERO (-5)  /* polynomial division by a zero leading coefficient     */
 #define B200_ENOMEM (-6)
+#define B200_ECOMM (-7)     /* NCCL: library not found, or a collective failed       */
 
 typedef uint64_t b200_bases_t; /* device-resident, window-precomputed base-point set */
 typedef uint64_t b200_pk_t;    /* device-resident proving key                        */
@@ -133,15 +134,28 @@ int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const vo
  * index slice [m*rank/world, m*(rank+1)/world) of every CRS array (and the same
  * fraction of PowersTauDelta); the blinding points ride on rank 0.  With such a key
  * b200_groth16_prove_device leaves a 1024-byte PARTIAL record (XYZZ sums A | B1 |
- * B2 | CH) in d_out instead of a proof; the caller all-gathers the records of all
- * ranks (NCCL, 1 KB per rank) and calls b200_groth16_finalize_device, which adds
- * them and applies groth16.go:272-275.  No EC-point reduction exists in NCCL, hence
- * gather-then-add.                                                     */
+ * B2 | CH) in d_out instead of a proof WHEN NO COMMUNICATOR IS ACTIVE (b200_comm_init):
+ * the caller then all-gathers the records of all ranks itself and calls
+ * b200_groth16_finalize_device, which adds them and applies groth16.go:272-275 (this is
+ * how the one-GPU tests emulate N ranks).  With a communicator the gather + finalize run
+ * inside the call and d_out receives the proof.  No EC-point reduction exists in NCCL,
+ * hence gather-then-add.                                               */
 int b200_groth16_pk_load_shard(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
                                size_t m, const uint64_t* ptd, size_t n_ptd, const uint64_t* z, size_t nz,
                                const uint64_t alpha1[12], const uint64_t beta1[12], const uint64_t delta1[12],
                                const uint64_t beta2[24], const uint64_t delta2[24], size_t npublic, int window_bits,
                                int rank, int world, b200_pk_t* out);
+/* ---- multi-GPU inside the library (one process per GPU) -------------------------------------------------
+ * b200_comm_unique_id (on one rank) mints an NCCL id; the caller distributes the 128 bytes by whatever means it has
+ * (a file, a socket, MPI, torch.distributed) and every rank calls b200_comm_init(id, rank, world) after b200_init.
+ * With a communicator, b200_groth16_prove / b200_groth16_prove_device on a key loaded with
+ * b200_groth16_pk_load_shard(.., rank, world) return the FINAL proof on every rank: each rank computes its partial
+ * sums, the 1 KB records are all-gathered over NVLink (ncclAllGather on the library's stream) and added.  All ranks
+ * must make the same call with the same witness, px, r and s (SPMD), as N copies of a Go process calling
+ * groth16.GenerateProofs (groth16/groth16.go:225) would.  libnccl.so.2 is dlopen'ed; absent -> B200_ECOMM.           */
+int b200_comm_unique_id(uint8_t out[128]);
+int b200_comm_init(const uint8_t id[128], int rank, int world);
+int b200_comm_destroy(void);
 /* What a sharded key reads: out = { A lo, hi, B1 lo, hi, B2 lo, hi (witness index ranges), C-part witness
  * range lo, hi, needs_px (0/1), rank, world, NVars }.  A caller that stages inputs per proof only has to upload
  * those witness ranges, and px only when needs_px is set.                                                        */

@@ -225,6 +225,20 @@ void oc_g2_mul_scalar(const uint64_t* p, const uint64_t* e, uint64_t* out) {
 DEFINE_LOOP(g1, 12)
 DEFINE_LOOP(g2, 24)
 
+/* out[i] = MulScalar(p, sc[i]) for one base point p (threads in parallel): mints sample CRS points k_i*G for the CPU
+ * baseline without touching the GPU library (groth16.go:139-219: every CRS entry is G.MulScalar(g, k)). */
+#define DEFINE_MINT(NAME, WORDS)                                                                         \
+  void oc_##NAME##_mul_batch_bcast(const uint64_t* p, const uint64_t* sc, long n, int threads, uint64_t* out) { \
+    if (threads < 1) threads = 1;                                                                        \
+    NAME##_pt base; NAME##_load(&base, p);                                                               \
+    _Pragma("omp parallel for num_threads(threads) schedule(dynamic, 16)")                               \
+    for (long i = 0; i < n; i++) {                                                                       \
+      NAME##_pt m; NAME##_mul_scalar(&m, &base, sc + 4 * i); NAME##_store(out + (size_t)WORDS * i, &m);  \
+    }                                                                                                    \
+  }
+DEFINE_MINT(g1, 12)
+DEFINE_MINT(g2, 24)
+
 int oc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

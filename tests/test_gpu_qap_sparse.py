@@ -181,8 +181,11 @@ def test_real_crs_witness_to_verified_proof(mods, logn):
             check(lib().b200_groth16_prove_witness(pk, syn.r1cs.handle, ptr(syn.w), syn.m, ptr(rr), ptr(ss), ptr(pa), ptr(pb),
                                                    ptr(pc)))
         outs.append((pa, pb, pc))
-    for x, y in zip(outs[0], outs[1]):
-        assert (x == y).all()
+    # same group elements from both entry points (the Jacobian representatives may differ from run to run: the counting
+    # sort scatters with atomics, so the order of additions inside a bucket is not fixed)
+    assert o.BN.G1.affine(_unflatten_g1(outs[0][0])[0]) == o.BN.G1.affine(_unflatten_g1(outs[1][0])[0])
+    assert o.BN.G2.affine(_unflatten_g2(outs[0][1])[0]) == o.BN.G2.affine(_unflatten_g2(outs[1][1])[0])
+    assert o.BN.G1.affine(_unflatten_g1(outs[0][2])[0]) == o.BN.G1.affine(_unflatten_g1(outs[1][2])[0])
     pa, pb, pc = outs[1]
     a, b, c = syn.expected_dlogs()
     A, B, C = _unflatten_g1(pa)[0], _unflatten_g2(pb)[0], _unflatten_g1(pc)[0]
