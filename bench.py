@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--with-qap", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / side measurements")
+    ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1], help="A/B: force the staged backward pass off / on")
     return ap.parse_args()
 
 
@@ -287,6 +288,8 @@ def setup_dist(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
     _lib.init(c.local)
     c.L = _lib.lib()
+    if args.tma_staging is not None:
+        _lib.check(c.L.b200_config(_lib.CFG_TMA_STAGING, args.tma_staging))
     c.stream = torch.cuda.Stream()
     torch.cuda.set_stream(c.stream)
     c.st = c.stream.cuda_stream
@@ -499,7 +502,8 @@ def run_prove(args, c):
     g2_ms, g2_l, g2_terms = prof_x[3], max(prof_x[4], 1), prof_x[5]
     ach = 96.0 * (g1_terms / g1_l) / (g1_ms / g1_l * 1e-3) / 1e9 if g1_ms > 0 else None
     tr = measured_traffic()
-    traffic = tr["g1_accumulation_dram_bytes_per_term"] * (g1_terms / g1_l) if tr and g1_ms > 0 else None
+    per_term = (tr or {}).get("g1_accumulation_dram_bytes_per_term")
+    traffic = per_term * (g1_terms / g1_l) if per_term and g1_ms > 0 else None
     metric, unit = metric_of("prove")
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world,

@@ -45,6 +45,7 @@ struct AffineRound {
   F* pre;                     // prefix products, one per pair
   F* others;                  // per thread: product of the other threads' totals in its block
   F* btot;                    // per block: product of all denominators (then inverted in place)
+  uint2* pair_ids;            // round 1: (entry id of P, entry id of Q) per pair, 0xffffffff = absent (forward writes, backward reads)
   uint32_t q_log;             // log2(pairs per slice in this round)
   uint32_t round;             // 1-based
 };
@@ -117,11 +118,14 @@ __device__ __forceinline__ bool aff_forward_denominator(const AffineRound<F>& a,
     uint32_t s = a.slice_start[slice], e = a.slice_end[slice];
     uint32_t i0 = s + 2 * j, i1 = i0 + 1;
     if (i1 >= e) {  // at most one live operand: nothing to invert
+      if (a.pair_ids) a.pair_ids[p] = make_uint2(i0 < e ? a.entries[i0] : 0xffffffffu, 0xffffffffu);
       d = F::one();
       return true;
     }
-    pp = &a.table[a.entries[i0] >> 1];
-    qp = &a.table[a.entries[i1] >> 1];
+    uint32_t e0 = a.entries[i0], e1 = a.entries[i1];
+    if (a.pair_ids) a.pair_ids[p] = make_uint2(e0, e1);
+    pp = &a.table[e0 >> 1];
+    qp = &a.table[e1 >> 1];
   } else {
     size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
     pp = &a.prev[base];
@@ -243,6 +247,241 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound
     int kind = aff_denominator(P, Q, d);
     F inv_d = inv_run * a.pre[p];
     inv_run = inv_run * d;
+    Affine<F> Rr;
+    if (kind == 1) {
+      F lam = (Q.y - P.y) * inv_d;
+      F x3 = lam.sqr() - P.x - Q.x;
+      Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+    } else if (kind == 2) {
+      F xx = P.x.sqr();
+      F lam = (xx.dbl() + xx) * inv_d;
+      F x3 = lam.sqr() - P.x.dbl();
+      Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+    } else {
+      Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
+    }
+    a.out[p] = Rr;
+  }
+}
+
+// ---- staged backward pass: TMA bulk copies + mbarrier (rounds >= 2), cp.async gathers (round 1) ---------------
+// The backward pass is bound by the integer-multiply pipe, but a third of its stall samples are long-scoreboard
+// waits: every iteration starts with the operand fetch (round 1: two random 64/128-byte point gathers from a >= 1 GB
+// table; later rounds: the node pair of the previous round) plus the prefix product, all through registers.  Here the
+// operands of the NEXT pair are staged into shared memory while the multiplies of the current pair run, without
+// holding a single register across the fetch:
+//   rounds >= 2  the 32 node pairs of a warp's iteration are CONTIGUOUS (4 / 8 KB) and so are its 32 prefix products:
+//                lane 0 issues two TMA bulk copies (cp.async.bulk.shared.global, SASS UBLKCP — a warp-uniform
+//                instruction, which is why one lane issues for the warp) that complete_tx on the warp's mbarrier,
+//                armed with arrive.expect_tx; all lanes then wait on its phase parity;
+//   round 1      the operands are per-thread random gathers: each thread copies its two points and its prefix product
+//                with 16-byte cp.async (LDGSTS) into its own row and waits on its own cp.async group.  The entry ids are
+//                needed one step earlier: the forward pass leaves them in `pair_ids` (8 B per pair, coalesced).
+// The copies for pair k-1 are issued in the MIDDLE of pair k, right after the last use of pair k's row, and have three
+// field multiplications of time to land.  Rows are read back with 128-bit shared loads; the linear row layout the bulk
+// copy produces costs bank conflicts on them (8-way on the points), ~300 extra shared-pipe cycles against ~20 000 cycles
+// of arithmetic per warp iteration.
+constexpr uint32_t kNoEntry = 0xffffffffu;
+template <class F>
+struct AffStageLayout {
+  static constexpr uint32_t kPairBytes = 2 * sizeof(Affine<F>);                        // 128 B (G1) / 256 B (G2)
+  static constexpr uint32_t kPQ = 0, kPre = kAffBlock * kPairBytes, kBar = kPre + kAffBlock * sizeof(F);
+  static constexpr uint32_t kSmem = kBar + (kAffBlock / 32) * 8;                       // 20.5 KB (G1) / 41 KB (G2)
+};
+
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__cvta_generic_to_shared(p);
+#else
+  return (uint32_t)(uintptr_t)p;
+#endif
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+#ifdef __CUDA_ARCH__
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  (void)bar; (void)count;
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+#ifdef __CUDA_ARCH__
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+#else
+  (void)bar; (void)bytes;
+#endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef __CUDA_ARCH__
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#else   // CPU test vehicle: the leader's copy was synchronous; a warp barrier orders it before the followers' reads
+  (void)bar; (void)parity;
+  stub_syncwarp();
+#endif
+}
+// global -> shared bulk copy (TMA, SASS: UBLKCP); bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+#else   // CPU test vehicle: synchronous copy, the barrier is a no-op
+  (void)bar;
+  memcpy(dst_smem, src_gmem, bytes);
+#endif
+}
+// per-thread asynchronous 16-byte copies (LDGSTS), L2 only; BYTES a multiple of 16
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst_smem, const void* src_gmem) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+  for (int o = 0; o < BYTES; o += 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem) + o), "l"(static_cast<const char*>(src_gmem) + o)
+                 : "memory");
+#else
+  memcpy(dst_smem, src_gmem, BYTES);
+#endif
+}
+__device__ __forceinline__ void cp_async_commit_and_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void lds128(const void* p, uint32_t* o) {
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(smem_u32(p)));
+#else
+  memcpy(o, p, 16);
+#endif
+}
+template <class P, bool I>
+__device__ __forceinline__ Fp<P, I> ld_row(const uint8_t* p, Fp<P, I>*) {
+  Fp<P, I> r;
+  lds128(p, r.l);
+  lds128(p + 16, r.l + 4);
+  return r;
+}
+template <bool I>
+__device__ __forceinline__ Fq2T<I> ld_row(const uint8_t* p, Fq2T<I>*) {
+  Fq2T<I> r;
+  r.c0 = ld_row(p, (decltype(r.c0)*)nullptr);
+  r.c1 = ld_row(p + 32, (decltype(r.c1)*)nullptr);
+  return r;
+}
+__device__ __forceinline__ void syncwarp() {
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+#elif !defined(__CUDACC__)
+  stub_syncwarp();
+#endif
+}
+}  // namespace tma
+
+#ifndef __CUDACC__
+inline thread_local uint8_t* g_stub_dyn_smem = nullptr;   // CPU test vehicle: the emulated CTA's dynamic shared memory
+#endif
+
+template <class F, int kAffT, int MINB = 1>
+__global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(AffineRound<F> a) {
+  using L = AffStageLayout<F>;
+#ifdef __CUDACC__
+  extern __shared__ __align__(128) uint8_t aff_smem[];
+  uint8_t* smem = aff_smem;
+#else
+  uint8_t* smem = g_stub_dyn_smem;
+#endif
+  const uint32_t nslices = *a.nslices_ptr;
+  const uint32_t npairs = nslices << a.q_log;
+  const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);
+  if (block_base >= npairs) return;
+  const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+  uint8_t* row_pq = smem + L::kPQ + (size_t)t * L::kPairBytes;
+  uint8_t* row_pre = smem + L::kPre + (size_t)t * sizeof(F);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar) + warp;
+  const bool leaves = a.round == 1;
+  if (!leaves && lane == 0) tma::mbar_init(bar, 1);
+  tma::syncwarp();
+
+  // stage the operands of pair p (this thread's pair of the warp-iteration starting at pair p0 = p - lane)
+  auto issue = [&](uint32_t p, uint2 ids) {
+    if (leaves) {   // per-thread gathers
+      if (p < npairs) {
+        if (ids.x != kNoEntry) tma::cp_async<(int)sizeof(Affine<F>)>(row_pq, &a.table[ids.x >> 1]);
+        if (ids.y != kNoEntry) tma::cp_async<(int)sizeof(Affine<F>)>(row_pq + sizeof(Affine<F>), &a.table[ids.y >> 1]);
+        tma::cp_async<(int)sizeof(F)>(row_pre, &a.pre[p]);
+      }
+      tma::cp_async_commit();
+    } else if (lane == 0) {   // one lane per warp: two bulk copies for the warp's 32 contiguous pairs
+      uint32_t valid = p < npairs ? (npairs - p < 32u ? npairs - p : 32u) : 0u;
+      tma::mbar_arrive_expect_tx(bar, valid * (L::kPairBytes + (uint32_t)sizeof(F)));
+      if (valid) {
+        tma::bulk_g2s(row_pq, &a.prev[2 * (size_t)p], valid * L::kPairBytes, bar);
+        tma::bulk_g2s(row_pre, &a.pre[p], valid * (uint32_t)sizeof(F), bar);
+      }
+    }
+  };
+  auto ids_of = [&](uint32_t p) -> uint2 {
+    if (leaves && p < npairs) return a.pair_ids[p];
+    return make_uint2(0u, 0u);
+  };
+
+  uint32_t gthread = blockIdx.x * kAffBlock + t;
+  F inv_run = a.btot[blockIdx.x] * a.others[gthread];  // 1 / (product of this thread's denominators)
+  uint2 ids_cur = ids_of(block_base + (kAffT - 1) * kAffBlock + t);
+  issue(block_base + (kAffT - 1) * kAffBlock + t, ids_cur);
+  uint32_t phase = 0;
+  for (int k = kAffT - 1; k >= 0; k--) {
+    const uint32_t p = block_base + k * kAffBlock + t;
+    uint2 ids_next = make_uint2(0u, 0u);
+    if (k > 0) ids_next = ids_of(p - kAffBlock);          // coalesced; consumed in the middle of this iteration
+    if (leaves) tma::cp_async_wait();
+    else tma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    const bool live = p < npairs;
+    Affine<F> P = Affine<F>::inf(), Q = Affine<F>::inf();
+    F pre = F::one(), d = F::one();
+    int kind = 0;
+    if (live) {
+      const bool has_p = !leaves || ids_cur.x != kNoEntry, has_q = !leaves || ids_cur.y != kNoEntry;
+      if (has_p) {
+        P.x = tma::ld_row(row_pq, (F*)nullptr);
+        P.y = tma::ld_row(row_pq + sizeof(F), (F*)nullptr);
+        if (leaves && (ids_cur.x & 1) && !P.is_inf()) P.y = P.y.neg();
+      }
+      if (has_q) {
+        Q.x = tma::ld_row(row_pq + sizeof(Affine<F>), (F*)nullptr);
+        Q.y = tma::ld_row(row_pq + sizeof(Affine<F>) + sizeof(F), (F*)nullptr);
+        if (leaves && (ids_cur.y & 1) && !Q.is_inf()) Q.y = Q.y.neg();
+      }
+      pre = tma::ld_row(row_pre, (F*)nullptr);
+      kind = aff_denominator(P, Q, d);
+    }
+    F inv_d = inv_run * pre;
+    if (live) inv_run = inv_run * d;
+    // every value of this iteration's rows has been consumed (compared or multiplied) by every lane: refill them
+    tma::syncwarp();
+    if (k > 0) issue(p - kAffBlock, ids_next);
+    ids_cur = ids_next;
+    if (!live) continue;
     Affine<F> Rr;
     if (kind == 1) {
       F lam = (Q.y - P.y) * inv_d;

@@ -42,6 +42,7 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
 int g_acc_mode = 0;
+int g_tma_staging = 1;   // B200_CFG_TMA_STAGING: backward pass with staged operands (k_affine_backward_staged)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
 // timing of the dominant kernel (k_accumulate), per group.
@@ -149,7 +150,7 @@ struct Bases {
   uint32_t nseg = 0, seg = 0;
   // batched-affine accumulation (affine_S > 0): ping-pong node buffers, prefix products, per-thread / per-block products
   uint32_t affine_S = 0;
-  DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot;
+  DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot, aff_ids;
 };
 
 int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
@@ -229,6 +230,7 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
       CU(b->nodeA.alloc(nsl * (S / 2) * sizeof(Affine<F>)));
       CU(b->nodeB.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(Affine<F>)));
       CU(b->aff_pre.alloc(nsl * (S / 2) * sizeof(F)));
+      CU(b->aff_ids.alloc(nsl * (S / 2) * sizeof(uint2)));
       size_t nblk_max = (nsl * (S / 2) + kAffBlock * kAffPairs - 1) / (kAffBlock * kAffPairs);
       CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
       CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
@@ -386,6 +388,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     ar.pre = b->aff_pre.as<F>();
     ar.others = b->aff_others.as<F>();
     ar.btot = b->aff_btot.as<F>();
+    ar.pair_ids = g_tma_staging ? b->aff_ids.as<uint2>() : nullptr;
     Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
     const Affine<F>* prev = nullptr;
     // all R rounds affine: inside a proof the per-round inversion latency is hidden by the other MSMs' streams
@@ -401,11 +404,13 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       if (sizeof(F) == 32) {
         k_affine_forward<F, kAffPairs, 8><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-        k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
+        if (g_tma_staging) k_affine_backward_staged<F, kAffPairs, 5><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
       } else {
         k_affine_forward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-        k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
+        if (g_tma_staging) k_affine_backward_staged<F, kAffPairs, 4><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
       }
       prev = ar.out;
       g_launches += 3;
@@ -1109,6 +1114,10 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
+    return B200_OK;
+  }
+  if (key == B200_CFG_TMA_STAGING && (value == 0 || value == 1)) {
+    g_tma_staging = value;
     return B200_OK;
   }
   return fail(B200_EINVAL, "b200_config: unknown key %d or bad value %d", key, value);

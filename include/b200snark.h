@@ -54,6 +54,9 @@ int b200_version(void);
  * proving keys — 0 auto (batched affine where bucket population and shard size amortise its rounds, else XYZZ mixed
  * adds), 1 batched affine, 2 XYZZ.  Same results either way; the parity tests run every MSM size under both.          */
 #define B200_CFG_ACC_MODE 1
+/* B200_CFG_TMA_STAGING: 1 (default) the batched-affine backward pass stages its operands into shared memory with
+ * cp.async.bulk + mbarrier; 0 the register-load kernel.  Same results; takes effect on the next MSM.                  */
+#define B200_CFG_TMA_STAGING 2
 int b200_config(int key, int value);
 
 /* ---- base-point sets (the CRS arrays of groth16.Pk / snark.Pk) ---------- */

@@ -48,6 +48,9 @@ uint32_t stub_shfl(uint32_t v, int arg, int mode, int width) {
   pthread_barrier_wait(&g_warp_bar[warp]);
   return r;
 }
+void stub_syncwarp() {
+  if (g_cta_mode) pthread_barrier_wait(&g_warp_bar[threadIdx.x >> 5]);
+}
 unsigned stub_ballot(int pred) {
   if (!g_cta_mode) stub_abort("__ballot_sync outside run_cta");
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,6 +146,17 @@ void run_forward(int variant, const AffineRound<F>& a, unsigned nb) {
 
 template <class F, int T>
 void run_backward(int variant, const AffineRound<F>& a, unsigned nb) {
+  if (variant == 1) {   // the staged kernel (TMA bulk copies / cp.async gathers emulated as synchronous copies), CTA by CTA
+    static std::vector<uint8_t> smem;
+    smem.assign(AffStageLayout<F>::kSmem + 128, 0);
+    uint8_t* base = smem.data();
+    for (unsigned b = 0; b < nb; b++)
+      run_cta(b, kAffBlock, nb, [&] {
+        g_stub_dyn_smem = base;
+        k_affine_backward_staged<F, T, 1>(a);
+      });
+    return;
+  }
   blockDim.x = kAffBlock;
   gridDim.x = nb;
   for (unsigned b = 0; b < nb; b++)
@@ -166,6 +180,7 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   const uint32_t S = 1u << R;
   std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
   std::vector<F> pre((size_t)nslices * (S / 2));
+  std::vector<uint2> ids((size_t)nslices * (S / 2));
   unsigned nb_max = (nslices * (S / 2) + kAffBlock * T - 1) / (kAffBlock * T);
   std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
   AffineRound<F> ar{};
@@ -177,6 +192,7 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   ar.pre = pre.data();
   ar.others = others.data();
   ar.btot = btot.data();
+  ar.pair_ids = ids.data();
   const Affine<F>* prev = nullptr;
   Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
   for (uint32_t r = 1; r <= R; r++) {
@@ -308,6 +324,7 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     constexpr int T = 8;
     std::vector<Affine<F>> bufA((size_t)nslices * (S / 2) + 1), bufB((size_t)nslices * (S / 2) + 1);
     std::vector<F> pre((size_t)nslices * (S / 2) + 1);
+    std::vector<uint2> ids((size_t)nslices * (S / 2) + 1);
     unsigned nb_max = cdiv((size_t)nslices * (S / 2), kAffBlock * T) + 1;
     std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
     AffineRound<F> ar{};
@@ -319,6 +336,7 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     ar.pre = pre.data();
     ar.others = others.data();
     ar.btot = btot.data();
+    ar.pair_ids = ids.data();
     const Affine<F>* prev = nullptr;
     Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
     for (uint32_t r = 1; r <= R; r++) {
@@ -330,7 +348,7 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
       if (nb == 0) nb = 1;
       for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_forward<F, T, 1>(ar); });
       for (unsigned b = 0; b < cdiv((size_t)nb * 32, 128); b++) run_cta(b, 128, cdiv((size_t)nb * 32, 128), [&] { k_affine_invert<F>(ar.btot, nb); });
-      run_threads(nb, kAffBlock, [&] { k_affine_backward<F, T, 1>(ar); });
+      run_backward<F, T>(1, ar, nb);   // the staged kernel, as the library launches it
       prev = ar.out;
     }
     for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)

@@ -47,6 +47,7 @@ inline uint32_t __shfl_sync(unsigned, uint32_t v, int lane, int width = 32) { re
 inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 1, width); }
 inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 2, width); }
 unsigned stub_ballot(int pred);
+void stub_syncwarp();   // warp barrier in CTA emulation, no-op otherwise
 inline unsigned __ballot_sync(unsigned, int pred) { return stub_ballot(pred); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -149,7 +149,9 @@ def go_groth16_verify(vk_json, proof_json, public):
         b = os.path.join(d, "gsc")
         shutil.copy(binary, b)
         os.chmod(b, 0o755)
-        for fname, obj in (("trustedsetup.json", {"Vk": vk_json}), ("publicInputs.json", public), ("proofs.json", proof_json)):
+        # the prebuilt binary also opens compiledcircuit.json (unused by VerifyProof): an empty object will do
+        for fname, obj in (("trustedsetup.json", {"Vk": vk_json}), ("publicInputs.json", public), ("proofs.json", proof_json),
+                           ("compiledcircuit.json", {})):
             with open(os.path.join(d, fname), "w") as f:
                 json.dump(obj, f)
         p = subprocess.run([b, "groth16", "verify"], cwd=d, capture_output=True, text=True, timeout=300)

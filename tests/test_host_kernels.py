@@ -93,13 +93,18 @@ def _run(lib, group, variant, T, R, nslices, seed, fwd=-1):
     assert got == exp
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("T,R,nslices", [(8, 4, 300), (8, 3, 37), (32, 5, 520)])
-def test_g1_backward_kernel(lib, T, R, nslices):
-    _run(lib, 1, 0, T, R, nslices, seed=100 * T + R)
+def test_g1_backward_kernels(lib, variant, T, R, nslices):
+    """variant 0: k_affine_backward (register loads); 1: k_affine_backward_staged — warp-leader TMA bulk copies +
+    per-warp mbarrier in rounds >= 2, per-thread cp.async gathers from the forward pass's pair ids in round 1 (the copies
+    are synchronous in the emulation, the mbarrier a warp barrier): index logic, phase parity, tail blocks, signs."""
+    _run(lib, 1, variant, T, R, nslices, seed=100 * T + R)
 
 
-def test_g2_backward_kernel(lib):
-    _run(lib, 2, 0, 8, 3, 70, seed=9)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_g2_backward_kernels(lib, variant):
+    _run(lib, 2, variant, 8, 3, 70, seed=9)
 
 
 @pytest.mark.parametrize("T,R,nslices", [(8, 4, 300), (32, 5, 520)])
