@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--with-qap", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / side measurements")
-    ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1], help="A/B: force the staged backward pass off / on")
+    ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1, 2], help="A/B: staged backward pass off / all rounds / rounds >= 2")
     return ap.parse_args()
 
 

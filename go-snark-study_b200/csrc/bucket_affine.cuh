@@ -323,7 +323,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-#else   // CPU test vehicle: the leader's copy was synchronous; a warp barrier orders it before the followers' reads
+#elif !defined(__CUDACC__)   // CPU test vehicle: the leader's copy was synchronous; a warp barrier orders it before the followers' reads
   (void)bar; (void)parity;
   stub_syncwarp();
 #endif

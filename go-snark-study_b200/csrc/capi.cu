@@ -42,7 +42,7 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
 int g_acc_mode = 0;
-int g_tma_staging = 1;   // B200_CFG_TMA_STAGING: backward pass with staged operands (k_affine_backward_staged)
+int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
 // timing of the dominant kernel (k_accumulate), per group.
@@ -388,7 +388,7 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     ar.pre = b->aff_pre.as<F>();
     ar.others = b->aff_others.as<F>();
     ar.btot = b->aff_btot.as<F>();
-    ar.pair_ids = g_tma_staging ? b->aff_ids.as<uint2>() : nullptr;
+    ar.pair_ids = g_tma_staging == 1 ? b->aff_ids.as<uint2>() : nullptr;
     Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
     const Affine<F>* prev = nullptr;
     // all R rounds affine: inside a proof the per-round inversion latency is hidden by the other MSMs' streams
@@ -404,12 +404,12 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       if (sizeof(F) == 32) {
         k_affine_forward<F, kAffPairs, 8><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-        if (g_tma_staging) k_affine_backward_staged<F, kAffPairs, 5><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
+        if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 5><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
         else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
       } else {
         k_affine_forward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
-        if (g_tma_staging) k_affine_backward_staged<F, kAffPairs, 4><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
+        if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 4><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
         else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
       }
       prev = ar.out;
@@ -1116,7 +1116,7 @@ int b200_config(int key, int value) {
     g_acc_mode = value;
     return B200_OK;
   }
-  if (key == B200_CFG_TMA_STAGING && (value == 0 || value == 1)) {
+  if (key == B200_CFG_TMA_STAGING && value >= 0 && value <= 2) {
     g_tma_staging = value;
     return B200_OK;
   }

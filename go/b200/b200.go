@@ -16,8 +16,12 @@ package b200
 import "C"
 
 import (
+	"crypto/sha256"
+	"encoding/binary"
 	"errors"
+	"hash"
 	"math/big"
+	"sync"
 	"unsafe"
 )
 
@@ -177,4 +181,202 @@ func Fq12Mul(a, b [2][3][2]*big.Int) ([2][3][2]*big.Int, error) {
 	out := make([]uint64, 48)
 	err := check(C.b200_fq12_mul_batch(u64(fa), u64(fb), 1, u64(out)))
 	return Fq12FromLimbs(out), err
+}
+
+// ---- proving-key cache for the drop-in GenerateProofs(circuit, pk, w, px) form --------------------------------------
+// The reference passes Pk BY VALUE (groth16/groth16.go:225), so neither pointer identity nor slice headers identify a
+// key across calls (a caller may rebuild an equal Pk, or reuse a backing array for a different one).  The cache key is
+// a CONTENT fingerprint: SHA-256 over the array lengths, NVars/NPublic, the three blinding points, Z, and the first
+// and last `fpSample` points of every CRS array.  (A maintainer who wants no hashing at all uses the explicit handle
+// API instead: LoadGroth16 once, key.Prove per proof.)  At most `cap` keys stay resident; eviction frees device tables.
+const fpSample = 8
+
+type fingerprint [32]byte
+
+func hashInt(h hash.Hash, x *big.Int) { h.Write(x.Bytes()); h.Write([]byte{0xff}) }
+func hashG1(h hash.Hash, pts [][3]*big.Int) {
+	binary.Write(h, binary.LittleEndian, uint64(len(pts)))
+	for i, p := range pts {
+		if i >= fpSample && i < len(pts)-fpSample {
+			continue
+		}
+		for k := 0; k < 3; k++ {
+			hashInt(h, p[k])
+		}
+	}
+}
+func hashG2(h hash.Hash, pts [][3][2]*big.Int) {
+	binary.Write(h, binary.LittleEndian, uint64(len(pts)))
+	for i, p := range pts {
+		if i >= fpSample && i < len(pts)-fpSample {
+			continue
+		}
+		for k := 0; k < 3; k++ {
+			hashInt(h, p[k][0])
+			hashInt(h, p[k][1])
+		}
+	}
+}
+
+// Groth16Fingerprint identifies a groth16.Pk by content (see above).
+func Groth16Fingerprint(at, b1 [][3]*big.Int, b2 [][3][2]*big.Int, bacDelta, ptd [][3]*big.Int, z []*big.Int,
+	alpha1, beta1, delta1 [3]*big.Int, beta2, delta2 [3][2]*big.Int, nVars, nPublic int) fingerprint {
+	h := sha256.New()
+	binary.Write(h, binary.LittleEndian, [2]uint64{uint64(nVars), uint64(nPublic)})
+	hashG1(h, at)
+	hashG1(h, b1)
+	hashG2(h, b2)
+	hashG1(h, bacDelta)
+	hashG1(h, ptd)
+	hashG1(h, [][3]*big.Int{alpha1, beta1, delta1})
+	hashG2(h, [][3][2]*big.Int{beta2, delta2})
+	for _, c := range z {
+		hashInt(h, c)
+	}
+	var f fingerprint
+	copy(f[:], h.Sum(nil))
+	return f
+}
+
+// KeyCache keeps the most recently used device keys (safe for concurrent callers).
+type KeyCache struct {
+	mu    sync.Mutex
+	cap   int
+	order []fingerprint
+	keys  map[fingerprint]*Groth16Key
+}
+
+func NewKeyCache(capacity int) *KeyCache {
+	return &KeyCache{cap: capacity, keys: make(map[fingerprint]*Groth16Key)}
+}
+
+// Get returns the cached key for fp or loads it with load() and evicts (and frees) the least recently used one.
+func (c *KeyCache) Get(fp fingerprint, load func() (*Groth16Key, error)) (*Groth16Key, error) {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	if k, ok := c.keys[fp]; ok {
+		for i, f := range c.order {
+			if f == fp {
+				c.order = append(append(c.order[:i:i], c.order[i+1:]...), fp)
+				break
+			}
+		}
+		return k, nil
+	}
+	k, err := load()
+	if err != nil {
+		return nil, err
+	}
+	c.keys[fp] = k
+	c.order = append(c.order, fp)
+	for len(c.order) > c.cap {
+		old := c.order[0]
+		c.order = c.order[1:]
+		c.keys[old].Free()
+		delete(c.keys, old)
+	}
+	return k, nil
+}
+
+// ---- sparse R1CS, witness -> px, witness -> proof (include/b200snark.h: b200_r1cs_load, b200_qap_px, ..) ---------------
+// The dense a, b, c [][]*big.Int of r1csqap.R1CSToQAP (r1csqap.go:161) cannot exist at 2^16+ constraints; a caller at
+// that size keeps the R1CS in CSR form and calls CombinePolynomials directly on it.
+type R1CS struct {
+	h    C.b200_r1cs_t
+	N, M int
+}
+
+// DenseToCSR converts the reference's dense matrix (rows = constraints) to CSR with coefficients mod r.
+func DenseToCSR(m [][]*big.Int) (rowptr, col []uint32, val []uint64) {
+	rowptr = append(rowptr, 0)
+	for _, row := range m {
+		for i, x := range row {
+			if c := Coeff(x); c.Sign() != 0 {
+				col = append(col, uint32(i))
+				val = limbs(val, c)
+			}
+		}
+		rowptr = append(rowptr, uint32(len(col)))
+	}
+	return
+}
+
+func u32(v []uint32) *C.uint32_t {
+	if len(v) == 0 {
+		return nil
+	}
+	return (*C.uint32_t)(unsafe.Pointer(&v[0]))
+}
+func u64n(v []uint64) *C.uint64_t {
+	if len(v) == 0 {
+		return nil
+	}
+	return u64(v)
+}
+
+// LoadR1CS uploads the three matrices (dense reference form) once.
+func LoadR1CS(a, b, c [][]*big.Int) (*R1CS, error) {
+	ar, ac, av := DenseToCSR(a)
+	br, bc, bv := DenseToCSR(b)
+	cr, cc, cv := DenseToCSR(c)
+	r := &R1CS{N: len(a), M: len(a[0])}
+	rc := C.b200_r1cs_load(C.size_t(r.N), C.size_t(r.M), u32(ar), u32(ac), u64n(av), u32(br), u32(bc), u64n(bv),
+		u32(cr), u32(cc), u64n(cv), &r.h)
+	return r, check(rc)
+}
+
+// CombinePolynomials == PolynomialField.CombinePolynomials(w, R1CSToQAP(a, b, c)...) (r1csqap.go:161-210).
+func (r *R1CS) CombinePolynomials(w []*big.Int) (ax, bx, cx, px []*big.Int, err error) {
+	fw := FlatFr(w, Coeff)
+	oa, ob, oc, op := make([]uint64, 4*r.N), make([]uint64, 4*r.N), make([]uint64, 4*r.N), make([]uint64, 4*(2*r.N-1))
+	if err = check(C.b200_qap_px(r.h, u64(fw), C.size_t(len(w)), u64(oa), u64(ob), u64(oc), u64(op))); err != nil {
+		return
+	}
+	un := func(v []uint64) []*big.Int {
+		out := make([]*big.Int, len(v)/4)
+		for i := range out {
+			out[i] = fromLimbs(v[4*i : 4*i+4])
+		}
+		return out
+	}
+	return un(oa), un(ob), un(oc), un(op), nil
+}
+func (r *R1CS) Free() { C.b200_r1cs_free(r.h) }
+
+// ProveWitness is GenerateProofs fed from the witness: px never leaves the device (b200_groth16_prove_witness).
+func (k *Groth16Key) ProveWitness(r1cs *R1CS, w []*big.Int, r, s *big.Int) (piA [3]*big.Int, piB [3][2]*big.Int, piC [3]*big.Int, err error) {
+	fw := FlatFr(w, Scalar)
+	fr, fs := limbs(nil, r), limbs(nil, s)
+	a, b, c := make([]uint64, 12), make([]uint64, 24), make([]uint64, 12)
+	rc := C.b200_groth16_prove_witness(k.h, r1cs.h, u64(fw), C.size_t(len(w)), u64(fr), u64(fs), u64(a), u64(b), u64(c))
+	if err = check(rc); err != nil {
+		return
+	}
+	return G1FromLimbs(a), G2FromLimbs(b), G1FromLimbs(c), nil
+}
+
+// ---- multi-GPU: one process per GPU, NCCL inside the library ----------------------------------------------------------
+// Rank 0 calls CommUniqueID and hands the 128 bytes to the other ranks (any side channel); every rank calls CommInit after
+// choosing its device, loads its shard with LoadGroth16Shard, and then calls key.Prove with the SAME w, px, r, s: the
+// proof comes back on every rank.
+func CommUniqueID() (id [128]byte, err error) {
+	err = check(C.b200_comm_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0]))))
+	return
+}
+func CommInit(id [128]byte, rank, world int) error {
+	return check(C.b200_comm_init((*C.uint8_t)(unsafe.Pointer(&id[0])), C.int(rank), C.int(world)))
+}
+func CommDestroy() error { return check(C.b200_comm_destroy()) }
+
+func LoadGroth16Shard(at, b1 [][3]*big.Int, b2 [][3][2]*big.Int, bacDelta, ptd [][3]*big.Int, z []*big.Int,
+	alpha1, beta1, delta1 [3]*big.Int, beta2, delta2 [3][2]*big.Int, nVars, nPublic, rank, world int) (*Groth16Key, error) {
+	fa, fb1, fb2, fc, fp := FlatG1(at[:nVars]), FlatG1(b1[:nVars]), FlatG2(b2[:nVars]), FlatG1(bacDelta[:nVars]), FlatG1(ptd)
+	fz := FlatFr(z, Coeff)
+	a1, be1, d1 := FlatG1([][3]*big.Int{alpha1}), FlatG1([][3]*big.Int{beta1}), FlatG1([][3]*big.Int{delta1})
+	be2, d2 := FlatG2([][3][2]*big.Int{beta2}), FlatG2([][3][2]*big.Int{delta2})
+	var k Groth16Key
+	rc := C.b200_groth16_pk_load_shard(u64(fa), u64(fb1), u64(fb2), u64(fc), C.size_t(nVars), u64(fp), C.size_t(len(ptd)),
+		u64(fz), C.size_t(len(z)), u64(a1), u64(be1), u64(d1), u64(be2), u64(d2), C.size_t(nPublic), 0,
+		C.int(rank), C.int(world), &k.h)
+	return &k, check(rc)
 }

@@ -54,8 +54,10 @@ int b200_version(void);
  * proving keys — 0 auto (batched affine where bucket population and shard size amortise its rounds, else XYZZ mixed
  * adds), 1 batched affine, 2 XYZZ.  Same results either way; the parity tests run every MSM size under both.          */
 #define B200_CFG_ACC_MODE 1
-/* B200_CFG_TMA_STAGING: 1 (default) the batched-affine backward pass stages its operands into shared memory with
- * cp.async.bulk + mbarrier; 0 the register-load kernel.  Same results; takes effect on the next MSM.                  */
+/* B200_CFG_TMA_STAGING: the batched-affine backward pass with its operands staged into shared memory — TMA bulk
+ * copies (cp.async.bulk + per-warp mbarrier) in the contiguous rounds, cp.async gathers in round 1.  0 (default) the
+ * register-load kernel: measured FASTER (18.92 vs 20.17 ms per 2^20 proof, profiles/r2_notes.md: the kernel is bound by
+ * the multiply pipe, not by the fetch); 1 staged in every round, 2 staged in rounds >= 2 only.  Same results.          */
 #define B200_CFG_TMA_STAGING 2
 int b200_config(int key, int value);
 

@@ -200,3 +200,26 @@ def test_msm_full_size_known_discrete_logs(bn, group, logn, mode):
         assert (got[0], got[1]) == (esum[0], esum[1])
     finally:
         bs.free()
+
+
+@pytest.mark.parametrize("staging", [1, 2])
+@pytest.mark.parametrize("g,n", [(1, 1 << 14), (2, 1 << 11)])
+def test_msm_staged_backward_pass(bn, g, n, staging):
+    """The opt-in backward pass with staged operands (B200_CFG_TMA_STAGING: TMA bulk copies + mbarrier in the contiguous
+    rounds, cp.async gathers in round 1) gives the same sums as the default register-load kernel."""
+    from gosnark_b200 import _lib
+    G = OG[g]
+    rng = random.Random(900 + g)
+    ks = [rng.randrange(1, R) for _ in range(n)]
+    pts = grp(bn, g).MulScalarBatch([G.G], ks)
+    bs = bn.BaseSet(g, pts, acc_mode=1)
+    try:
+        _lib.check(_lib.lib().b200_config(_lib.CFG_TMA_STAGING, staging))
+        for dist in ("full", "small"):
+            ss = [rng.randrange(R if dist == "full" else 1 << 16) for _ in range(n)]
+            ss[0], ss[1] = 0, 1
+            exp = G.mul_scalar(G.G, sum(k * s for k, s in zip(ks, ss)) % R)
+            assert bs.msm(ss) == aff(g, exp), dist
+    finally:
+        _lib.check(_lib.lib().b200_config(_lib.CFG_TMA_STAGING, 0))
+        bs.free()
