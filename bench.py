@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--with-qap", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / side measurements")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed device-resident steps (ncu --profile-from-start off)")
     ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1, 2], help="A/B: staged backward pass off / all rounds / rounds >= 2")
     return ap.parse_args()
 
@@ -312,11 +314,13 @@ def barrier(c):
     c.torch.cuda.synchronize()
 
 
-def timed(c, fn, steps, wall=False):
+def timed(c, fn, steps, wall=False, profile=False):
     """Device time of `steps` calls bracketed by barrier + synchronize, MAX over ranks.  wall=True for calls that
     synchronise internally on the library's own stream (the host-pointer C ABI)."""
     torch = c.torch
     barrier(c)
+    if profile:
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(c.stream)
@@ -324,6 +328,8 @@ def timed(c, fn, steps, wall=False):
         fn()
     e1.record(c.stream)
     torch.cuda.synchronize()
+    if profile:
+        torch.cuda.profiler.stop()
     ms = (time.perf_counter() - t0) * 1e3 if wall else e0.elapsed_time(e1)
     if c.world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -366,12 +372,13 @@ def _nwin(n):
     return (255 + best - 1) // best
 
 
-def alu_model(terms_per_launch, ms_per_launch, fq_mults_per_add, wide_per_mult=123 + 8):
+def alu_model(terms_per_launch, ms_per_launch, fq_mults_per_add, wide_per_mult=137.5):
     macs = fq_mults_per_add * wide_per_mult * _nwin(terms_per_launch) * terms_per_launch / (ms_per_launch * 1e-3)
     return {"achieved": macs, "peak": IMAD_WIDE_PEAK, "unit": "32x32+64 multiply-accumulates/s", "frac": macs / IMAD_WIDE_PEAK,
             "windows_per_term": _nwin(terms_per_launch),
             "note": f"one bucket add per term and window; {fq_mults_per_add} F_q multiplies per batched-affine add x {wide_per_mult} "
-                    "IMAD.WIDE-class fmaheavy slots each (SASS of fp_mul_outlined, profiles/r2_sass_fp_mul.txt); peak = 32 "
+                    "IMAD.WIDE-equivalent fmaheavy slots each (SASS of fp_mul_outlined, profiles/r2_sass_fp_mul.txt: 120 IMAD.WIDE x 4 cycles + 35 "
+                    "IMAD / IMAD.HI / IMAD.X / IMAD.MOV x 2 cycles); peak = 32 "
                     "IMAD.WIDE / clk / SM (ncu: sm__pipe_fmaheavy_cycles_active, profiles/r2_notes.md) x 148 SMs x 1.965 GHz"}
 
 
@@ -455,7 +462,7 @@ def run_prove(args, c):
     check(L.b200_profile(1))
     prof0 = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof0))          # reset counters
-    ms_total = timed(c, step_device, args.steps)
+    ms_total = timed(c, step_device, args.steps, profile=args.profile_region)
     prof = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof))
     check(L.b200_profile(0))
@@ -621,7 +628,7 @@ def run_msm(args, c):
     check(L.b200_profile(1))
     prof = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof))
-    ms = timed(c, step_device, args.steps) / args.steps
+    ms = timed(c, step_device, args.steps, profile=args.profile_region) / args.steps
     check(L.b200_profile_read(prof))
     check(L.b200_profile(0))
     clk = clocks.stop() if rank == 0 else None
@@ -654,7 +661,7 @@ def run_msm(args, c):
             "roofline": {"bound": "hbm", "kernel": f"G{group} bucket accumulation phase of this rank's shard", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src, "traffic": None,
                          "avg_launch_ms": acc_ms / acc_l,
-                         "alu": alu_model(acc_terms / acc_l, acc_ms / acc_l, 6 if group == 1 else 6 * 320 / 131.0) if acc_ms > 0 else None}}
+                         "alu": alu_model(acc_terms / acc_l, acc_ms / acc_l, 6 if group == 1 else 6 * 2.6) if acc_ms > 0 else None}}
     if not args.no_extras and world == 1:
         try:
             ref = CpuReference()

@@ -324,6 +324,20 @@ void launch_tree_sum(XYZZ<F>* partials, uint32_t n, XYZZ<F>* d_out, cudaStream_t
   g_launches += 2;
 }
 
+// sum_b b * S_b over the bucket array -> one XYZZ record (msm.cuh: rows / columns, bit planes, Horner).  `scratch` holds
+// H + K + (c - 1) + 1 records.  Tiny bucket sets keep the segment kernel.
+template <class F>
+void launch_bucket_tail(const XYZZ<F>* buckets, uint32_t c, XYZZ<F>* scratch, XYZZ<F>* d_out, cudaStream_t st) {
+  const uint32_t bits = c - 1, kl = (bits + 1) / 2, kh = bits - kl, K = 1u << kl, H = 1u << kh;
+  XYZZ<F>* R = scratch;
+  XYZZ<F>* C = scratch + H;
+  XYZZ<F>* planes = C + K;
+  k_tail_rowcol<F><<<nblocks((size_t)(H + K) * 32, 128), 128, 0, st>>>(buckets, kl, H, R, C);
+  k_tail_planes<F><<<nblocks((size_t)(bits + 1) * 32, 128), 128, 0, st>>>(R, C, kl, kh, planes);
+  k_tail_horner<F><<<1, 32, 0, st>>>(planes, bits, d_out);
+  g_launches += 3;
+}
+
 // Front end: signed-digit recode + counting sort of n scalars into bucket order (3 launches).
 int msm_sort(SortScratch& ss, const MsmShape& shape, const Fr* d_scalars, size_t n, int mont, cudaStream_t st) {
   if (n > ss.sh.n || shape.c != ss.sh.c || shape.table_stride != ss.sh.table_stride)
@@ -420,9 +434,14 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
       g_prof_recs.push_back(pr);
     }
     k_merge_slices_affine<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(prev, stb, sh.nbuckets, buckets);
-    k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
-    launch_tree_sum<F>(partials, b->nseg, d_out, st);
-    g_launches += 2;
+    if (sh.c >= 7) {
+      launch_bucket_tail<F>(buckets, sh.c, partials, d_out, st);
+      g_launches += 1;
+    } else {
+      k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
+      launch_tree_sum<F>(partials, b->nseg, d_out, st);
+      g_launches += 2;
+    }
     CU(cudaGetLastError());
     return B200_OK;
   }
@@ -435,9 +454,14 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     g_prof_recs.push_back(pr);
   }
   k_merge_slices<F><<<nblocks(sh.nbuckets, 128), 128, 0, st>>>(b->slice_out.as<XYZZ<F>>(), stb, sh.nbuckets, buckets);
-  k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
-  launch_tree_sum<F>(partials, b->nseg, d_out, st);
-  g_launches += 3;
+  if (sh.c >= 7) {
+    launch_bucket_tail<F>(buckets, sh.c, partials, d_out, st);
+    g_launches += 1;
+  } else {
+    k_bucket_reduce<F><<<nblocks(b->nseg, 128), 128, 0, st>>>(buckets, sh.nbuckets, b->seg, partials, b->nseg);
+    launch_tree_sum<F>(partials, b->nseg, d_out, st);
+    g_launches += 3;
+  }
   CU(cudaGetLastError());
   return B200_OK;
 }

@@ -232,43 +232,56 @@ struct SliceTables {
 };
 // fixed != 0: slices hold exactly `cap` entry slots (last one of a bucket partially filled) — the
 // perfect-binary-tree layout of the batched-affine accumulation.
-__global__ void k_scan(const uint32_t* __restrict__ counts, uint32_t m, uint32_t cap, int fixed, uint32_t* offsets,
-                       uint32_t* cursor, SliceTables st) {
-  __shared__ uint32_t part[1024];
-  __shared__ uint32_t spart[1024];
-  uint32_t t = threadIdx.x, T = blockDim.x;
-  uint32_t per = (m + T - 1) / T;
-  uint32_t lo = t * per, hi = lo + per < m ? lo + per : m;
-  uint32_t sum = 0, ssum = 0;
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t c = counts[k];
-    sum += c;
-    ssum += k == 0 ? 0 : (c <= cap ? 1 : (c + cap - 1) / cap);
-  }
-  part[t] = sum;
-  spart[t] = ssum;
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t m, uint32_t cap, int fixed,
+                                               uint32_t* offsets, uint32_t* cursor, SliceTables st) {
+  // One block walks the m counters in coalesced tiles of blockDim.x; (entry count, slice count) are packed into one
+  // 64-bit value so a single warp-shuffle scan + a scan of the warp totals serves both prefix sums.  (The first version
+  // gave every thread 64 consecutive counters: uncoalesced and serial, 140 us for 2^16 buckets.)
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry_s;
+  const uint32_t t = threadIdx.x, T = blockDim.x, lane = t & 31u, warp = t >> 5, nwarps = T >> 5;
+  if (t == 0) carry_s = 0ull;
   __syncthreads();
-  for (uint32_t off = 1; off < T; off <<= 1) {  // Hillis-Steele inclusive scan
-    uint32_t v = t >= off ? part[t - off] : 0;
-    uint32_t sv = t >= off ? spart[t - off] : 0;
+  for (uint32_t base = 0; base < m; base += T) {
+    uint32_t k = base + t;
+    uint32_t c = k < m ? counts[k] : 0u;
+    uint32_t sl = (k == 0 || k >= m) ? 0u : (c <= cap ? 1u : (c + cap - 1) / cap);
+    unsigned long long v = ((unsigned long long)sl << 32) | c, incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long up = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((int)lane >= off) incl += up;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    part[t] += v;
-    spart[t] += sv;
+    if (warp == 0) {
+      unsigned long long w = lane < nwarps ? wsum[lane] : 0ull, wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned long long up = __shfl_up_sync(0xffffffffu, wi, off);
+        if ((int)lane >= off) wi += up;
+      }
+      wsum[lane] = wi - w;   // exclusive prefix of the warp totals; lane 31's inclusive value is the tile total
+    }
+    __syncthreads();
+    unsigned long long carry = carry_s;
+    unsigned long long excl = carry + wsum[warp] + (incl - v);
+    if (k < m) {
+      uint32_t run = (uint32_t)excl, srun = (uint32_t)(excl >> 32);
+      offsets[k] = run;
+      cursor[k] = run;
+      st.slice_off[k] = srun;
+    }
+    __syncthreads();
+    if (t == T - 1) carry_s = excl + v;   // inclusive prefix of the tile's last element = new carry
     __syncthreads();
   }
-  uint32_t run = part[t] - sum, srun = spart[t] - ssum;
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t c = counts[k];
-    offsets[k] = run;
-    cursor[k] = run;
-    st.slice_off[k] = srun;
-    if (k) srun += c <= cap ? 1 : (c + cap - 1) / cap;
-    run += c;
+  if (t == 0) {
+    unsigned long long tot = carry_s;
+    offsets[m] = (uint32_t)tot;
+    st.slice_off[m] = (uint32_t)(tot >> 32);
   }
-  if (t == T - 1) {
-    offsets[m] = part[T - 1];
-    st.slice_off[m] = spart[T - 1];
-  }
+  (void)fixed;
 }
 
 // slice_start / slice_end of every slice, one thread per bucket (k_scan wrote slice_off and offsets)
@@ -407,6 +420,73 @@ k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t per_block,
     }
     if (t == 0) out[blockIdx.x] = r;
   }
+}
+
+// ---- weighted bucket reduction with a short dependency chain ---------------------------------------------------------
+// sum_{b=1..B} b * S_b (buckets[b-1] = S_b, B = 2^(c-1)) without running sums: with b - 1 = hi*K + lo (K = 2^kl),
+//     sum b S_b = K * sum_hi hi * R_hi + sum_lo lo * C_lo + sum_hi R_hi,   R_hi = sum_lo S_(hi,lo),  C_lo = sum_hi S_(hi,lo)
+// (1) k_tail_rowcol: one warp per row and per column (strided adds + a 5-level shuffle tree);
+// (2) k_tail_planes: sum_i i * P_i over <= K points by bit planes, one warp per (group, bit): T_j = sum over the i with
+//     bit j set, plus one warp for the plain sum of the rows;
+// (3) k_tail_horner: the c-1 planes of the combined weight (low kl bits from the columns, high bits from the rows) in one
+//     Horner chain of c-1 doublings and additions, plus the plain sum.
+// Depth: ~(K/32 + 5) + (K/32 + 5) + 2(c-1) dependent group operations instead of 2*seg + 16 doublings + ... per thread
+// followed by two more tree levels — 0.59 -> ~0.2 ms on a 2^16-bucket set, which is the serial tail of every MSM
+// (stand-alone MSM latency, and the per-rank critical path when a proof is sharded over 8 GPUs).
+template <class F>
+__device__ __forceinline__ XYZZ<F> warp_sum_xyzz(XYZZ<F> acc) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    XYZZ<F> other = shfl_down_struct(acc, off, 32);
+    xyzz_add(acc, other);
+  }
+  return acc;   // lane 0 holds the sum
+}
+// warps [0, H): R[hi];  warps [H, H+K): C[lo]      (H = B / K rows of K buckets)
+template <class F>
+__global__ void __launch_bounds__(128) k_tail_rowcol(const XYZZ<F>* __restrict__ buckets, uint32_t kl, uint32_t H,
+                                                     XYZZ<F>* __restrict__ R, XYZZ<F>* __restrict__ C) {
+  const uint32_t K = 1u << kl;
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (w >= H + K) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (w < H) {
+    for (uint32_t lo = lane; lo < K; lo += 32) xyzz_add(acc, buckets[((size_t)w << kl) + lo]);
+  } else {
+    uint32_t lo = w - H;
+    for (uint32_t hi = lane; hi < H; hi += 32) xyzz_add(acc, buckets[((size_t)hi << kl) + lo]);
+  }
+  acc = warp_sum_xyzz(acc);
+  if (lane == 0) (w < H ? R[w] : C[w - H]) = acc;
+}
+// planes[j] for j < kl: sum of C[i] over i with bit j set; planes[kl + j] for j < kh: sum of R[i] over i with bit j set;
+// planes[kl + kh]: sum of all R[i].   One warp per plane.
+template <class F>
+__global__ void __launch_bounds__(128) k_tail_planes(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict__ C, uint32_t kl,
+                                                     uint32_t kh, XYZZ<F>* __restrict__ planes) {
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (w > kl + kh) return;
+  const XYZZ<F>* src = w < kl ? C : R;
+  const uint32_t n = w < kl ? (1u << kl) : (1u << kh);
+  const uint32_t bit = w < kl ? w : w - kl;
+  const bool all = w == kl + kh;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = lane; i < n; i += 32)
+    if (all || ((i >> bit) & 1u)) xyzz_add(acc, src[i]);
+  acc = warp_sum_xyzz(acc);
+  if (lane == 0) planes[w] = acc;
+}
+// out = sum_{j < kl + kh} 2^j planes[j] + planes[kl + kh]
+template <class F>
+__global__ void __launch_bounds__(32) k_tail_horner(const XYZZ<F>* __restrict__ planes, uint32_t nplanes, XYZZ<F>* __restrict__ out) {
+  if (threadIdx.x | blockIdx.x) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int j = (int)nplanes - 1; j >= 0; j--) {
+    acc = xyzz_dbl(acc);
+    xyzz_add(acc, planes[j]);
+  }
+  xyzz_add(acc, planes[nplanes]);
+  out[0] = acc;
 }
 
 // XYZZ (Montgomery) -> standard-form Jacobian (x, y, 1), infinity -> zeros.

@@ -243,11 +243,27 @@ int msm_tail(const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t 
   SliceTables st{const_cast<uint32_t*>(slice_off), nullptr, nullptr};
   unsigned nb = (nbuckets + 127) / 128;
   for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_merge_slices_affine<F>(pts.data(), st, nbuckets, buckets.data()); });
+  XYZZ<F> total;
+  if (seg == 0) {   // the rows / columns + bit planes + Horner tail (nbuckets = 2^(c-1)), as launch_bucket_tail issues it
+    uint32_t bits = 0;
+    while ((1u << bits) < nbuckets) bits++;
+    if ((1u << bits) != nbuckets) return 7;
+    const uint32_t kl = (bits + 1) / 2, kh = bits - kl, K = 1u << kl, H = 1u << kh;
+    std::vector<XYZZ<F>> scratch((size_t)H + K + bits + 1);
+    XYZZ<F>*R = scratch.data(), *C = R + H, *planes = C + K;
+    unsigned nb1 = ((H + K) * 32 + 127) / 128, nb2 = ((bits + 1) * 32 + 127) / 128;
+    for (unsigned b = 0; b < nb1; b++) run_cta(b, 128, nb1, [&] { k_tail_rowcol<F>(buckets.data(), kl, H, R, C); });
+    for (unsigned b = 0; b < nb2; b++) run_cta(b, 128, nb2, [&] { k_tail_planes<F>(R, C, kl, kh, planes); });
+    run_cta(0, 32, 1, [&] { k_tail_horner<F>(planes, bits, &total); });
+    F out[3];
+    run_cta(0, 32, 1, [&] { k_finalize<F>(&total, out); });
+    std::memcpy(out_std, out, sizeof out);
+    return 0;
+  }
   uint32_t nseg = (nbuckets + seg - 1) / seg;
   std::vector<XYZZ<F>> partials((size_t)nseg + 1024);
   nb = (nseg + 127) / 128;
   for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_bucket_reduce<F>(buckets.data(), nbuckets, seg, partials.data(), nseg); });
-  XYZZ<F> total;
   if (nseg <= 64) {  // (the library switches at 1024; a low threshold here exercises the two-level path on small inputs)
     run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data(), nseg, nseg, &total); });
   } else {
@@ -360,12 +376,22 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)
       run_cta(b, 128, cdiv(sh.nbuckets, 128), [&] { k_merge_slices<F>(slice_out.data(), stb, sh.nbuckets, buckets.data()); });
   }
-  uint32_t seg = sh.nbuckets >= 256 ? 4 : 1, nseg = (sh.nbuckets + seg - 1) / seg;
-  std::vector<XYZZ<F>> partials((size_t)nseg + 1024);
-  for (unsigned b = 0; b < cdiv(nseg, 128); b++)
-    run_cta(b, 128, cdiv(nseg, 128), [&] { k_bucket_reduce<F>(buckets.data(), sh.nbuckets, seg, partials.data(), nseg); });
   XYZZ<F> total_pt;
-  run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data(), nseg, nseg, &total_pt); });
+  if (c >= 7) {
+    const uint32_t bits = c - 1, kl = (bits + 1) / 2, kh = bits - kl, K = 1u << kl, H = 1u << kh;
+    std::vector<XYZZ<F>> scratch((size_t)H + K + bits + 1);
+    XYZZ<F>*Rr = scratch.data(), *Cc = Rr + H, *planes = Cc + K;
+    unsigned nb1 = cdiv((size_t)(H + K) * 32, 128), nb2 = cdiv((size_t)(bits + 1) * 32, 128);
+    for (unsigned b = 0; b < nb1; b++) run_cta(b, 128, nb1, [&] { k_tail_rowcol<F>(buckets.data(), kl, H, Rr, Cc); });
+    for (unsigned b = 0; b < nb2; b++) run_cta(b, 128, nb2, [&] { k_tail_planes<F>(Rr, Cc, kl, kh, planes); });
+    run_cta(0, 32, 1, [&] { k_tail_horner<F>(planes, bits, &total_pt); });
+  } else {
+    uint32_t seg = sh.nbuckets >= 256 ? 4 : 1, nseg = (sh.nbuckets + seg - 1) / seg;
+    std::vector<XYZZ<F>> partials((size_t)nseg + 1024);
+    for (unsigned b = 0; b < cdiv(nseg, 128); b++)
+      run_cta(b, 128, cdiv(nseg, 128), [&] { k_bucket_reduce<F>(buckets.data(), sh.nbuckets, seg, partials.data(), nseg); });
+    run_cta(0, 256, 1, [&] { k_sum_points<F>(partials.data(), nseg, nseg, &total_pt); });
+  }
   F out[3];
   run_cta(0, 32, 1, [&] { k_finalize<F>(&total_pt, out); });
   std::memcpy(out_std, out, sizeof out);

@@ -119,7 +119,9 @@ def test_g2_forward_kernel_cta_emulation(lib):
     _run(lib, 2, 0, 8, 3, 70, seed=11, fwd=0)
 
 
-@pytest.mark.parametrize("group,nbuckets,seg", [(1, 300, 4), (1, 37, 1), (1, 700, 4), (2, 90, 4)])
+@pytest.mark.parametrize("group,nbuckets,seg", [(1, 300, 4), (1, 37, 1), (1, 700, 4), (2, 90, 4),
+                                                # seg = 0: rows / columns + bit planes + Horner tail, nbuckets = 2^(c-1)
+                                                (1, 64, 0), (1, 128, 0), (1, 2048, 0), (2, 256, 0)])
 def test_msm_tail_kernels(lib, group, nbuckets, seg):
     """k_merge_slices_affine (thread-per-bucket path and the warp path for buckets with > 12 slices, ballot + shuffles),
     k_bucket_reduce (running sums + small scalar multiple per segment), k_sum_points (one and two levels) and k_finalize:
@@ -161,7 +163,8 @@ def test_msm_tail_kernels(lib, group, nbuckets, seg):
         assert got == ((e[0], e[1], 1) if group == 1 else (e[0], e[1], (1, 0)))
 
 
-@pytest.mark.parametrize("group,n,c,S", [(1, 150, 5, 0), (1, 150, 5, 16), (1, 97, 4, 64), (1, 40, 9, 0), (2, 48, 4, 8)])
+@pytest.mark.parametrize("group,n,c,S", [(1, 150, 5, 0), (1, 150, 5, 16), (1, 97, 4, 64), (1, 40, 9, 0), (2, 48, 4, 8),
+                                         (1, 300, 8, 8), (2, 60, 7, 0)])
 def test_whole_msm_pipeline_on_the_cpu(lib, group, n, c, S):
     """Every kernel of an MSM in the library's order (window precompute, signed-digit recode, counting sort, slice tables,
     bucket accumulation in both modes, slice merge, weighted bucket reduction, tree sum, normalisation) on the CPU
