@@ -476,17 +476,31 @@ __global__ void __launch_bounds__(128) k_tail_planes(const XYZZ<F>* __restrict__
   acc = warp_sum_xyzz(acc);
   if (lane == 0) planes[w] = acc;
 }
-// out = sum_{j < kl + kh} 2^j planes[j] + planes[kl + kh]
+// out = sum_{j < nplanes} 2^j planes[j] + planes[nplanes].  One warp; lane q < 16 takes `per` consecutive planes (Horner),
+// shifts its partial sum by q * per doublings, and a 4-level shuffle tree adds the 16 partial sums: ~nplanes + 5 dependent
+// group operations instead of 2 * nplanes for a single Horner chain.
 template <class F>
 __global__ void __launch_bounds__(32) k_tail_horner(const XYZZ<F>* __restrict__ planes, uint32_t nplanes, XYZZ<F>* __restrict__ out) {
-  if (threadIdx.x | blockIdx.x) return;
+  if (blockIdx.x) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t per = (nplanes + 15) / 16;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (int j = (int)nplanes - 1; j >= 0; j--) {
-    acc = xyzz_dbl(acc);
-    xyzz_add(acc, planes[j]);
+  if (lane < 16) {
+    const uint32_t lo = lane * per, hi = lo + per < nplanes ? lo + per : nplanes;
+    for (int j = (int)hi - 1; j >= (int)lo; j--) {
+      acc = xyzz_dbl(acc);
+      xyzz_add(acc, planes[j]);
+    }
+    if (lo < nplanes)
+      for (uint32_t d = 0; d < lo; d++) acc = xyzz_dbl(acc);
+    if (lane == 0) xyzz_add(acc, planes[nplanes]);
   }
-  xyzz_add(acc, planes[nplanes]);
-  out[0] = acc;
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    XYZZ<F> other = shfl_down_struct(acc, off, 32);
+    xyzz_add(acc, other);
+  }
+  if (lane == 0) out[0] = acc;
 }
 
 // XYZZ (Montgomery) -> standard-form Jacobian (x, y, 1), infinity -> zeros.
