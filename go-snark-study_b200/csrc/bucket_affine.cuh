@@ -45,9 +45,6 @@ struct AffineRound {
   F* pre;                     // prefix products, one per pair
   F* others;                  // per thread: product of the other threads' totals in its block
   F* btot;                    // per block: product of all denominators (then inverted in place)
-  const F* dx_in;             // rounds >= 2: x-difference of every pair, left by the previous round's backward pass
-                              //   (zero = "decide from the full operands": an operand at infinity / x = 0 / equal x)
-  F* dx_out;                  // backward pass: x-differences of the next round's pairs (null in the last round)
   uint2* pair_ids;            // round 1: (entry id of P, entry id of Q) per pair, 0xffffffff = absent (forward writes, backward reads)
   uint32_t q_log;             // log2(pairs per slice in this round)
   uint32_t round;             // 1-based
@@ -130,17 +127,6 @@ __device__ __forceinline__ bool aff_forward_denominator(const AffineRound<F>& a,
     pp = &a.table[e0 >> 1];
     qp = &a.table[e1 >> 1];
   } else {
-    if (a.dx_in) {   // 32 contiguous bytes per pair instead of two x-coordinates out of two 64 / 128-byte nodes
-      F dxs = ld_fe(&a.dx_in[p]);
-      if (!dxs.is_zero()) {
-        d = dxs;
-        return true;
-      }
-      Affine<F> P, Q;
-      aff_operands(a, p, npairs, P, Q);
-      aff_denominator(P, Q, d);
-      return true;
-    }
     size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
     pp = &a.prev[base];
     qp = &a.prev[base + 1];
@@ -174,15 +160,6 @@ __device__ __forceinline__ F shfl_down_fe(const F& v, int delta) {
   uint32_t* d = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
   for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
-  return r;
-}
-template <class F>
-__device__ __forceinline__ F shfl_xor1_fe(const F& v) {   // the value of the neighbouring lane (lane ^ 1)
-  F r;
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = __shfl_xor_sync(0xffffffffu, s[i], 1);
   return r;
 }
 template <class F>
@@ -265,34 +242,25 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound
   for (int k = kAffT - 1; k >= 0; k--) {
     uint32_t p = block_base + k * kAffBlock + t;
     Affine<F> P, Q;
-    Affine<F> Rr = Affine<F>::inf();
-    const bool live = aff_operands(a, p, npairs, P, Q);
-    if (live) {
-      F d;
-      int kind = aff_denominator(P, Q, d);
-      F inv_d = inv_run * a.pre[p];
-      inv_run = inv_run * d;
-      if (kind == 1) {
-        F lam = (Q.y - P.y) * inv_d;
-        F x3 = lam.sqr() - P.x - Q.x;
-        Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
-      } else if (kind == 2) {
-        F xx = P.x.sqr();
-        F lam = (xx.dbl() + xx) * inv_d;
-        F x3 = lam.sqr() - P.x.dbl();
-        Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
-      } else {
-        Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
-      }
-      a.out[p] = Rr;
+    if (!aff_operands(a, p, npairs, P, Q)) continue;
+    F d;
+    int kind = aff_denominator(P, Q, d);
+    F inv_d = inv_run * a.pre[p];
+    inv_run = inv_run * d;
+    Affine<F> Rr;
+    if (kind == 1) {
+      F lam = (Q.y - P.y) * inv_d;
+      F x3 = lam.sqr() - P.x - Q.x;
+      Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+    } else if (kind == 2) {
+      F xx = P.x.sqr();
+      F lam = (xx.dbl() + xx) * inv_d;
+      F x3 = lam.sqr() - P.x.dbl();
+      Rr = Affine<F>{x3, lam * (P.x - x3) - P.y};
+    } else {
+      Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
     }
-    if (a.dx_out) {   // the next round pairs node p (even lane) with node p + 1 (odd lane): leave their x-difference
-      F xo = shfl_xor1_fe(Rr.x);
-      if (live && !(t & 1u)) {
-        F dxn = (Rr.x.is_zero() || xo.is_zero()) ? F::zero() : xo - Rr.x;
-        a.dx_out[p >> 1] = dxn;
-      }
-    }
+    a.out[p] = Rr;
   }
 }
 

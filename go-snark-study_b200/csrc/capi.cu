@@ -42,6 +42,7 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
 int g_acc_mode = 0;
+int g_bwd_pad = 0;       // B200_CFG_BWD_SMEM_PAD (experiment): dynamic shared memory given to the backward pass to cap its CTAs/SM
 int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
@@ -150,7 +151,7 @@ struct Bases {
   uint32_t nseg = 0, seg = 0;
   // batched-affine accumulation (affine_S > 0): ping-pong node buffers, prefix products, per-thread / per-block products
   uint32_t affine_S = 0;
-  DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot, aff_ids, aff_dx;
+  DevBuf nodeA, nodeB, aff_pre, aff_others, aff_btot, aff_ids;
 };
 
 int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
@@ -231,7 +232,6 @@ int bases_create(const uint64_t* pts, size_t n, int c, int group, std::unique_pt
       CU(b->nodeB.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(Affine<F>)));
       CU(b->aff_pre.alloc(nsl * (S / 2) * sizeof(F)));
       CU(b->aff_ids.alloc(nsl * (S / 2) * sizeof(uint2)));
-      CU(b->aff_dx.alloc(nsl * (S / 4 ? S / 4 : 1) * sizeof(F)));
       size_t nblk_max = (nsl * (S / 2) + kAffBlock * kAffPairs - 1) / (kAffBlock * kAffPairs);
       CU(b->aff_others.alloc(nblk_max * kAffBlock * sizeof(F)));
       CU(b->aff_btot.alloc(nblk_max * sizeof(F)));
@@ -407,18 +407,11 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
     const Affine<F>* prev = nullptr;
     // all R rounds affine: inside a proof the per-round inversion latency is hidden by the other MSMs' streams
-    bool dx_valid = false;
     for (uint32_t r = 1; r <= R; r++) {
       ar.round = r;
       ar.q_log = R - r;
       ar.prev = prev;
       ar.out = bufs[(r - 1) & 1];
-      // the backward pass of round r leaves the x-differences of round r + 1's pairs: that round's forward pass then
-      // reads 32 contiguous bytes per pair instead of two x-coordinates out of two nodes
-      const bool staged = g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2);
-      ar.dx_in = (r >= 2 && dx_valid) ? b->aff_dx.as<F>() : nullptr;
-      ar.dx_out = (r < R && !staged) ? b->aff_dx.as<F>() : nullptr;
-      dx_valid = ar.dx_out != nullptr;
       uint64_t npairs_max = nsl_bound << ar.q_log;
       unsigned nb = (unsigned)((npairs_max + kAffBlock * kAffPairs - 1) / (kAffBlock * kAffPairs));
       // CTAs/SM bounds = register caps (ptxas -v: forward 64 / 128 registers, backward 96 / 128, G1 / G2; measured
@@ -427,12 +420,12 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
         k_affine_forward<F, kAffPairs, 8><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
         if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 5><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
-        else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, g_bwd_pad, st>>>(ar);
       } else {
         k_affine_forward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
         if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 4><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
-        else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, g_bwd_pad, st>>>(ar);
       }
       prev = ar.out;
       g_launches += 3;
@@ -1153,6 +1146,10 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
+    return B200_OK;
+  }
+  if (key == 3 && value >= 0 && value <= 48 * 1024) {   // experiment knob, not in the header
+    g_bwd_pad = value;
     return B200_OK;
   }
   if (key == B200_CFG_TMA_STAGING && value >= 0 && value <= 2) {

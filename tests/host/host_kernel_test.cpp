@@ -43,7 +43,6 @@ uint32_t stub_shfl(uint32_t v, int arg, int mode, int width) {
   int seg = lane & ~(width - 1), pos = lane & (width - 1), src;
   if (mode == 0) src = seg + (arg & (width - 1));
   else if (mode == 1) src = pos - arg >= 0 ? lane - arg : lane;
-  else if (mode == 3) src = seg + ((pos ^ arg) & (width - 1));
   else src = pos + arg < width ? lane + arg : lane;
   uint32_t r = g_xchg[warp][src];
   pthread_barrier_wait(&g_warp_bar[warp]);
@@ -158,7 +157,15 @@ void run_backward(int variant, const AffineRound<F>& a, unsigned nb) {
       });
     return;
   }
-  for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_backward<F, T, 1>(a); });   // (lane shuffles)
+  blockDim.x = kAffBlock;
+  gridDim.x = nb;
+  for (unsigned b = 0; b < nb; b++)
+    for (unsigned t = 0; t < kAffBlock; t++) {
+      blockIdx.x = b;
+      threadIdx.x = t;
+      (void)variant;
+      k_affine_backward<F, T, 1>(a);
+    }
 }
 
 template <class F, int T>
@@ -174,8 +181,6 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
   std::vector<F> pre((size_t)nslices * (S / 2));
   std::vector<uint2> ids((size_t)nslices * (S / 2));
-  std::vector<F> dx((size_t)nslices * (S / 4 ? S / 4 : 1));
-  bool dx_valid = false;
   unsigned nb_max = (nslices * (S / 2) + kAffBlock * T - 1) / (kAffBlock * T);
   std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
   AffineRound<F> ar{};
@@ -195,9 +200,6 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
     ar.q_log = R - r;
     ar.prev = prev;
     ar.out = bufs[(r - 1) & 1];
-    ar.dx_in = (r >= 2 && dx_valid) ? dx.data() : nullptr;
-    ar.dx_out = (r < R && variant == 0) ? dx.data() : nullptr;
-    dx_valid = ar.dx_out != nullptr;
     uint32_t npairs = nslices << ar.q_log;
     unsigned nb = (npairs + kAffBlock * T - 1) / (kAffBlock * T);
     if (fwd_variant < 0) {
@@ -339,7 +341,6 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     std::vector<Affine<F>> bufA((size_t)nslices * (S / 2) + 1), bufB((size_t)nslices * (S / 2) + 1);
     std::vector<F> pre((size_t)nslices * (S / 2) + 1);
     std::vector<uint2> ids((size_t)nslices * (S / 2) + 1);
-    std::vector<F> dx((size_t)nslices * (S / 4 ? S / 4 : 1) + 1);
     unsigned nb_max = cdiv((size_t)nslices * (S / 2), kAffBlock * T) + 1;
     std::vector<F> others((size_t)nb_max * kAffBlock), btot(nb_max);
     AffineRound<F> ar{};
@@ -359,14 +360,11 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
       ar.q_log = R - r;
       ar.prev = prev;
       ar.out = bufs[(r - 1) & 1];
-      // the library's default: register-load backward pass that leaves the next round's x-differences
-      ar.dx_in = r >= 2 ? dx.data() : nullptr;
-      ar.dx_out = r < R ? dx.data() : nullptr;
       unsigned nb = cdiv((size_t)nslices << ar.q_log, kAffBlock * T);
       if (nb == 0) nb = 1;
       for (unsigned b = 0; b < nb; b++) run_cta(b, kAffBlock, nb, [&] { k_affine_forward<F, T, 1>(ar); });
       for (unsigned b = 0; b < cdiv((size_t)nb * 32, 128); b++) run_cta(b, 128, cdiv((size_t)nb * 32, 128), [&] { k_affine_invert<F>(ar.btot, nb); });
-      run_backward<F, T>(0, ar, nb);
+      run_backward<F, T>(1, ar, nb);   // the staged kernel, as the library launches it
       prev = ar.out;
     }
     for (unsigned b = 0; b < cdiv(sh.nbuckets, 128); b++)

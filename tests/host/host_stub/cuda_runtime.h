@@ -46,7 +46,6 @@ inline void __syncthreads() { stub_syncthreads(); }
 inline uint32_t __shfl_sync(unsigned, uint32_t v, int lane, int width = 32) { return stub_shfl(v, lane, 0, width); }
 inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 1, width); }
 inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d, int width = 32) { return stub_shfl(v, (int)d, 2, width); }
-inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int mask, int width = 32) { return stub_shfl(v, mask, 3, width); }
 inline unsigned long long __shfl_up_sync(unsigned m, unsigned long long v, unsigned d, int width = 32) {
   uint32_t lo = __shfl_up_sync(m, (uint32_t)v, d, width), hi = __shfl_up_sync(m, (uint32_t)(v >> 32), d, width);
   return ((unsigned long long)hi << 32) | lo;
