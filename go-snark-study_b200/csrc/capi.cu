@@ -42,7 +42,6 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
 int g_acc_mode = 0;
-int g_bwd_pad = 0;       // B200_CFG_BWD_SMEM_PAD (experiment): dynamic shared memory given to the backward pass to cap its CTAs/SM
 int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
@@ -420,12 +419,12 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
         k_affine_forward<F, kAffPairs, 8><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
         if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 5><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
-        else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, g_bwd_pad, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 5><<<nb, kAffBlock, 0, st>>>(ar);
       } else {
         k_affine_forward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
         k_affine_invert<F><<<nblocks((size_t)nb * 32, 128), 128, 0, st>>>(ar.btot, nb);
         if (g_tma_staging == 1 || (g_tma_staging == 2 && r >= 2)) k_affine_backward_staged<F, kAffPairs, 4><<<nb, kAffBlock, AffStageLayout<F>::kSmem, st>>>(ar);
-        else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, g_bwd_pad, st>>>(ar);
+        else k_affine_backward<F, kAffPairs, 4><<<nb, kAffBlock, 0, st>>>(ar);
       }
       prev = ar.out;
       g_launches += 3;
@@ -1146,10 +1145,6 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
-    return B200_OK;
-  }
-  if (key == 3 && value >= 0 && value <= 48 * 1024) {   // experiment knob, not in the header
-    g_bwd_pad = value;
     return B200_OK;
   }
   if (key == B200_CFG_TMA_STAGING && value >= 0 && value <= 2) {
