@@ -54,6 +54,10 @@ _SIGNATURES = {
     "b200_pinocchio_pk_load": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _int,
                                ctypes.POINTER(_h)],
     "b200_pinocchio_prove": [_h, _vp, _sz, _vp, _sz, _vp, _vp],
+    "b200_pinocchio_pk_load_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _int, _int, _int,
+                                     ctypes.POINTER(_h)],
+    "b200_pinocchio_prove_record_device": [_h, _vp, _sz, _vp, _sz, _vp],
+    "b200_pinocchio_finalize_records": [_vp, _int, _vp, _vp],
     "b200_pk_free": [_h],
     "b200_groth16_prove_device": [_h, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp],
     "b200_groth16_pk_load_shard": [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _sz, _int,

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "b200snark.h"
 #include "msm.cuh"
@@ -964,7 +965,28 @@ int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t
                            int window_bits, b200_pk_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();
-  return pinocchio_pk_load(a, ap, b2, bp, c, cp, kp, m, g1t, n_g1t, z, nz, npublic, window_bits, out);
+  return pinocchio_pk_load(a, ap, b2, bp, c, cp, kp, m, g1t, n_g1t, z, nz, npublic, window_bits, 0, 1, out);
+}
+int b200_pinocchio_pk_load_shard(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
+                                 const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
+                                 const uint64_t* g1t, size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic,
+                                 int window_bits, int rank, int world, b200_pk_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return pinocchio_pk_load(a, ap, b2, bp, c, cp, kp, m, g1t, n_g1t, z, nz, npublic, window_bits, rank, world, out);
+}
+int b200_pinocchio_prove_record_device(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx, void* d_record) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  if (!d_record) return fail(B200_EINVAL, "pinocchio_prove_record_device: null record pointer");
+  int rc = pinocchio_prove(pk, w, nw, px, npx, nullptr, nullptr, (uint8_t*)d_record);
+  if (rc) return rc;
+  return check_err_flag<Fr>("pinocchio_prove_record");
+}
+int b200_pinocchio_finalize_records(const void* d_records, int world, uint64_t* out_g1, uint64_t pi_b[24]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  NEED_INIT();
+  return pinocchio_finalize_records((const uint8_t*)d_records, world, out_g1, pi_b);
 }
 int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                          uint64_t* out_g1 /* 7 x 12: PiA PiAp PiBp PiC PiCp PiH PiKp */, uint64_t pi_b[24]) {

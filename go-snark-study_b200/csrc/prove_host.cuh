@@ -159,7 +159,9 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   const size_t l1 = npublic + 1;
   const size_t n_c_full = pk->n_c_full = m - l1;
   const size_t len[4] = {m, m, m, n_c_full + n_ptd};
-  const double wgt[4] = {1.0, 1.0, 2.8, 1.0};
+  // cost of a G2 term in G1 terms: 2.3-2.4 measured on the batched-affine kernels at the shard sizes of 1-4 ranks, 3.6 on the
+  // XYZZ kernels an 8-way split falls back to (profiles/r2_notes.md: per-rank phase times)
+  const double wgt[4] = {1.0, 1.0, world >= 8 ? 3.6 : 2.8, 1.0};
   double off[5] = {0, 0, 0, 0, 0};
   for (int k = 0; k < 4; k++) off[k + 1] = off[k] + wgt[k] * (double)len[k];
   auto cut = [&](int g, int k) -> size_t {   // first index of set k at or after the g-th cut of the line
@@ -592,12 +594,50 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
   return B200_OK;
 }
 
+// Pinocchio result slots (XYZZ, 256 B each): 0 PiA, 1 PiAp, 2 PiBp, 3 PiC, 4 PiCp, 5 PiH, 6 PiKp, 7 PiB (G2).
+// Base sets g[k]: 0 A, 1 Ap, 2 B (G2), 3 Bp, 4 C, 5 Cp, 6 Kp, 7 G1T.
+constexpr int kPinSlot[8] = {0, 1, 7, 2, 3, 4, 6, 5};
+constexpr size_t kPinRecordBytes = 8 * 256;
+
+// Sharded mode (world > 1): the eight MSMs are independent objects, so whole MSMs are dealt to the ranks — greedy
+// longest-first onto the least loaded rank by term count (a G2 term ~2.8 G1 terms) — and no MSM is split.  `owner[k]` is the
+// same on every rank.  (Eight objects: more than 8 ranks leave the rest idle.)
+void pinocchio_owners(size_t m, size_t l1, size_t n_g1t, int world, int owner[8]) {
+  double cost[8] = {(double)(m - l1), (double)(m - l1), 2.8 * (double)m, (double)m, (double)m, (double)m, (double)m, (double)n_g1t};
+  int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  std::stable_sort(order, order + 8, [&](int x, int y) { return cost[x] > cost[y]; });
+  std::vector<double> load((size_t)world, 0.0);
+  for (int q = 0; q < 8; q++) {
+    int k = order[q], best = 0;
+    for (int g = 1; g < world; g++)
+      if (load[g] < load[best]) best = g;
+    owner[k] = best;
+    load[best] += cost[k];
+  }
+}
+
+// sum the world records slot by slot (every slot is non-infinity on exactly one rank) -> standard-form outputs
+__global__ void k_pinocchio_gather_finalize(const uint8_t* recs, int world, Fq* out_g1, Fq2* out_b) {
+  uint32_t t = threadIdx.x;
+  if (t < 7) {
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (int g = 0; g < world; g++) xyzz_add(acc, *reinterpret_cast<const XYZZ<Fq>*>(recs + kPinRecordBytes * g + 256 * t));
+    store_jacobian_std(acc, out_g1 + 3 * t);
+  }
+  if (t == 32) {
+    XYZZ<Fq2> acc = XYZZ<Fq2>::inf();
+    for (int g = 0; g < world; g++) xyzz_add(acc, *reinterpret_cast<const XYZZ<Fq2>*>(recs + kPinRecordBytes * g + 256 * 7));
+    store_jacobian_std(acc, out_b);
+  }
+}
+
 int pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
                       const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m, const uint64_t* g1t,
-                      size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic, int wb, b200_pk_t* out) {
+                      size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic, int wb, int rank, int world, b200_pk_t* out) {
   if (!a || !ap || !b2 || !bp || !c || !cp || !kp || !g1t || !out)
     return fail(B200_EINVAL, "pinocchio_pk_load: null pointer");
   if (m == 0 || npublic + 1 > m || n_g1t == 0) return fail(B200_EINVAL, "pinocchio_pk_load: bad sizes");
+  if (world < 1 || rank < 0 || rank >= world) return fail(B200_EINVAL, "pinocchio_pk_load: bad shard %d/%d", rank, world);
   auto pk = std::make_unique<ProvingKey>();
   pk->kind = 2;
   pk->m = m;
@@ -606,17 +646,22 @@ int pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2,
   int rc = pk_common_init(*pk, z, nz, m);
   if (rc) return rc;
   size_t l1 = npublic + 1;
+  pk->rank = rank;
+  pk->world = world;
+  int owner[8];
+  pinocchio_owners(m, l1, n_g1t, world, owner);
+  auto mine = [&](int k) { return owner[k] == rank; };
   // snark.go:265-268: PiA, PiAp run over i in [NPublic+1, NVars)
   if (m > l1) {
-    if ((rc = bases_create<Fq>(a + 12 * l1, m - l1, wb, 1, pk->g[0], true))) return rc;
-    if ((rc = bases_create<Fq>(ap + 12 * l1, m - l1, wb, 1, pk->g[1], true))) return rc;
+    if (mine(0) && (rc = bases_create<Fq>(a + 12 * l1, m - l1, wb, 1, pk->g[0], true))) return rc;
+    if (mine(1) && (rc = bases_create<Fq>(ap + 12 * l1, m - l1, wb, 1, pk->g[1], true))) return rc;
   }
-  if ((rc = bases_create<Fq2>(b2, m, wb, 2, pk->g[2], true))) return rc;
-  if ((rc = bases_create<Fq>(bp, m, wb, 1, pk->g[3], true))) return rc;
-  if ((rc = bases_create<Fq>(c, m, wb, 1, pk->g[4], true))) return rc;
-  if ((rc = bases_create<Fq>(cp, m, wb, 1, pk->g[5], true))) return rc;
-  if ((rc = bases_create<Fq>(kp, m, wb, 1, pk->g[6], true))) return rc;
-  if ((rc = bases_create<Fq>(g1t, n_g1t, wb, 1, pk->g[7], true))) return rc;
+  if (mine(2) && (rc = bases_create<Fq2>(b2, m, wb, 2, pk->g[2], true))) return rc;
+  if (mine(3) && (rc = bases_create<Fq>(bp, m, wb, 1, pk->g[3], true))) return rc;
+  if (mine(4) && (rc = bases_create<Fq>(c, m, wb, 1, pk->g[4], true))) return rc;
+  if (mine(5) && (rc = bases_create<Fq>(cp, m, wb, 1, pk->g[5], true))) return rc;
+  if (mine(6) && (rc = bases_create<Fq>(kp, m, wb, 1, pk->g[6], true))) return rc;
+  if (mine(7) && (rc = bases_create<Fq>(g1t, n_g1t, wb, 1, pk->g[7], true))) return rc;
   CU(pk->s3.alloc((n_g1t + 4) * sizeof(Fr)));
   uint64_t h = g_next_pk++;
   g_pks[h] = std::move(pk);
@@ -624,66 +669,118 @@ int pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2,
   return B200_OK;
 }
 
+// d_rec_out != nullptr: leave this rank's 2 KB record of XYZZ results there (device) and return without synchronising —
+// the form the one-GPU tests use to emulate N ranks.
 int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx, uint64_t* out_g1,
-                    uint64_t* pi_b) {
+                    uint64_t* pi_b, uint8_t* d_rec_out = nullptr) {
   ProvingKey* pk = find_pk(h, 2);
   if (!pk) return fail(B200_EINVAL, "pinocchio_prove: bad proving-key handle");
-  if (!w || !px || !out_g1 || !pi_b) return fail(B200_EINVAL, "pinocchio_prove: null pointer");
+  if (!w || !px || (!d_rec_out && (!out_g1 || !pi_b))) return fail(B200_EINVAL, "pinocchio_prove: null pointer");
   size_t m = pk->m, l1 = pk->npublic + 1;
   if (nw != m) return fail(B200_EINVAL, "pinocchio_prove: witness length %zu != NVars %zu", nw, m);
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "pinocchio_prove: len(px) < len(Z)");
   size_t nq = npx - pk->Z.nb + 1;
   if (nq > pk->n_h_bases) return fail(B200_EINVAL, "pinocchio_prove: len(hx)=%zu exceeds len(G1T)=%zu", nq, pk->n_h_bases);
-  cudaStream_t st = g_stream, s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
-  cudaEvent_t e_in = pk->ev[0], e_wp = pk->ev[1], e_w = pk->ev[2], e1 = pk->ev[3], e2 = pk->ev[4], e3 = pk->ev[5];
+  const bool sharded = pk->world > 1;
+  const bool gather = sharded && !d_rec_out;
+  if (gather && !(g_comm.active() && g_comm.world == pk->world && g_comm.rank == pk->rank))
+    return fail(B200_EINVAL, "pinocchio_prove: sharded key (rank %d/%d) without a matching communicator (b200_comm_init)",
+                pk->rank, pk->world);
+  cudaStream_t st = g_stream, side[3] = {g_side[0], g_side[1], g_side[2]};
+  cudaEvent_t e_in = pk->ev[0], e_sorted[2] = {pk->ev[1], pk->ev[2]}, e_done[3] = {pk->ev[3], pk->ev[4], pk->ev[5]};
   Fr* dw = pk->s1.as<Fr>();
   Fr* dh = pk->s3.as<Fr>();
-  CU(pk->px.ensure(npx * sizeof(Fr)));
-  CU(cudaMemcpyAsync(dw, w, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  EV_REC(e_in, st);
   uint8_t* res = pk->res.as<uint8_t>();
-  auto R1 = [&](int k) { return reinterpret_cast<XYZZ<Fq>*>(res + 256 * k); };
-  int rc;
-  // result slots: 0 PiA, 1 PiAp, 2 PiBp, 3 PiC, 4 PiCp, 5 PiH, 6 PiKp, 7 PiB(G2)
-  // side stream 3: hx = px / Z (snark.go:280) and PiH (snark.go:284-286)
-  EV_WAIT(s3, e_in);
-  CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, s3));
-  if ((rc = msm_enqueue<Fq>(pk->g[7].get(), dh, nq, 0, R1(5), s3))) return rc;
-  // two shared sorts: w[l+1..m) feeds PiA, PiAp (snark.go:265-268); w feeds PiB, PiBp, PiC, PiCp, PiKp (:270-278)
-  if (m > l1) {
-    SortScratch& swp = pk->g[0]->sort;
-    if ((rc = msm_sort(swp, pk->g[0]->sh, dw + l1, m - l1, 0, st))) return rc;
-    EV_REC(e_wp, st);
-    EV_WAIT(s1, e_wp);
-    if ((rc = msm_buckets<Fq>(pk->g[1].get(), swp, m - l1, R1(1), s1))) return rc;
-  } else {
-    CU(cudaMemsetAsync(res, 0, 512, st));
+  CU(cudaMemcpyAsync(dw, w, m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(res, 0, kPinRecordBytes, st));        // slots this rank does not own stay at infinity
+  if (pk->g[7]) {
+    CU(pk->px.ensure(npx * sizeof(Fr)));
+    CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
   }
-  SortScratch& sw = pk->g[3]->sort;
-  if ((rc = msm_sort(sw, pk->g[3]->sh, dw, m, 0, st))) return rc;
-  EV_REC(e_w, st);
-  EV_WAIT(s2, e_w);
-  if ((rc = msm_buckets<Fq2>(pk->g[2].get(), sw, m, reinterpret_cast<XYZZ<Fq2>*>(res + 256 * 7), s2))) return rc;
-  EV_WAIT(s1, e_w);
-  if ((rc = msm_buckets<Fq>(pk->g[4].get(), sw, m, R1(3), s1))) return rc;
-  if ((rc = msm_buckets<Fq>(pk->g[5].get(), sw, m, R1(4), s1))) return rc;
-  EV_WAIT(s3, e_w);
-  if ((rc = msm_buckets<Fq>(pk->g[6].get(), sw, m, R1(6), s3))) return rc;
-  if (m > l1 && (rc = msm_buckets<Fq>(pk->g[0].get(), pk->g[0]->sort, m - l1, R1(0), st))) return rc;
-  if ((rc = msm_buckets<Fq>(pk->g[3].get(), sw, m, R1(2), st))) return rc;
-  EV_REC(e1, s1);
-  EV_REC(e2, s2);
-  EV_REC(e3, s3);
-  EV_WAIT(st, e1);
-  EV_WAIT(st, e2);
-  EV_WAIT(st, e3);
+  EV_REC(e_in, st);
+  int rc;
+  int next_side = 0;
+  auto slot_g1 = [&](int k) { return reinterpret_cast<XYZZ<Fq>*>(res + 256 * kPinSlot[k]); };
+  // side stream: hx = px / Z (snark.go:280) and PiH (snark.go:284-286)
+  bool used[3] = {false, false, false};
+  if (pk->g[7]) {
+    cudaStream_t s3 = side[2];
+    used[2] = true;
+    EV_WAIT(s3, e_in);
+    CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, s3));
+    if ((rc = msm_enqueue<Fq>(pk->g[7].get(), dh, nq, 0, slot_g1(7), s3))) return rc;
+  }
+  // two scalar vectors: w[l+1..m) feeds PiA, PiAp (snark.go:265-268); w feeds PiB, PiBp, PiC, PiCp, PiKp (:270-278).
+  // Per vector ONE digit sort (held by the first owned set of the group), the bucket phases fan out over the streams.
+  const int groups[2][5] = {{0, 1, -1, -1, -1}, {2, 3, 4, 5, 6}};
+  int holder[2] = {-1, -1};
+  for (int gi = 0; gi < 2; gi++) {   // both sorts first (main stream), then the bucket phases fan out
+    for (int q = 0; q < 5; q++)
+      if (groups[gi][q] >= 0 && pk->g[groups[gi][q]]) { holder[gi] = groups[gi][q]; break; }
+    if (holder[gi] < 0) continue;
+    const Fr* sc = gi == 0 ? dw + l1 : dw;
+    const size_t cnt = gi == 0 ? m - l1 : m;
+    if ((rc = msm_sort(pk->g[holder[gi]]->sort, pk->g[holder[gi]]->sh, sc, cnt, 0, st))) return rc;
+    EV_REC(e_sorted[gi], st);
+  }
+  for (int gi = 1; gi >= 0; gi--) {   // the larger group first
+    if (holder[gi] < 0) continue;
+    const size_t cnt = gi == 0 ? m - l1 : m;
+    SortScratch& ss = pk->g[holder[gi]]->sort;
+    for (int q = 0; q < 5; q++) {
+      int k = groups[gi][q];
+      if (k < 0 || !pk->g[k]) continue;
+      cudaStream_t sk = st;
+      if (!(gi == 1 && k == holder[1])) {   // one bucket phase stays on the main stream, the others rotate over the side streams
+        int si = next_side++ % 3;
+        sk = side[si];
+        used[si] = true;
+        EV_WAIT(sk, e_sorted[gi]);
+      }
+      if (k == 2) rc = msm_buckets<Fq2>(pk->g[2].get(), ss, cnt, reinterpret_cast<XYZZ<Fq2>*>(res + 256 * 7), sk);
+      else rc = msm_buckets<Fq>(pk->g[k].get(), ss, cnt, slot_g1(k), sk);
+      if (rc) return rc;
+    }
+  }
+  for (int si = 0; si < 3; si++)
+    if (used[si]) {
+      EV_REC(e_done[si], side[si]);
+      EV_WAIT(st, e_done[si]);
+    }
+  if (d_rec_out) {
+    CU(cudaMemcpyAsync(d_rec_out, res, kPinRecordBytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaGetLastError());
+    return B200_OK;
+  }
   Fq* o = pk->out_std.as<Fq>();
-  k_pinocchio_finalize<<<1, 64, 0, st>>>(res, o, reinterpret_cast<Fq2*>(o + 21));
+  if (gather) {
+    CU(pk->gather.ensure(kPinRecordBytes * (size_t)pk->world));
+    ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPinRecordBytes, ncclUint8, g_comm.comm, st);
+    if (nrc != ncclSuccess) return fail(B200_ECOMM, "ncclAllGather: %s", g_comm.api.GetErrorString(nrc));
+    k_pinocchio_gather_finalize<<<1, 64, 0, st>>>(pk->gather.as<uint8_t>(), pk->world, o, reinterpret_cast<Fq2*>(o + 21));
+  } else {
+    k_pinocchio_finalize<<<1, 64, 0, st>>>(res, o, reinterpret_cast<Fq2*>(o + 21));
+  }
   CU(cudaGetLastError());
   uint64_t host_out[(21 + 6) * 4];
   CU(cudaMemcpyAsync(host_out, o, sizeof host_out, cudaMemcpyDeviceToHost, st));
   rc = check_err_flag<Fr>("pinocchio_prove");
+  if (rc) return rc;
+  memcpy(out_g1, host_out, 84 * 8);
+  memcpy(pi_b, host_out + 84, 24 * 8);
+  return B200_OK;
+}
+
+// one-GPU emulation of the collective: sum `world` gathered records (device) -> the proof (host)
+int pinocchio_finalize_records(const uint8_t* d_recs, int world, uint64_t* out_g1, uint64_t* pi_b) {
+  if (!d_recs || world < 1 || !out_g1 || !pi_b) return fail(B200_EINVAL, "pinocchio_finalize: bad arguments");
+  DevBuf o;
+  CU(o.alloc(64 * sizeof(Fq)));
+  k_pinocchio_gather_finalize<<<1, 64, 0, g_stream>>>(d_recs, world, o.as<Fq>(), reinterpret_cast<Fq2*>(o.as<Fq>() + 21));
+  CU(cudaGetLastError());
+  uint64_t host_out[(21 + 6) * 4];
+  CU(cudaMemcpyAsync(host_out, o.p, sizeof host_out, cudaMemcpyDeviceToHost, g_stream));
+  int rc = check_err_flag<Fr>("pinocchio_finalize");
   if (rc) return rc;
   memcpy(out_g1, host_out, 84 * 8);
   memcpy(pi_b, host_out + 84, 24 * 8);

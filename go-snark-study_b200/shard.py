@@ -7,11 +7,15 @@ holds whole MSMs where it can and index ranges where it must.  A set's blinding 
 (alpha/beta/delta tails) belong to the rank that holds the set's last element.
 """
 
-WEIGHTS = (1.0, 1.0, 2.8, 1.0)     # A, B1, B2 (G2), C||PTD
+def weights(world):
+    """A, B1, B2 (G2), C||PTD: a G2 term costs 2.8 G1 terms on the batched-affine kernels, 3.6 on the XYZZ kernels that the
+    small shards of an 8-way split use (measured, profiles/r2_notes.md)."""
+    return (1.0, 1.0, 3.6 if world >= 8 else 2.8, 1.0)
 
 
 def shard_ranges(m, npublic, n_ptd, rank, world):
     assert world >= 1 and 0 <= rank < world
+    WEIGHTS = weights(world)
     n_c_full = m - npublic - 1
     lens = (m, m, m, n_c_full + n_ptd)
     off = [0.0]

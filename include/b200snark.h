@@ -177,6 +177,19 @@ int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t
  * order PiA, PiAp, PiBp, PiC, PiCp, PiH, PiKp (84 u64); pi_b = PiB (G2).           */
 int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                          uint64_t* out_g1, uint64_t pi_b[24]);
+/* Multi-GPU Pinocchio: the eight MSMs of snark.GenerateProofs are independent, so rank `rank` of `world` keeps WHOLE MSMs
+ * (dealt greedily by cost, identically on every rank; no MSM is split).  With a communicator (b200_comm_init)
+ * b200_pinocchio_prove on such a key computes the rank's MSMs, all-gathers the 2 KB result records and returns the whole
+ * proof on every rank.  Without one, b200_pinocchio_prove_record_device leaves the rank's record (8 XYZZ slots, 256 B
+ * each, device memory) to the caller and b200_pinocchio_finalize_records sums `world` gathered records — how the
+ * one-GPU tests emulate N ranks.                                                                                      */
+int b200_pinocchio_pk_load_shard(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
+                                 const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
+                                 const uint64_t* g1t, size_t n_g1t, const uint64_t* z, size_t nz, size_t npublic,
+                                 int window_bits, int rank, int world, b200_pk_t* out);
+int b200_pinocchio_prove_record_device(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
+                                       void* d_record);
+int b200_pinocchio_finalize_records(const void* d_records, int world, uint64_t* out_g1, uint64_t pi_b[24]);
 int b200_pk_free(b200_pk_t pk);
 
 /* ---- instrumentation (bench.py) -------------------------------------------- */

@@ -78,3 +78,49 @@ def test_synthetic_matches_oracle_prove():
     ea, eb, ec = syn.expected_dlogs()
     assert G1.affine(ref["PiA"]) == G1.affine(G1.mul_scalar(G1.G, ea))
     assert G1.affine(ref["PiC"]) == G1.affine(G1.mul_scalar(G1.G, ec))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pinocchio_sharded_equals_go_binary(golden_dir, world):
+    """Sharded Pinocchio keys (whole MSMs dealt to the ranks, b200_pinocchio_pk_load_shard): every rank's 2 KB record,
+    concatenated as the NCCL all-gather would and summed by b200_pinocchio_finalize_records, reproduces the Go binary's
+    proof (snark.go:254-289) on affine coordinates; the host-pointer call refuses a sharded key without a communicator."""
+    import json
+    import os
+    import torch
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+    from gosnark_b200.bn128 import R, _flatten_g1, _flatten_g2, _unflatten_g1, _unflatten_g2, reduce_scalar
+    from tests.test_gpu_prove import pinocchio_pk
+    _lib.init()
+    L = lib()
+    with open(os.path.join(golden_dir, "gobin_chain21.json")) as f:
+        g = json.load(f)
+    cc = g["compiledcircuit"]
+    pk = pinocchio_pk(g["pinocchio_setup"])
+    m, npub = cc["NVars"], cc["NPublic"]
+    arr = {k: _flatten_g1(pk[k][:m]) for k in ("A", "Ap", "Bp", "C", "Cp", "Kp")}
+    b2, g1t = _flatten_g2(pk["B"][:m]), _flatten_g1(pk["G1T"])
+    z = ints_to_limbs([int(x) % R for x in pk["Z"]])
+    w = ints_to_limbs([reduce_scalar(x) for x in g["witness"]])
+    px = ints_to_limbs([int(x) % R for x in g["px"]])
+    recs = torch.zeros(256 * world, dtype=torch.int64, device="cuda")          # world x 2 KB
+    handles = []
+    for rk in range(world):
+        h = _lib._h(0)
+        check(L.b200_pinocchio_pk_load_shard(ptr(arr["A"]), ptr(arr["Ap"]), ptr(b2), ptr(arr["Bp"]), ptr(arr["C"]), ptr(arr["Cp"]),
+                                             ptr(arr["Kp"]), m, ptr(g1t), len(pk["G1T"]), ptr(z), len(pk["Z"]), npub, 0, rk, world, h))
+        handles.append(h.value)
+        check(L.b200_pinocchio_prove_record_device(h.value, ptr(w), m, ptr(px), px.shape[0], recs[256 * rk:].data_ptr()))
+    out_g1, out_b = np.zeros(84, dtype=np.uint64), np.zeros(24, dtype=np.uint64)
+    check(L.b200_pinocchio_finalize_records(recs.data_ptr(), world, ptr(out_g1), ptr(out_b)))
+    proof = dict(zip(("PiA", "PiAp", "PiBp", "PiC", "PiCp", "PiH", "PiKp"), _unflatten_g1(out_g1)))
+    proof["PiB"] = _unflatten_g2(out_b)[0]
+    ref = g["pinocchio_proofs"]
+    for k in ("PiA", "PiAp", "PiBp", "PiC", "PiCp", "PiH", "PiKp"):
+        assert o.BN.G1.affine(proof[k]) == o.BN.G1.affine(tuple(ref[k])), k
+    assert o.BN.G2.affine(proof["PiB"]) == o.BN.G2.affine(tuple(tuple(c) for c in ref["PiB"]))
+    with pytest.raises(_lib.B200Error):          # no communicator: the host-pointer call cannot finish a sharded proof
+        check(L.b200_pinocchio_prove(handles[0], ptr(w), m, ptr(px), px.shape[0], ptr(out_g1), ptr(out_b)))
+    for h in handles:
+        check(L.b200_pk_free(h))
