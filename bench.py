@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / side measurements")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device-resident steps (ncu --profile-from-start off)")
+    ap.add_argument("--acc-mode", type=int, default=None, choices=[0, 1, 2], help="A/B: bucket accumulation auto / batched affine / XYZZ")
     ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1, 2], help="A/B: staged backward pass off / all rounds / rounds >= 2")
     return ap.parse_args()
 
@@ -290,6 +291,8 @@ def setup_dist(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", c.local))
     _lib.init(c.local)
     c.L = _lib.lib()
+    if args.acc_mode is not None:
+        _lib.check(c.L.b200_config(_lib.CFG_ACC_MODE, args.acc_mode))
     if args.tma_staging is not None:
         _lib.check(c.L.b200_config(_lib.CFG_TMA_STAGING, args.tma_staging))
     c.stream = torch.cuda.Stream()

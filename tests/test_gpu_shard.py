@@ -91,7 +91,15 @@ def test_pinocchio_sharded_equals_go_binary(golden_dir, world):
     from gosnark_b200 import _lib
     from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
     from gosnark_b200.bn128 import R, _flatten_g1, _flatten_g2, _unflatten_g1, _unflatten_g2, reduce_scalar
-    from tests.test_gpu_prove import pinocchio_pk
+    def t3(p):
+        return tuple(p)
+
+    def pinocchio_pk(setup):
+        pk = {k: [t3(p) for p in setup["Pk"][k]] for k in ("A", "C", "Kp", "Ap", "Bp", "Cp")}
+        pk["B"] = [tuple(tuple(c) for c in p) for p in setup["Pk"]["B"]]
+        pk["Z"] = setup["Pk"]["Z"]
+        pk["G1T"] = [t3(p) for p in setup["G1T"]]
+        return pk
     _lib.init()
     L = lib()
     with open(os.path.join(golden_dir, "gobin_chain21.json")) as f:
