@@ -43,6 +43,8 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 // b200_config: bucket-accumulation kernel of base sets / proving keys created afterwards
 // (0 auto: batched affine where the bucket population and the shard size amortise its rounds, else XYZZ; 1, 2 force)
 int g_acc_mode = 0;
+// partition tuning (b200_config keys 10..13; defaults = the measured best, profiles/r2_notes.md §8)
+int g_w_ab = 100, g_w_g2 = 280, g_aff_min_g1 = 700000, g_aff_min_g2 = 200000;
 int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
@@ -1167,6 +1169,10 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
+    return B200_OK;
+  }
+  if (key >= 10 && key <= 13 && value > 0) {   // shard-partition tuning (tools/shard_times.py sweeps them)
+    (key == 10 ? g_w_ab : key == 11 ? g_w_g2 : key == 12 ? g_aff_min_g1 : g_aff_min_g2) = value;
     return B200_OK;
   }
   if (key == B200_CFG_TMA_STAGING && value >= 0 && value <= 2) {

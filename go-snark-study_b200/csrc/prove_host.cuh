@@ -159,9 +159,10 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   const size_t l1 = npublic + 1;
   const size_t n_c_full = pk->n_c_full = m - l1;
   const size_t len[4] = {m, m, m, n_c_full + n_ptd};
-  // cost of a G2 term in G1 terms: 2.3-2.4 measured on the batched-affine kernels at the shard sizes of 1-4 ranks, 3.6 on the
-  // XYZZ kernels an 8-way split falls back to (profiles/r2_notes.md: per-rank phase times)
-  const double wgt[4] = {1.0, 1.0, world >= 8 ? 3.6 : 2.8, 1.0};
+  // Cost weights of the line partition, in G1 terms of the C||PTD set: a G2 term (B2), and a term of A / B1 — whose ranks
+  // also pay the two GLV products s*A_part + r*B1_part (1 ms of single-warp latency) on their critical path when sharded.
+  const double w_ab = world > 1 ? g_w_ab / 100.0 : 1.0;
+  const double wgt[4] = {w_ab, w_ab, g_w_g2 / 100.0, 1.0};
   double off[5] = {0, 0, 0, 0, 0};
   for (int k = 0; k < 4; k++) off[k + 1] = off[k] + wgt[k] * (double)len[k];
   auto cut = [&](int g, int k) -> size_t {   // first index of set k at or after the g-th cut of the line
@@ -179,39 +180,36 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   }
   // a set whose end falls exactly on a cut: the rank holding its last element owns the tail (checked above);
   // if no rank holds elements of it (len == 0) the last rank does.
+  // Accumulation kernel per SET of this rank (measured stand-alone, profiles/r2_notes.md §8): G2 sets win with the
+  // batched-affine tree from ~2^18 terms (3.82 vs 4.21 ms at 2^18, 5.20 vs 6.54 at 2^19), G1 sets from ~2^19.5 (2.53 vs 2.45 ms
+  // at 2^19, 3.96 vs 4.12 at 2^20).  A single-GPU key always takes the affine tree: its four MSMs cover each other's gaps.
+  auto set_terms = [&](int k) { return (double)(pk->hi[k] - pk->lo[k]); };
+  auto affine_for = [&](int k) { return world == 1 || set_terms(k) >= (double)(k == 2 ? g_aff_min_g2 : g_aff_min_g1); };
   // sets that consume identical scalar slices share one digit sort
   for (int k = 1; k < 3; k++)
     for (int j = 0; j < k; j++)
-      if (pk->sort_src[k] == k && pk->lo[k] == pk->lo[j] && pk->hi[k] == pk->hi[j] && pk->tail[k] == pk->tail[j] &&
+      if (pk->sort_src[k] == k && pk->lo[k] == pk->lo[j] && pk->hi[k] == pk->hi[j] && pk->tail[k] == pk->tail[j] && affine_for(k) == affine_for(j) &&
           (pk->lo[k] < pk->hi[k] || pk->tail[k]))
         pk->sort_src[k] = pk->sort_src[j];
-  // Accumulation kernel per rank: the batched-affine tree pays off when the rank has enough overlapping work to
-  // cover its per-round inversion gaps; a rank left with one or two small MSMs (4+ GPUs at 2^20) is faster with
-  // the XYZZ kernel (measured per-rank maxima at 2^20, XYZZ vs affine: N=8 5.06 vs 5.89 ms, N=4 8.12 vs 7.40,
-  // N=2 14.5 vs 11.4 -- profiles/r1_notes.md); the threshold sits between the N=4 and N=8 shares.
-  double weighted_terms = 0;
-  for (int k = 0; k < 4; k++) weighted_terms += wgt[k] * (double)(pk->hi[k] - pk->lo[k]);
-  const double min_terms = 1.3e6;
-  const bool affine_ok = weighted_terms >= min_terms;
   static const uint64_t inf1[12] = {0}, inf2[24] = {0};
   auto has = [&](int k) { return pk->lo[k] < pk->hi[k] || pk->tail[k]; };
   if (has(0)) {
     PointCat cat(12);
     cat.add(at + 12 * pk->lo[0], pk->hi[0] - pk->lo[0]);
     if (pk->tail[0]) { cat.add(alpha1, 1); cat.add(delta1, 1); cat.add(inf1, 1); }
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], affine_ok))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[0], affine_for(0)))) return rc;
   }
   if (has(1)) {
     PointCat cat(12);
     cat.add(b1 + 12 * pk->lo[1], pk->hi[1] - pk->lo[1]);
     if (pk->tail[1]) { cat.add(beta1, 1); cat.add(inf1, 1); cat.add(delta1, 1); }
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], affine_ok))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[1], affine_for(1)))) return rc;
   }
   if (has(2)) {
     PointCat cat(24);
     cat.add(b2 + 24 * pk->lo[2], pk->hi[2] - pk->lo[2]);
     if (pk->tail[2]) { cat.add(beta2, 1); cat.add(inf2, 1); cat.add(delta2, 1); }
-    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], affine_ok))) return rc;
+    if ((rc = bases_create<Fq2>(cat.v.data(), cat.count(), c, 2, pk->g[2], affine_for(2)))) return rc;
   }
   if (has(3)) {
     PointCat cat(12);
@@ -221,7 +219,7 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
     cat.add(bacdelta + 12 * (l1 + c_lo), c_hi - c_lo);
     cat.add(ptd + 12 * p_lo, p_hi - p_lo);
     if (pk->tail[3]) cat.add(delta1, 1);
-    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], affine_ok))) return rc;
+    if ((rc = bases_create<Fq>(cat.v.data(), cat.count(), c, 1, pk->g[3], affine_for(3)))) return rc;
   }
   CU(pk->s3.alloc((m + n_ptd + 4) * sizeof(Fr)));
   CU(pk->s4.alloc((m + 4) * sizeof(Fr)));

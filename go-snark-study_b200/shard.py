@@ -7,10 +7,13 @@ holds whole MSMs where it can and index ranges where it must.  A set's blinding 
 (alpha/beta/delta tails) belong to the rank that holds the set's last element.
 """
 
+W_AB, W_G2 = 1.0, 2.8          # mirror of g_w_ab / g_w_g2 (csrc/capi.cu)
+
+
 def weights(world):
-    """A, B1, B2 (G2), C||PTD: a G2 term costs 2.8 G1 terms on the batched-affine kernels, 3.6 on the XYZZ kernels that the
-    small shards of an 8-way split use (measured, profiles/r2_notes.md)."""
-    return (1.0, 1.0, 3.6 if world >= 8 else 2.8, 1.0)
+    """A, B1, B2 (G2), C||PTD in G1 terms of the C||PTD set (csrc/prove_host.cuh: groth16_pk_load)."""
+    w_ab = W_AB if world > 1 else 1.0
+    return (w_ab, w_ab, W_G2, 1.0)
 
 
 def shard_ranges(m, npublic, n_ptd, rank, world):

@@ -14,6 +14,15 @@ logn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 _lib.init(0)
 L = lib()
+# optional tuning: key=value pairs for b200_config (10 w_ab x100, 11 w_g2 x100, 12 affine min G1 terms, 13 affine min G2 terms)
+from gosnark_b200 import shard as _shard
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    check(L.b200_config(int(k), int(v)))
+    if int(k) == 10:
+        _shard.W_AB = int(v) / 100.0
+    if int(k) == 11:
+        _shard.W_G2 = int(v) / 100.0
 syn = SyntheticGroth16(logn)
 r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
 d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
@@ -34,5 +43,9 @@ for rk in range(world):
     torch.cuda.synchronize()
     sh = shard_ranges(syn.m, syn.npublic, syn.n_ptd, rk, world)
     desc = " ".join(f"{n}[{s['lo']}:{s['hi']}{'+t' if s['tail'] else ''}]" for n, s in zip("A B1 B2 CH".split(), sh["sets"]) if s["lo"] < s["hi"] or s["tail"])
-    print(f"rank {rk}/{world}: {e0.elapsed_time(e1)/5:.3f} ms   {desc}")
+    ms = e0.elapsed_time(e1) / 5
+    times = globals().setdefault("times", [])
+    times.append(ms)
+    print(f"rank {rk}/{world}: {ms:.3f} ms   {desc}")
     check(L.b200_pk_free(pk))
+print(f"config {sys.argv[3:]}: slowest rank {max(times):.3f} ms, mean {sum(times)/len(times):.3f} ms")
