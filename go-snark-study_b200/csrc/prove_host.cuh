@@ -180,9 +180,11 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   }
   // a set whose end falls exactly on a cut: the rank holding its last element owns the tail (checked above);
   // if no rank holds elements of it (len == 0) the last rank does.
-  // Accumulation kernel per SET of this rank (measured stand-alone, profiles/r2_notes.md §8): G2 sets win with the
-  // batched-affine tree from ~2^18 terms (3.82 vs 4.21 ms at 2^18, 5.20 vs 6.54 at 2^19), G1 sets from ~2^19.5 (2.53 vs 2.45 ms
-  // at 2^19, 3.96 vs 4.12 at 2^20).  A single-GPU key always takes the affine tree: its four MSMs cover each other's gaps.
+  // Accumulation kernel per SET of this rank (profiles/r2_notes.md §8).  Stand-alone, G2 sets win with the batched-affine
+  // tree from 2^18 terms (3.82 vs 4.21 ms; 5.20 vs 6.54 at 2^19) and G1 sets from ~2^19.5 (2.53 vs 2.45 ms at 2^19, 3.96 vs 4.12
+  // at 2^20); inside a sharded proof a 318 k-term G2 shard was still faster on the XYZZ kernel (4.81 vs 5.69 ms per rank), a
+  // 524 k-term one on the affine tree — hence 4e5 / 7e5.  A single-GPU key always takes the affine tree: its four MSMs cover
+  // each other's gaps.
   auto set_terms = [&](int k) { return (double)(pk->hi[k] - pk->lo[k]); };
   auto affine_for = [&](int k) { return world == 1 || set_terms(k) >= (double)(k == 2 ? g_aff_min_g2 : g_aff_min_g1); };
   // sets that consume identical scalar slices share one digit sort
@@ -276,39 +278,46 @@ __device__ Jacobian<Fq> jac_add_complete(const Jacobian<Fq>& a, const Jacobian<F
   return r;
 }
 
-// One warp: lanes 0..3 -> prod[0] = s*A, lanes 4..7 -> prod[1] = r*B1; res layout as in k_groth16_finalize.
+// One warp, all 32 lanes: lanes 0..15 -> prod[0] = s*A, lanes 16..31 -> prod[1] = r*B1 (res layout as in k_groth16_finalize).
+// Inside a product, lanes 0..7 take the eight 16-bit chunks of |k1| on P and lanes 8..15 those of |k2| on phi(P): a chunk is
+// 16 doublings + <= 16 additions, lane q then shifts by 16 q doublings, and a 3-level shuffle tree + one addition join the
+// sixteen partial products.  Depth: 128 Jacobian doublings + ~12 additions (the doublings are the floor of any
+// double-and-add on a 128-bit GLV half), against 128 + ~36 with four 64-bit chunks.
 __global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* prod) {
-  uint32_t t = threadIdx.x;
-  if (t >= 32) return;
-  uint32_t grp = (t >> 2) & 1, lane4 = t & 3, base_lane = t & ~3u;
-  bool active = t < 8;
+  const uint32_t t = threadIdx.x & 31u;
+  const uint32_t grp = t >> 4, half = (t >> 3) & 1u, q = t & 7u;
   Jacobian<Fq> p = xyzz_to_jacobian(*reinterpret_cast<const XYZZ<Fq>*>(res + (grp ? 256 : 0)));
-  if (lane4 >= 2) {  // phi(P): x -> beta * x
+  if (half) {  // phi(P): x -> beta * x
     Fq beta;
     const uint32_t bm[8] = {0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu, 0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du};
 #pragma unroll
     for (int i = 0; i < 8; i++) beta.l[i] = bm[i];
     p.X = p.X * beta;
   }
-  if (g.neg[grp][lane4 >> 1]) p.Y = p.Y.neg();
-  uint64_t chunk = active ? g.k[grp][lane4] : 0;
+  if (g.neg[grp][half]) p.Y = p.Y.neg();
+  const uint64_t word = g.k[grp][2 * half + (q >> 2)];
+  const uint32_t chunk = (uint32_t)(word >> (16 * (q & 3u))) & 0xffffu;
   Jacobian<Fq> r = Jacobian<Fq>::inf();
   bool started = false;
-  for (int b = 63; b >= 0; b--) {
-    uint32_t bit = (uint32_t)(chunk >> b) & 1;
+  for (int b = 15; b >= 0; b--) {
+    uint32_t bit = (chunk >> b) & 1u;
     if (!started && !bit) continue;
     started = true;
     r = jac_double_ref(r);
     if (bit) r = jac_add_ref(r, p);   // r = m*p with m >= 2 or infinity: never equal to +-p
   }
-  if (lane4 & 1)
-    for (int d = 0; d < 64; d++) r = jac_double_ref(r);   // high chunks: * 2^64
-  Jacobian<Fq> hi = shfl_jac(r, base_lane + (lane4 | 1));
-  if ((lane4 & 1) == 0) r = jac_add_complete(r, hi);      // lanes 0, 2: |k1|*P , |k2|*phi(P)
-  Jacobian<Fq> other = shfl_jac(r, base_lane + 2);
-  if (lane4 == 0) {
-    r = jac_add_complete(r, other);
-    if (active) prod[grp] = jacobian_to_xyzz(r);
+  if (started)
+    for (uint32_t d = 0; d < 16 * q; d++) r = jac_double_ref(r);   // * 2^(16 q)
+  const uint32_t base8 = t & ~7u;
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) {
+    Jacobian<Fq> other = shfl_jac(r, (int)(base8 + ((q + off) & 7u)));
+    if ((int)q < off) r = jac_add_complete(r, other);
+  }
+  Jacobian<Fq> k2part = shfl_jac(r, (int)((t & ~15u) + 8));
+  if ((t & 15u) == 0) {
+    r = jac_add_complete(r, k2part);
+    prod[grp] = jacobian_to_xyzz(r);
   }
 }
 __global__ void k_groth16_combine(const uint8_t* res, const XYZZ<Fq>* prod, Fq* out_a, Fq* out_c, Fq2* out_b) {
@@ -506,7 +515,12 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   GlvScalars glv;
   if (glv_decompose(fr_s, glv.k[0], glv.neg[0]) || glv_decompose(fr_r, glv.k[1], glv.neg[1]))
     return fail(B200_EINVAL, "groth16_prove: GLV decomposition out of range");
-  k_groth16_products<<<1, 32, 0, s1>>>(res, glv, prod);
+  if (pk->g[0] || pk->g[1]) {
+    k_groth16_products<<<1, 32, 0, s1>>>(res, glv, prod);
+  } else {   // a rank that holds no part of A or B1: both products are the point at infinity (all-zero XYZZ) — skip the
+    // 1 ms single-warp chain (it sat on the critical path of 5 of the 8 ranks of an 8-way proof)
+    CU(cudaMemsetAsync(prod, 0, 2 * sizeof(XYZZ<Fq>), s1));
+  }
   EV_REC(e_prod, s1);
   EV_WAIT(st, e_prod);
   EV_WAIT(st, e_b2);
