@@ -923,6 +923,12 @@ int group_op_host(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64
 
 }  // namespace
 
+// On an error return, work already queued on the library's streams is drained first: no entry point leaves kernels in
+// flight that still read the caller's (or the library's soon-to-be-reused) buffers.
+inline int drain_on_error(int rc) {
+  if (rc != B200_OK && g_init) cudaDeviceSynchronize();
+  return rc;
+}
 extern "C" {
 
 int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, const uint64_t* bacdelta,
@@ -951,15 +957,15 @@ int b200_groth16_finalize_device(b200_pk_t pk, const void* d_parts, int nparts, 
   NEED_INIT();
   ProvingKey* p = find_pk(pk, 1);
   if (!p || !d_parts || nparts < 1 || !r || !s || !d_out) return fail(B200_EINVAL, "groth16_finalize_device: bad arguments");
-  return groth16_finalize_enqueue(p, (const uint8_t*)d_parts, nparts, r, s, (Fq*)d_out,
-                                  stream ? (cudaStream_t)stream : g_stream);
+  return drain_on_error(groth16_finalize_enqueue(p, (const uint8_t*)d_parts, nparts, r, s, (Fq*)d_out,
+                                  stream ? (cudaStream_t)stream : g_stream));
 }
 int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                        const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
                        uint64_t pi_c[12]) {
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();
-  return groth16_prove(pk, w, nw, px, npx, r, s, pi_a, pi_b, pi_c);
+  return drain_on_error(groth16_prove(pk, w, nw, px, npx, r, s, pi_a, pi_b, pi_c));
 }
 int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
                            const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
@@ -994,7 +1000,7 @@ int b200_pinocchio_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint6
                          uint64_t* out_g1 /* 7 x 12: PiA PiAp PiBp PiC PiCp PiH PiKp */, uint64_t pi_b[24]) {
   std::lock_guard<std::mutex> lk(g_mu);
   NEED_INIT();
-  return pinocchio_prove(pk, w, nw, px, npx, out_g1, pi_b);
+  return drain_on_error(pinocchio_prove(pk, w, nw, px, npx, out_g1, pi_b));
 }
 int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const void* d_px, size_t npx,
                               const uint64_t r[4], const uint64_t s[4], void* d_out, void* stream) {
@@ -1002,8 +1008,8 @@ int b200_groth16_prove_device(b200_pk_t pk, const void* d_w, size_t nw, const vo
   NEED_INIT();
   ProvingKey* p = find_pk(pk, 1);
   if (!p || !d_w || !d_px || !r || !s || !d_out) return fail(B200_EINVAL, "groth16_prove_device: bad arguments");
-  return groth16_enqueue(p, (const Fr*)d_w, nw, (const Fr*)d_px, npx, r, s, (Fq*)d_out,
-                         stream ? (cudaStream_t)stream : g_stream);
+  return drain_on_error(groth16_enqueue(p, (const Fr*)d_w, nw, (const Fr*)d_px, npx, r, s, (Fq*)d_out,
+                         stream ? (cudaStream_t)stream : g_stream));
 }
 int b200_comm_unique_id(uint8_t out[128]) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -1097,7 +1103,7 @@ int b200_pk_free(b200_pk_t pk) {
 #define B200_API_BODY(expr)              \
   std::lock_guard<std::mutex> lk(g_mu);  \
   NEED_INIT();                           \
-  return expr;
+  return drain_on_error(expr);
 int b200_r1cs_to_qap(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, size_t m, uint64_t* alphas,
                      uint64_t* betas, uint64_t* gammas, uint64_t* z) {
   B200_API_BODY(r1cs_to_qap_host(a, b, c, n, m, alphas, betas, gammas, z))
