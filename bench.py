@@ -225,7 +225,7 @@ def metric_of(workload):
 
 
 def default_logn(workload):
-    return {"prove": 20, "g1msm": 20, "g2msm": 22, "verify": 12}[workload]
+    return {"prove": 20, "g1msm": 20, "g2msm": 22, "verify": 16}[workload]
 
 
 def make_config(args, logn, world):

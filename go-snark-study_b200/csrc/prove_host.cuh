@@ -419,7 +419,9 @@ inline int glv_decompose(const Fr& k_std, uint64_t out[4], uint32_t neg[2]) {
 // form).  d_out receives PiA (3 Fq) | PiC (3 Fq) | PiB (3 Fq2) in standard form
 // (or, for a sharded key, the 1 KB partial record).  No host synchronisation.
 int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, size_t npx, const uint64_t* r,
-                    const uint64_t* s, Fq* d_out, cudaStream_t st, int px_mont = 0) {
+                    const uint64_t* s, Fq* d_out, cudaStream_t st, int px_mont = 0, const Fr* d_h_std = nullptr) {
+  // d_h_std != nullptr: the quotient h (npx - len(Z) + 1 coefficients, standard form, device) is supplied by the caller
+  // (witness path: qap_h_enqueue on side stream 3) and the division is skipped; d_px is then unused.
   size_t m = pk->m;
   if (nw != m) return fail(B200_EINVAL, "groth16_prove: witness length %zu != NVars %zu", nw, m);
   if (npx < pk->Z.nb) return fail(B200_EINVAL, "groth16_prove: len(px) < len(Z)");
@@ -474,7 +476,8 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
       bool direct = p_lo == 0 && nq <= n_p;
       Fr* h_dst = direct ? sCH + n_c : pk->h_full.as<Fr>();
       if (!direct && !pk->h_full.p) CU(pk->h_full.alloc((pk->m + pk->n_h_bases + 4) * sizeof(Fr)));
-      CU(poly_div_device(*g_poly, pk->Z, d_px, npx, px_mont, h_dst, nullptr, g_d_err, s3));
+      if (d_h_std) CU(cudaMemcpyAsync(h_dst, d_h_std, nq * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
+      else CU(poly_div_device(*g_poly, pk->Z, d_px, npx, px_mont, h_dst, nullptr, g_d_err, s3));
       size_t have = nq > p_lo ? (nq < p_hi ? nq - p_lo : n_p) : 0;   // valid h coefficients inside [p_lo, p_hi)
       if (!direct && have)
         CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + p_lo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));

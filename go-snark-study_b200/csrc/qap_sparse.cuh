@@ -22,6 +22,7 @@
 //
 // Included by capi.cu only.
 #pragma once
+#include <memory>
 #include <vector>
 
 #include "poly_host.cuh"
@@ -144,13 +145,23 @@ __global__ void k_take(const Fr* __restrict__ src, uint32_t n, uint32_t N, Fr* _
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < N) d[k] = k < n ? src[k] : Fr::zero();
 }
-// leaves of the subproduct tree: t[k] = -(k+1)
-__global__ void k_tree_leaves(Fr* t, uint32_t N) {
+// leaves of the subproduct tree over the points offset+1 .. offset+N: t[k] = -(offset + k + 1)
+__global__ void k_tree_leaves(Fr* t, uint32_t N, uint32_t offset) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N) return;
   Fr v = Fr::zero();
-  v.l[0] = k + 1;
+  v.l[0] = offset + k + 1;
   t[k] = v.to_mont().neg();
+}
+// f[j] = j!  (from the inverse factorials: one inversion per element is avoided by the caller's host table)
+// hv[j] = (Va[Y] * Vb[Y] * Y! - Vc[Y]) * j!   with Y = n + j,  j < n - 1   — the quotient h = (a b - c) / Z at x = Y + 1
+// (a(x) = Va[Y] * Y!, Z(x) = Y! / j!); V* are the three cyclic convolutions d * (1/i!) laid out with stride M.
+__global__ void k_h_values(const Fr* __restrict__ V, uint32_t M, const Fr* __restrict__ fact, uint32_t n, Fr* __restrict__ hv) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j + 1 >= n) return;
+  uint32_t Y = n + j;
+  Fr va = V[Y], vb = V[(size_t)M + Y], vc = V[2 * (size_t)M + Y];
+  hv[j] = (va * vb * fact[Y] - vc) * fact[j];
 }
 // schoolbook level of the tree: tc2[p*2s + i] = sum_{a+b=i} tL[a] tR[b] + (i >= s ? tL[i-s] + tR[i-s] : 0)
 __global__ void k_tree_school(const Fr* __restrict__ tc, uint32_t s, uint32_t N, Fr* __restrict__ tc2) {
@@ -251,28 +262,41 @@ __global__ void k_lagrange_at(const Fr* __restrict__ invfact, uint32_t n, Fr tau
 struct QapDomain {
   size_t N = 0;                 // power of two: Newton coefficients d_0..d_{N-1}
   int logN = 0;
-  DevBuf invfact;               // 1/j!, j <= N (Montgomery)
+  DevBuf invfact;               // 1/j!, j <= nfact (Montgomery)
+  DevBuf fact;                  // j! (only for the h-direct domain)
   DevBuf level[32];             // level l (s = 2^l < N): s < kDcSchool: t coefficients of every node (N elements);
                                 //                        else: transformed, 1/2s-scaled t of the LEFT nodes (N elements)
   DevBuf root;                  // t of the root: prod_{i=1..N}(x - i) - x^N, N coefficients (Montgomery)
 };
 
-inline cudaError_t qap_domain_build(PolyCtx& pc, QapDomain& dom, size_t N, cudaStream_t st) {
+// offset: the tree covers the points offset+1 .. offset+N (0: the QAP domain itself; n: the points n+1.. on which the
+// quotient h is interpolated directly).  nfact: factorial tables up to nfact (>= N); `fact` only when want_fact.
+inline cudaError_t qap_domain_build(PolyCtx& pc, QapDomain& dom, size_t N, cudaStream_t st, size_t offset = 0, size_t nfact = 0,
+                                    bool want_fact = false) {
   dom.N = N;
   dom.logN = ceil_log2(N);
-  // factorial inverses on the host (one-time, O(N) multiplications)
+  if (nfact < N) nfact = N;
+  // factorials and their inverses on the host (one-time, O(nfact) multiplications)
   {
-    std::vector<Fr> inv(N + 1);
+    std::vector<Fr> inv(nfact + 1), fac(want_fact ? nfact + 1 : 1);
     Fr f = Fr::one();
-    for (size_t j = 1; j <= N; j++) f = f * fr_from_u64(j);
+    if (want_fact) fac[0] = f;
+    for (size_t j = 1; j <= nfact; j++) {
+      f = f * fr_from_u64(j);
+      if (want_fact) fac[j] = f;
+    }
     Fr fi = f.inverse_impl();
-    for (size_t j = N; j >= 1; j--) {
+    for (size_t j = nfact; j >= 1; j--) {
       inv[j] = fi;
       fi = fi * fr_from_u64(j);
     }
     inv[0] = Fr::one();
-    PCU(dom.invfact.alloc((N + 1) * sizeof(Fr)));
-    PCU(cudaMemcpyAsync(dom.invfact.p, inv.data(), (N + 1) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    PCU(dom.invfact.alloc((nfact + 1) * sizeof(Fr)));
+    PCU(cudaMemcpyAsync(dom.invfact.p, inv.data(), (nfact + 1) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (want_fact) {
+      PCU(dom.fact.alloc((nfact + 1) * sizeof(Fr)));
+      PCU(cudaMemcpyAsync(dom.fact.p, fac.data(), (nfact + 1) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    }
     PCU(cudaStreamSynchronize(st));
   }
   DevBuf tcA, tcB, Y, W;
@@ -280,7 +304,7 @@ inline cudaError_t qap_domain_build(PolyCtx& pc, QapDomain& dom, size_t N, cudaS
   PCU(tcB.alloc(N * sizeof(Fr)));
   Fr* tc = tcA.as<Fr>();
   Fr* tc2 = tcB.as<Fr>();
-  B200_LAUNCH(k_tree_leaves, nblk(N, 256), 256, st, tc, (uint32_t)N);
+  B200_LAUNCH(k_tree_leaves, nblk(N, 256), 256, st, tc, (uint32_t)N, (uint32_t)offset);
   for (int l = 0; l < dom.logN; l++) {
     uint32_t s = 1u << l;
     PCU(dom.level[l].alloc(N * sizeof(Fr)));
@@ -344,8 +368,9 @@ struct QapWork {
   size_t n_e = 0, N_e = 0;   // E currently holds the series for this (n, N)
 };
 
-inline cudaError_t interpolate_ap(PolyCtx& pc, const QapDomain& dom, QapWork& wk, const Fr* v, size_t stride, size_t n,
-                                  int polys, Fr* out, cudaStream_t st) {
+// Newton coefficients d (polys blocks of N, zero padded) of the values v on n consecutive integer points
+inline cudaError_t newton_coeffs(PolyCtx& pc, const QapDomain& dom, QapWork& wk, const Fr* v, size_t stride, size_t n,
+                                 int polys, Fr* out, cudaStream_t st) {
   const size_t N = dom.N, N2 = 2 * N;
   const int l2 = dom.logN + 1;
   PCU(wk.U.ensure(polys * N2 * sizeof(Fr)));
@@ -370,7 +395,65 @@ inline cudaError_t interpolate_ap(PolyCtx& pc, const QapDomain& dom, QapWork& wk
   for (int q = 0; q < polys; q++)
     B200_LAUNCH(k_take, nblk(N, 256), 256, st, U + q * N2, (uint32_t)n, (uint32_t)N, out + q * N);   // d mod x^n, padded to N
   pc.note(2 * polys + 2);
+  return cudaGetLastError();
+}
+inline cudaError_t interpolate_ap(PolyCtx& pc, const QapDomain& dom, QapWork& wk, const Fr* v, size_t stride, size_t n,
+                                  int polys, Fr* out, cudaStream_t st) {
+  PCU(newton_coeffs(pc, dom, wk, v, stride, n, polys, out, st));
   return newton_to_monomial(pc, dom, out, wk.X.as<Fr>(), polys, st);
+}
+
+// ---- the quotient h = (a b - c) / Z directly from the values of a, b, c on {1..n} ------------------------------------
+// GenerateProofs only consumes px through h = px / Z (groth16.go:266), and h has degree n - 2: instead of three
+// interpolations (a, b, c -> coefficients), one product and one division, evaluate a, b, c on the NEXT n - 1 points
+// n+1 .. 2n-1 from their Newton coefficients (a(1 + Y) / Y! = sum_k d_k / (Y - k)!: one cyclic product with the cached
+// transform of 1/i! each), form h there pointwise — Z(1 + Y) = Y! / (Y - n)! — and interpolate h ONCE over the points
+// n+1 .. 2n-1 (subproduct tree with offset n).  Same field elements as DivisorPolynomial(CombinePolynomials(..)), ~40 % fewer
+// multiplications than going through px.
+struct QapHDomain {
+  size_t n = 0, M = 0;          // constraints; cyclic size of the shift products (2 * pow2 >= n)
+  QapDomain tree;               // points n+1 .. n+N', factorials up to 2n
+  DevBuf G;                     // transform of (1/i!)_{i < 2n-1}, size M, pre-scaled by 1/M
+  QapWork work;                 // e^-x cache etc. of the final interpolation
+  DevBuf V, hv, coef;           // 3 x M shift products; n-1 values of h; N' coefficients
+};
+inline cudaError_t qap_hdomain_build(PolyCtx& pc, QapHDomain& hd, size_t n, cudaStream_t st) {
+  hd.n = n;
+  size_t N0 = 1;
+  while (N0 < n) N0 <<= 1;
+  hd.M = 2 * N0;
+  size_t Np = 1;
+  while (Np < (n > 1 ? n - 1 : 1)) Np <<= 1;
+  PCU(qap_domain_build(pc, hd.tree, Np, st, n, 2 * n, true));
+  PCU(hd.G.alloc(hd.M * sizeof(Fr)));
+  PCU(hd.V.alloc(3 * hd.M * sizeof(Fr)));
+  PCU(hd.hv.alloc(n * sizeof(Fr)));
+  PCU(hd.coef.alloc(Np * sizeof(Fr)));
+  const int lm = ceil_log2(hd.M);
+  NttPlan* pl;
+  PCU(pc.plan(lm, &pl, st));
+  B200_LAUNCH(k_take, nblk(hd.M, 256), 256, st, hd.tree.invfact.as<Fr>(), (uint32_t)(2 * n - 1), (uint32_t)hd.M, hd.G.as<Fr>());
+  PCU(ntt_batched(pc, hd.G.as<Fr>(), lm, hd.M, 0, st));
+  B200_LAUNCH(k_scale, nblk(hd.M, 256), 256, st, hd.G.as<Fr>(), (uint32_t)hd.M, pl->n_inv);
+  PCU(cudaStreamSynchronize(st));
+  return cudaGetLastError();
+}
+// d: Newton coefficients of a | b | c over {1..n} (3 blocks of `dstride`, from newton_coeffs on the QAP domain);
+// h_out: n - 1 coefficients of h (Montgomery) in hd.coef.
+inline cudaError_t qap_h_from_newton(PolyCtx& pc, QapHDomain& hd, const Fr* d, size_t dstride, cudaStream_t st) {
+  const size_t n = hd.n, M = hd.M;
+  const int lm = ceil_log2(M);
+  Fr* V = hd.V.as<Fr>();
+  for (int q = 0; q < 3; q++) B200_LAUNCH(k_take, nblk(M, 256), 256, st, d + q * dstride, (uint32_t)n, (uint32_t)M, V + q * M);
+  PCU(ntt_batched(pc, V, lm, 3 * M, 0, st));
+  B200_LAUNCH(k_dc_pointwise, nblk(3 * M, 256), 256, st, V, hd.G.as<Fr>(), (uint32_t)M, (uint32_t)(3 * M));
+  PCU(ntt_batched(pc, V, lm, 3 * M, 1, st));
+  if (n >= 2) {
+    B200_LAUNCH(k_h_values, nblk(n - 1, 256), 256, st, V, (uint32_t)M, hd.tree.fact.as<Fr>(), (uint32_t)n, hd.hv.as<Fr>());
+    PCU(interpolate_ap(pc, hd.tree, hd.work, hd.hv.as<Fr>(), n - 1, n - 1, 1, hd.coef.as<Fr>(), st));
+  }
+  pc.note(8);
+  return cudaGetLastError();
 }
 
 // ---- a sparse R1CS resident on the device ------------------------------------------------------------------
@@ -385,6 +468,7 @@ struct R1cs {
   DevBuf w_mont, vals, coef, lag;   // witness (m), A w | B w | C w (3 x n), coefficients (3 x N), Lagrange basis at tau (n)
   DevBuf px_mont;                   // 2n - 1
   QapWork work;
+  std::unique_ptr<QapHDomain> hd;   // witness -> h directly (b200_groth16_prove_witness), built on first use
 };
 
 }  // namespace b200

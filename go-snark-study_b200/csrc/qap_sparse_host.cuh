@@ -132,6 +132,35 @@ int qap_px_enqueue(R1cs* r, const Fr* d_w_std, Fr* d_abc_std /* 3 x n or null */
   return B200_OK;
 }
 
+// d_w: m witness values (device, standard form) -> the n - 1 coefficients of h = (ax*bx - cx) / Z in d_h_std (standard form),
+// without forming px (qap_sparse.cuh: QapHDomain).  Requires n >= 2.
+int qap_h_enqueue(R1cs* r, const Fr* d_w_std, Fr* d_h_std, cudaStream_t st) {
+  const size_t n = r->n, m = r->m, N = pow2_at_least(n);
+  if (n < 2) return fail(B200_EINVAL, "qap_h: needs at least 2 constraints");
+  QapDomain* dom;
+  int rc = get_domain(N, &dom);
+  if (rc) return rc;
+  PolyCtx& pc = *g_poly;
+  if (!r->hd) {
+    r->hd = std::make_unique<QapHDomain>();
+    CU(qap_hdomain_build(pc, *r->hd, n, st));
+  }
+  Fr* w = r->w_mont.as<Fr>();
+  k_poly_load<<<nblk(m, 256), 256, 0, st>>>(d_w_std, (uint32_t)m, (uint32_t)m, 0, 0, w, (uint32_t)m, g_d_err);
+  Fr* vals = r->vals.as<Fr>();
+  for (int k = 0; k < 3; k++)
+    k_spmv_csr<<<nblk(n, 128), 128, 0, st>>>(r->M[k].rowptr.as<uint32_t>(), r->M[k].col.as<uint32_t>(), r->M[k].val.as<Fr>(), w,
+                                              (uint32_t)n, vals + k * n);
+  g_launches += 4;
+  Fr* coef = r->coef.as<Fr>();   // here: the Newton coefficients of a | b | c (N-strided)
+  CU(newton_coeffs(pc, *dom, r->work, vals, n, n, 3, coef, st));
+  CU(qap_h_from_newton(pc, *r->hd, coef, N, st));
+  k_poly_store<<<nblk(n - 1, 256), 256, 0, st>>>(r->hd->coef.as<Fr>(), (uint32_t)(n - 1), 0, 1, d_h_std);
+  g_launches += 1;
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
 int qap_px_host(b200_r1cs_t h, const uint64_t* w, size_t nw, uint64_t* ax, uint64_t* bx, uint64_t* cx, uint64_t* px) {
   R1cs* r = find_r1cs(h);
   if (!r) return fail(B200_EINVAL, "qap_px: bad R1CS handle");

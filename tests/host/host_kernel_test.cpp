@@ -493,6 +493,29 @@ int qap_interpolate(const uint32_t* values_std, uint32_t n, uint32_t* coeffs_std
   std::memcpy(coeffs_std, out.data(), (size_t)n * sizeof(Fr));
   return 0;
 }
+// h = (a b - c) / Z straight from the values of a, b, c on {1..n} (qap_sparse.cuh: QapHDomain), as qap_h_enqueue runs it
+int qap_h_direct(const uint32_t* abc_std, uint32_t n, uint32_t* h_std) {
+  size_t N = 1;
+  while (N < n) N <<= 1;
+  QapDomain dom;
+  if (qap_domain_build(poly_ctx(), dom, N, nullptr)) return 1;
+  std::vector<Fr> v(3 * (size_t)n), d(3 * N);
+  std::memcpy(v.data(), abc_std, v.size() * sizeof(Fr));
+  for (auto& x : v) x = x.to_mont();
+  QapWork wk;
+  if (newton_coeffs(poly_ctx(), dom, wk, v.data(), n, n, 3, d.data(), nullptr)) return 2;
+  QapHDomain hd;
+  if (qap_hdomain_build(poly_ctx(), hd, n, nullptr)) return 3;
+  if (qap_h_from_newton(poly_ctx(), hd, d.data(), N, nullptr)) return 4;
+  const Fr* c = hd.coef.as<Fr>();
+  for (uint32_t i = 0; i + 1 < n; i++) {
+    Fr x = c[i].from_mont();
+    std::memcpy(h_std + 8 * (size_t)i, &x, sizeof(Fr));
+  }
+  for (size_t i = n - 1; i < hd.tree.N; i++)
+    if (!c[i].is_zero()) return 5;   // degree <= n - 2
+  return 0;
+}
 int qap_zero_poly(uint32_t n, uint32_t* out_std) {   // prod_{i=1..n}(x - i): Newton basis element n
   size_t N = 1;
   while (N < (size_t)n + 1) N <<= 1;
@@ -527,6 +550,7 @@ int poly_div_orch(const uint32_t* a_std, uint32_t na, const uint32_t* b_std, uin
 extern "C" {
 int t_qap_interpolate(const uint32_t* values_std, uint32_t n, uint32_t* coeffs_std) { return qap_interpolate(values_std, n, coeffs_std); }
 int t_qap_zero_poly(uint32_t n, uint32_t* out_std) { return qap_zero_poly(n, out_std); }
+int t_qap_h_direct(const uint32_t* abc_std, uint32_t n, uint32_t* h_std) { return qap_h_direct(abc_std, n, h_std); }
 int t_poly_div_orch(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* q, uint32_t* rem) {
   return poly_div_orch(a, na, b, nb, q, rem);
 }

@@ -277,6 +277,43 @@ def test_zero_poly_orchestration_on_the_cpu(lib, n):
         assert _horner(z, t) == e
 
 
+@pytest.mark.parametrize("n", [2, 3, 7, 16, 21, 40, 100, 1024, 1500])
+def test_quotient_h_directly_from_the_values(lib, n):
+    """h = DivisorPolynomial(px, Z) (r1csqap.go:213-216; groth16.go:266) without forming px: a, b, c are shifted from
+    {1..n} to n+1..2n-1 in Newton form, h is formed there pointwise and interpolated once over the offset tree
+    (qap_sparse.cuh: QapHDomain).  Equal to the oracle's exact quotient for small n; checked through the identity
+    h(x) Z(x) = a(x) b(x) - c(x) at random points for the larger ones."""
+    rng = random.Random(5000 + n)
+    a = [rng.randrange(R_) for _ in range(n)]
+    b = [rng.randrange(R_) for _ in range(n)]
+    if n > 3:
+        a[1], b[2] = 0, 1
+    c = [x * y % R_ for x, y in zip(a, b)]              # a satisfied R1CS: (a b - c) vanishes on 1..n
+    out = np.zeros(8 * max(n - 1, 1), dtype=np.uint32)
+    assert lib.t_qap_h_direct(_ptr(_u32(a + b + c)), n, _ptr(out)) == 0
+    h = _limbs_to_ints(out, n - 1)
+
+    def interp(v):
+        o_ = np.zeros(8 * n, dtype=np.uint32)
+        assert lib.t_qap_interpolate(_ptr(_u32(v)), n, _ptr(o_)) == 0
+        return _limbs_to_ints(o_, n)
+    if n <= 40:
+        ax, bx, cx = (o.PF.lagrange_interpolation(v) for v in (a, b, c))
+        px = o.PF.sub(o.PF.mul(ax, bx), cx)
+        z = [1]
+        for i in range(1, n + 1):
+            z = o.PF.mul(z, [(-i) % R_, 1])
+        assert h == o.PF.divisor_polynomial(px, z)
+    else:
+        ax, bx, cx = interp(a), interp(b), interp(c)
+        for _ in range(6):
+            t = rng.randrange(R_)
+            zt = 1
+            for i in range(1, n + 1):
+                zt = zt * (t - i) % R_
+            assert _horner(h, t) * zt % R_ == (_horner(ax, t) * _horner(bx, t) - _horner(cx, t)) % R_
+
+
 @pytest.mark.parametrize("na,nb", [(13, 7), (200, 101), (1023, 513), (2600, 1300)])
 def test_division_orchestration_on_the_cpu(lib, na, nb):
     """poly_div_device (poly_host.cuh: Newton inverse series of the reversed divisor, cached transform, fused transform
