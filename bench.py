@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device-resident steps (ncu --profile-from-start off)")
     ap.add_argument("--acc-mode", type=int, default=None, choices=[0, 1, 2], help="A/B: bucket accumulation auto / batched affine / XYZZ")
+    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2],
+                    help="prove workload: independent proofs kept in flight (2 = two proving-key contexts on two streams, the "
+                         "latency chains of one proof overlap the accumulation of the other; 1 = one proof at a time)")
     ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1, 2], help="A/B: staged backward pass off / all rounds / rounds >= 2")
     return ap.parse_args()
 
@@ -317,9 +320,10 @@ def barrier(c):
     c.torch.cuda.synchronize()
 
 
-def timed(c, fn, steps, wall=False, profile=False):
+def timed(c, fn, steps, wall=False, profile=False, extra_streams=()):
     """Device time of `steps` calls bracketed by barrier + synchronize, MAX over ranks.  wall=True for calls that
-    synchronise internally on the library's own stream (the host-pointer C ABI)."""
+    synchronise internally on the library's own stream (the host-pointer C ABI).  extra_streams: further streams `fn`
+    launches on (proofs in flight): they start after the opening event and the closing event waits for them."""
     torch = c.torch
     barrier(c)
     if profile:
@@ -327,8 +331,14 @@ def timed(c, fn, steps, wall=False, profile=False):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(c.stream)
+    for s_ in extra_streams:
+        s_.wait_event(e0)
     for _ in range(steps):
         fn()
+    for s_ in extra_streams:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        c.stream.wait_event(ev)
     e1.record(c.stream)
     torch.cuda.synchronize()
     if profile:
@@ -394,12 +404,25 @@ def run_prove(args, c):
     logn = args.logn if args.logn is not None else 20
     n = 1 << logn
     syn = CircuitGroth16(logn) if args.with_qap else SyntheticGroth16(logn)
-    pk = syn.load_pk(rank, world)
+    # proofs in flight: one proving-key context (own tables, scratch, side streams: B200_CFG_PK_CONTEXT) and one stream each
+    n_fly = 1 if args.with_qap else max(1, args.in_flight)
+    if n_fly > 1 and world > 1:    # latency hidden by the second proof: every shard takes the batched-affine tree (6 vs 10 multiplies per add)
+        check(L.b200_config(_lib.CFG_SHARD_AFFINE_MIN_G1, 1))
+        check(L.b200_config(_lib.CFG_SHARD_AFFINE_MIN_G2, 1))
+    pks = []
+    for k in range(n_fly):
+        check(L.b200_config(_lib.CFG_PK_CONTEXT, k))
+        pks.append(syn.load_pk(rank, world))
+    check(L.b200_config(_lib.CFG_PK_CONTEXT, 0))
+    pk = pks[0]
+    fly_streams = [c.stream] + [torch.cuda.Stream() for _ in range(n_fly - 1)]
     m, npx = syn.m, 2 * n - 1
     r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
     d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
     d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
-    d_out = torch.zeros(48, dtype=torch.int64, device="cuda")
+    d_outs = [torch.zeros(48, dtype=torch.int64, device="cuda") for _ in range(n_fly)]
+    d_out = d_outs[0]
+    torch.cuda.synchronize()
     h_w = torch.from_numpy(syn.w.view(np.int64)).pin_memory()
     h_px = torch.from_numpy(syn.px.view(np.int64)).pin_memory()
     host_out = (np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64))
@@ -407,6 +430,14 @@ def run_prove(args, c):
 
     def step_device():      # with a communicator the all-gather + finalize run inside the call (csrc/prove_host.cuh)
         check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l), d_out.data_ptr(), st))
+
+    fly_ctr = [0]
+
+    def step_in_flight():    # proof k on context k mod n_fly: consecutive proofs overlap (independent keys, streams, outputs)
+        k = fly_ctr[0] % n_fly
+        fly_ctr[0] += 1
+        check(L.b200_groth16_prove_device(pks[k], d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l), d_outs[k].data_ptr(),
+                                          fly_streams[k].cuda_stream))
 
     def step_e2e():          # the reference-facing call: host pointers in, proof out — on every rank
         if qap:
@@ -438,15 +469,17 @@ def run_prove(args, c):
         return (G1o.affine(pa) == G1o.affine(G1o.mul_scalar(G1o.G, ea)) and G2o.affine(pb) == G2o.affine(G2o.mul_scalar(G2o.G, eb))
                 and G1o.affine(pc) == G1o.affine(G1o.mul_scalar(G1o.G, ec)))
 
-    step_device()
+    for _ in range(n_fly):
+        step_in_flight()
     torch.cuda.synchronize()
     step_e2e()
     parity, verified = None, None
     if rank == 0:
-        out = d_out.cpu().numpy().view(np.uint64)
-        pa, pc = _unflatten_g1(out[:24])
-        parity = matches(pa, _unflatten_g2(out[24:])[0], pc) and \
-            matches(_unflatten_g1(host_out[0])[0], _unflatten_g2(host_out[1])[0], _unflatten_g1(host_out[2])[0])
+        parity = matches(_unflatten_g1(host_out[0])[0], _unflatten_g2(host_out[1])[0], _unflatten_g1(host_out[2])[0])
+        for d_o in d_outs:                      # every context's device-resident proof
+            out = d_o.cpu().numpy().view(np.uint64)
+            pa, pc = _unflatten_g1(out[:24])
+            parity = parity and matches(pa, _unflatten_g2(out[24:])[0], pc)
         if not parity:
             print(json.dumps({"error": "proof does not match the known-discrete-log expectation"}))
             return 1
@@ -460,18 +493,21 @@ def run_prove(args, c):
     clocks = ClockSampler(c.local)
     if rank == 0:
         clocks.start()                         # sampled across warm-up + timed region (the region can be < 100 ms)
-    for _ in range(args.warmup):
-        step_device()
+    for _ in range(args.warmup * n_fly):
+        step_in_flight()
+    torch.cuda.synchronize()
     check(L.b200_profile(1))
     prof0 = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof0))          # reset counters
-    ms_total = timed(c, step_device, args.steps, profile=args.profile_region)
+    ms_total = timed(c, step_in_flight, args.steps, profile=args.profile_region, extra_streams=fly_streams[1:])
     prof = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof))
     check(L.b200_profile(0))
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
+    # one proof at a time on one context (the latency of a proof; equals ms_step when n_fly == 1)
+    ms_one = timed(c, step_device, args.steps) / args.steps if n_fly > 1 else ms_step
 
     # ---- exclusive timing of the dominant kernels: the same step with the MSMs serialised on one stream
     # (in the overlapped step above the bucket phases of the four MSMs share the SMs, so their event times overlap)
@@ -490,7 +526,42 @@ def run_prove(args, c):
     # ---- e2e through the host-pointer API (wall clock around the calls: they synchronise internally)
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
-    e2e_ms = timed(c, step_e2e, args.steps, wall=True) / args.steps
+    e2e_one_ms = timed(c, step_e2e, args.steps, wall=True) / args.steps
+    e2e_ms = e2e_one_ms
+    if n_fly > 1:
+        # the same K calls issued by n_fly host threads, thread k proving on context k's key: a call holds the library
+        # mutex while it ENQUEUES and waits for its proof with the mutex released, so the next proof's staging copies and
+        # latency chains overlap this one's accumulation (ctypes drops the GIL for the duration of a call)
+        import threading
+        host_outs = [host_out] + [(np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64))
+                                  for _ in range(n_fly - 1)]
+        errs = []
+
+        def e2e_worker(k, count):
+            try:
+                ho = host_outs[k]
+                for _ in range(count):
+                    check(L.b200_groth16_prove(pks[k], h_w.data_ptr(), m, h_px.data_ptr(), npx, ptr(r_l), ptr(s_l), ptr(ho[0]), ptr(ho[1]),
+                                               ptr(ho[2])))
+            except Exception as e:      # surfaced after the join
+                errs.append(e)
+
+        def e2e_threads(total):
+            ths = [threading.Thread(target=e2e_worker, args=(k, total // n_fly + (1 if k < total % n_fly else 0))) for k in range(n_fly)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errs:
+                raise errs[0]
+
+        e2e_threads(2 * n_fly)                                   # warm-up of every context's host path
+        e2e_ms = timed(c, lambda: e2e_threads(args.steps), 1, wall=True) / args.steps
+        if rank == 0:
+            for ho in host_outs:
+                if not matches(_unflatten_g1(ho[0])[0], _unflatten_g2(ho[1])[0], _unflatten_g1(ho[2])[0]):
+                    print(json.dumps({"error": "a host-pointer proof in flight does not match the known-discrete-log expectation"}))
+                    return 1
 
     # ---- per-rank phase times (exclusive, ms per proof) so the limiter of the 1 -> N curve is visible
     mine = {"rank": rank, "g1_acc_ms": prof_x[0] / ser_steps, "g1_phases": prof_x[1] / ser_steps, "g1_terms": prof_x[2] / ser_steps,
@@ -521,8 +592,13 @@ def run_prove(args, c):
         "scaling": "strong", "vs_baseline": None, "dtype": "u256 (mod q/r)", "data": "synthetic",
         "config": make_config(args, logn, world),
         "constraints_per_sec": value * n, "parity_vs_known_dlog": parity,
+        "proofs_in_flight": n_fly,
+        "one_at_a_time": {"ms_per_step": ms_one, "value": 1e3 / ms_one, "unit": unit,
+                          "note": "the same K steps with ONE proof in flight (device-resident, one context): the latency of a proof; "
+                                  "`value` keeps `proofs_in_flight` independent proofs in flight on as many proving-key contexts"},
         "e2e": {"value": 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 384,
+                "proofs_in_flight": n_fly, "one_at_a_time_ms_per_step": e2e_one_ms,
                 "note": ("b200_groth16_prove_witness: pinned witness in, px computed on the device, proof out" if qap else
                          "the host-pointer C ABI call b200_groth16_prove on every rank (pinned witness and px in, proof out); at N > 1 "
                          "each rank stages only the witness ranges it reads (+ px on ranks holding PowersTauDelta) and the NCCL "
@@ -549,6 +625,7 @@ def run_prove(args, c):
         "algorithmic_bytes_per_proof": syn.algorithmic_bytes(),
         "per_rank": per_rank,
     }
+    line["config"]["proofs_in_flight"] = n_fly
     if args.with_qap:
         line["verified_under_real_vk"] = verified
     if not args.no_extras and world == 1:
@@ -583,13 +660,31 @@ def run_msm(args, c):
     gen = _flatten_g1([G1_GEN]) if group == 1 else _flatten_g2([G2_GEN])
     pts = np.zeros((hi - lo, words), dtype=np.uint64)
     check((L.b200_g1_mul_batch_bcast if group == 1 else L.b200_g2_mul_batch_bcast)(ptr(gen), ptr(ks), hi - lo, ptr(pts)))
-    hb = _lib._h(0)
-    check((L.b200_g1_bases_load if group == 1 else L.b200_g2_bases_load)(ptr(pts), hi - lo, 0, hb))
+    # MSMs in flight: independent base-set objects (own tables and scratch) on their own streams
+    n_fly = max(1, args.in_flight)
+    hbs = []
+    for _ in range(n_fly):
+        h_ = _lib._h(0)
+        check((L.b200_g1_bases_load if group == 1 else L.b200_g2_bases_load)(ptr(pts), hi - lo, 0, h_))
+        hbs.append(h_)
+    hb = hbs[0]
     del pts
     rec = 128 if group == 1 else 256                                     # XYZZ partial record bytes
     d_s = torch.from_numpy(ss.view(np.int64)).cuda()
-    d_part = torch.zeros(rec // 8, dtype=torch.int64, device="cuda")
-    d_all = torch.zeros(rec // 8 * world, dtype=torch.int64, device="cuda")
+    d_parts = [torch.zeros(rec // 8, dtype=torch.int64, device="cuda") for _ in range(n_fly)]
+    d_alls = [torch.zeros(rec // 8 * world, dtype=torch.int64, device="cuda") for _ in range(n_fly)]
+    d_part, d_all = d_parts[0], d_alls[0]
+    fly_streams = [c.stream] + [torch.cuda.Stream() for _ in range(n_fly - 1)]
+    fly_ctr = [0]
+    torch.cuda.synchronize()
+
+    def step_in_flight():
+        k = fly_ctr[0] % n_fly
+        fly_ctr[0] += 1
+        check(L.b200_msm_device(hbs[k].value, d_s.data_ptr(), hi - lo, 0, d_parts[k].data_ptr(), fly_streams[k].cuda_stream))
+        if world > 1:
+            with torch.cuda.stream(fly_streams[k]):
+                dist.all_gather_into_tensor(d_alls[k], d_parts[k])
     h_s = torch.from_numpy(ss.view(np.int64)).pin_memory()
     out = np.zeros(words, dtype=np.uint64)
 
@@ -626,15 +721,18 @@ def run_msm(args, c):
     clocks = ClockSampler(c.local)
     if rank == 0:
         clocks.start()
-    for _ in range(args.warmup):
-        step_device()
+    for _ in range(args.warmup * n_fly):
+        step_in_flight()
+    torch.cuda.synchronize()
+    ms = timed(c, step_in_flight, args.steps, profile=args.profile_region, extra_streams=fly_streams[1:]) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    # one MSM at a time (its latency), with CUDA events around its accumulation phase for the roofline
     check(L.b200_profile(1))
     prof = (ctypes.c_double * 8)()
     check(L.b200_profile_read(prof))
-    ms = timed(c, step_device, args.steps, profile=args.profile_region) / args.steps
+    ms_one = timed(c, step_device, args.steps) / args.steps
     check(L.b200_profile_read(prof))
     check(L.b200_profile(0))
-    clk = clocks.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(c, step_e2e, args.steps, wall=True) / args.steps
@@ -659,6 +757,10 @@ def run_msm(args, c):
                     "d2h_bytes_per_step": 8 * words,
                     "note": "pinned scalars -> device, b200_msm_device, all-gather of the XYZZ partial records, b200_g*_sum_partials "
                             "to host; the points are the resident CRS"},
+            "msms_in_flight": n_fly,
+            "one_at_a_time": {"ms_per_step": ms_one, "value": n / ms_one / 1e3, "unit": unit,
+                              "note": "the same K steps with ONE MSM in flight: the latency of an MSM; `value` keeps `msms_in_flight` "
+                                      "independent MSMs (own base-set objects and streams) in flight"},
             "gpu_launches": int(prof[6]), "clocks": clk, "accumulation_kernel": {1: "batched affine", 2: "xyzz"}[mode.value],
             "whole_msm_hbm_algorithmic_GBps": bpt * n / (ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": f"G{group} bucket accumulation phase of this rank's shard", "achieved": ach, "peak": peak,

@@ -35,8 +35,14 @@ bool g_init = false;
 int g_device = -1;
 cudaStream_t g_stream = nullptr;
 cudaStream_t g_side[4] = {nullptr, nullptr, nullptr, nullptr};  // side streams: independent MSMs of one proof overlap
+// Second prove context (B200_CFG_PK_CONTEXT): a proving key loaded under context 1 runs on its own side streams and
+// polynomial workspace, so a proof on it can be in flight beside a proof on a context-0 key (two proofs pipelined on two
+// caller streams: the latency-bound sort / tail / product chains of one overlap the accumulation of the other).
+cudaStream_t g_side1[4] = {nullptr, nullptr, nullptr, nullptr};
+cudaStream_t g_stream1 = nullptr;   // context 1's main stream (host-pointer entry points)
+int g_pk_ctx = 0;
 int* g_d_err = nullptr;  // device error flags (bit0: coordinate >= q, bit1: scalar >= r, bit2: zero leading coeff)
-std::unique_ptr<PolyCtx> g_poly;
+std::unique_ptr<PolyCtx> g_poly, g_poly1;
 
 Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = none
 
@@ -109,8 +115,12 @@ int init_locked(int device) {
   for (auto& sd : g_side) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));  // (stream priorities: no measurable effect)
   CU(cudaMalloc(&g_d_err, sizeof(int)));
   CU(cudaMemset(g_d_err, 0, sizeof(int)));
+  for (auto& sd : g_side1) CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g_stream1, cudaStreamNonBlocking));
   g_poly = std::make_unique<PolyCtx>();
   g_poly->launch_counter = &g_launches;
+  g_poly1 = std::make_unique<PolyCtx>();
+  g_poly1->launch_counter = &g_launches;
   g_device = device;
   g_init = true;
   return B200_OK;
@@ -176,11 +186,21 @@ int sort_alloc(SortScratch& ss, const MsmShape& sh, uint32_t slice_S) {
 std::map<uint64_t, std::unique_ptr<Bases>> g_bases;
 uint64_t g_next_handle = 1;
 
+// Reads the device error flags behind everything queued on `st` and waits for the stream.  With `lk` (the library mutex,
+// held by the caller) the wait itself runs UNLOCKED, so a second host thread can enqueue a proof on the other prove
+// context meanwhile (two host-pointer proofs in flight, B200_CFG_PK_CONTEXT).
 template <class F>
-int check_err_flag(const char* what) {
-  int h = 0;
-  CU(cudaMemcpyAsync(&h, g_d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-  CU(cudaStreamSynchronize(g_stream));
+int check_err_flag(const char* what, cudaStream_t st = nullptr, std::unique_lock<std::mutex>* lk = nullptr, int* pinned = nullptr) {
+  if (!st) st = g_stream;
+  int h_local = 0;
+  int* hp = pinned ? pinned : &h_local;   // `pinned`: a page-locked word, so the copy does not block the host under the mutex
+  *hp = 0;
+  CU(cudaMemcpyAsync(hp, g_d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (lk) lk->unlock();
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (lk) lk->lock();
+  CU(se);
+  const int h = *hp;
   if (h) {
     CU(cudaMemset(g_d_err, 0, sizeof(int)));
     if (h & 16) return fail(B200_EINVAL, "%s: tau is one of the interpolation points 1..n", what);
@@ -974,9 +994,9 @@ int b200_groth16_finalize_device(b200_pk_t pk, const void* d_parts, int nparts, 
 int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                        const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
                        uint64_t pi_c[12]) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::unique_lock<std::mutex> lk(g_mu);
   NEED_INIT();
-  return drain_on_error(groth16_prove(pk, w, nw, px, npx, r, s, pi_a, pi_b, pi_c));
+  return drain_on_error(groth16_prove(pk, w, nw, px, npx, r, s, pi_a, pi_b, pi_c, &lk));
 }
 int b200_pinocchio_pk_load(const uint64_t* a, const uint64_t* ap, const uint64_t* b2, const uint64_t* bp,
                            const uint64_t* c, const uint64_t* cp, const uint64_t* kp, size_t m,
@@ -1047,6 +1067,13 @@ int b200_comm_init(const uint8_t id[128], int rank, int world) {
   }
   g_comm.rank = rank;
   g_comm.world = world;
+  // context 1's communicator (collective: every rank is inside b200_comm_init); older NCCL without ncclCommSplit: both
+  // contexts share `comm` and only ONE host thread may prove on sharded keys
+  g_comm.comm1 = nullptr;
+  if (g_comm.api.CommSplit && world > 1) {
+    rc = g_comm.api.CommSplit(g_comm.comm, 0, rank, &g_comm.comm1, nullptr);
+    if (rc != ncclSuccess) g_comm.comm1 = nullptr;
+  }
   return B200_OK;
 }
 int b200_comm_destroy(void) {
@@ -1054,6 +1081,8 @@ int b200_comm_destroy(void) {
   if (!g_comm.active()) return B200_OK;
   cudaSetDevice(g_device);
   cudaDeviceSynchronize();
+  if (g_comm.comm1) g_comm.api.CommDestroy(g_comm.comm1);
+  g_comm.comm1 = nullptr;
   g_comm.api.CommDestroy(g_comm.comm);
   g_comm.comm = nullptr;
   g_comm.world = 1;
@@ -1192,6 +1221,10 @@ int b200_config(int key, int value) {
     (key == 10 ? g_w_ab : key == 11 ? g_w_g2 : key == 12 ? g_aff_min_g1 : g_aff_min_g2) = value;
     return B200_OK;
   }
+  if (key == B200_CFG_PK_CONTEXT && (value == 0 || value == 1)) {
+    g_pk_ctx = value;
+    return B200_OK;
+  }
   if (key == B200_CFG_TMA_STAGING && value >= 0 && value <= 2) {
     g_tma_staging = value;
     return B200_OK;
@@ -1212,6 +1245,8 @@ int b200_shutdown(void) {
   cudaSetDevice(g_device);
   if (g_comm.active()) {
     cudaDeviceSynchronize();
+    if (g_comm.comm1) g_comm.api.CommDestroy(g_comm.comm1);
+    g_comm.comm1 = nullptr;
     g_comm.api.CommDestroy(g_comm.comm);
     g_comm.comm = nullptr;
     g_comm.world = 1;
@@ -1221,9 +1256,13 @@ int b200_shutdown(void) {
   g_r1cs.clear();
   g_domains.clear();
   g_poly.reset();
+  g_poly1.reset();
   if (g_d_err) cudaFree(g_d_err);
   if (g_stream) cudaStreamDestroy(g_stream);
   for (auto& sd : g_side) { if (sd) cudaStreamDestroy(sd); sd = nullptr; }
+  for (auto& sd : g_side1) { if (sd) cudaStreamDestroy(sd); sd = nullptr; }
+  if (g_stream1) cudaStreamDestroy(g_stream1);
+  g_stream1 = nullptr;
   g_d_err = nullptr;
   g_stream = nullptr;
   g_init = false;

@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;   // optional (NCCL >= 2.18)
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   const char* load() {
@@ -33,6 +34,7 @@ struct NcclApi {
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(so, "ncclCommDestroy"));
     AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(so, "ncclAllGather"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(so, "ncclGetErrorString"));
+    CommSplit = reinterpret_cast<decltype(CommSplit)>(dlsym(so, "ncclCommSplit"));
     if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) {
       so = nullptr;
       return "libnccl: missing symbols";
@@ -44,8 +46,13 @@ struct NcclApi {
 struct Comm {
   NcclApi api;
   ncclComm_t comm = nullptr;
+  // Prove context 1 (B200_CFG_PK_CONTEXT) gathers on its own communicator (ncclCommSplit of `comm`): NCCL matches
+  // collectives by issue order per communicator, and two host threads proving on the two contexts reach their
+  // all-gathers in an order that differs from rank to rank.
+  ncclComm_t comm1 = nullptr;
   int rank = 0, world = 1;
   bool active() const { return comm != nullptr; }
+  ncclComm_t of(int ctx) const { return ctx && comm1 ? comm1 : comm; }
 };
 
 static_assert(sizeof(ncclUniqueId) == 128, "b200_comm_unique_id hands out 128 bytes");

@@ -32,6 +32,10 @@ struct ProvingKey {
   // whole MSMs where it can and index ranges where it must: fewer sorts / reduction tails per rank than
   // slicing every MSM `world` ways.  set k: 0 A, 1 B1, 2 B2, 3 C||PTD.
   int rank = 0, world = 1;
+  int ctx = 0;  // prove context (B200_CFG_PK_CONTEXT at load): side streams + polynomial workspace this key's proofs run on
+  cudaStream_t* side() const { return ctx ? g_side1 : g_side; }
+  cudaStream_t main() const { return ctx ? g_stream1 : g_stream; }
+  PolyCtx& poly() const { return ctx ? *g_poly1 : *g_poly; }
   size_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};  // index range inside set k
   bool tail[4] = {false, false, false, false};        // this rank also holds set k's blinding points
   size_t n_c_full = 0;                                // length of the C part of the C||PTD set (m - npublic - 1)
@@ -40,7 +44,14 @@ struct ProvingKey {
   DevBuf h_full;              // full quotient (sharded mode)
   DevBuf gather;              // all-gathered partial records (world x 1 KB), when a communicator is active
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  ~ProvingKey() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+  // pinned landing area of the host-pointer entry points: 48 words of proof + the error flags.  Pinned, so the D2H copies
+  // are truly asynchronous and the call can wait for them with the library mutex released (a pageable destination
+  // makes cudaMemcpyAsync block until the proof is done — under the mutex).
+  uint64_t* h_out = nullptr;
+  ~ProvingKey() {
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    if (h_out) cudaFreeHost(h_out);
+  }
   std::unique_ptr<Bases> g[8];  // Groth16: A, B1, B2(G2), CH   Pinocchio: A, Ap, B(G2), Bp, C, Cp, Kp, H
   Divisor Z;
   DevBuf s1, s2, s3;   // scalar vectors
@@ -128,6 +139,7 @@ struct PointCat {
 
 int pk_common_init(ProvingKey& pk, const uint64_t* z, size_t nz, size_t m) {
   if (!z || nz == 0) return fail(B200_EINVAL, "pk_load: missing Z");
+  pk.ctx = g_pk_ctx;
   int rc = divisor_init(pk.Z, z, nz);
   if (rc) return rc;
   CU(pk.s1.alloc((m + 4) * sizeof(Fr)));
@@ -136,6 +148,7 @@ int pk_common_init(ProvingKey& pk, const uint64_t* z, size_t nz, size_t m) {
   CU(pk.out_std.alloc(64 * sizeof(Fq)));
   CU(pk.rs.alloc(8 * sizeof(Fr)));
   for (auto& e : pk.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaHostAlloc(reinterpret_cast<void**>(&pk.h_out), 64 * sizeof(uint64_t), cudaHostAllocDefault));
   return check_err_flag<Fr>("pk_load(Z)");
 }
 
@@ -434,7 +447,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
   Fr neg_rs = (fr_r.to_mont() * fr_s.to_mont()).neg().from_mont();  // -(r*s) mod r  (groth16.go:274)
   Fr one = Fr::zero();
   one.l[0] = 1;
-  cudaStream_t s1 = g_side[0], s2 = g_side[1], s3 = g_side[2];
+  cudaStream_t s1 = pk->side()[0], s2 = pk->side()[1], s3 = pk->side()[2];
   if (g_serial) s1 = s2 = s3 = st;  // measurement mode (b200_profile bit 1): no overlap, exclusive kernel timings
   cudaEvent_t e_in = pk->ev[0], e_w = pk->ev[1], e_a = pk->ev[2], e_b1 = pk->ev[3], e_b2 = pk->ev[4],
               e_ch = pk->ev[5], e_prod = pk->ev[6];
@@ -477,7 +490,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
       Fr* h_dst = direct ? sCH + n_c : pk->h_full.as<Fr>();
       if (!direct && !pk->h_full.p) CU(pk->h_full.alloc((pk->m + pk->n_h_bases + 4) * sizeof(Fr)));
       if (d_h_std) CU(cudaMemcpyAsync(h_dst, d_h_std, nq * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
-      else CU(poly_div_device(*g_poly, pk->Z, d_px, npx, px_mont, h_dst, nullptr, g_d_err, s3));
+      else CU(poly_div_device(pk->poly(), pk->Z, d_px, npx, px_mont, h_dst, nullptr, g_d_err, s3));
       size_t have = nq > p_lo ? (nq < p_hi ? nq - p_lo : n_p) : 0;   // valid h coefficients inside [p_lo, p_hi)
       if (!direct && have)
         CU(cudaMemcpyAsync(sCH + n_c, pk->h_full.as<Fr>() + p_lo, have * sizeof(Fr), cudaMemcpyDeviceToDevice, s3));
@@ -535,7 +548,7 @@ int groth16_enqueue(ProvingKey* pk, const Fr* d_w, size_t nw, const Fr* d_px, si
     if (g_comm.active() && g_comm.world == pk->world) {
       if (g_comm.rank != pk->rank) return fail(B200_EINVAL, "groth16_prove: key shard %d on communicator rank %d", pk->rank, g_comm.rank);
       CU(pk->gather.ensure(kPartialBytes * (size_t)pk->world));
-      ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPartialBytes, ncclUint8, g_comm.comm, st);
+      ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPartialBytes, ncclUint8, g_comm.of(pk->ctx), st);
       if (nrc != ncclSuccess) return fail(B200_ECOMM, "ncclAllGather: %s", g_comm.api.GetErrorString(nrc));
       k_groth16_finalize<<<1, 96, 0, st>>>(pk->gather.as<uint8_t>(), pk->world, d_out, d_out + 3, reinterpret_cast<Fq2*>(d_out + 6));
       g_launches += 2;
@@ -559,7 +572,7 @@ int groth16_finalize_enqueue(ProvingKey* pk, const uint8_t* d_parts, int nparts,
 }
 
 int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx, const uint64_t* r,
-                  const uint64_t* s, uint64_t* pi_a, uint64_t* pi_b, uint64_t* pi_c) {
+                  const uint64_t* s, uint64_t* pi_a, uint64_t* pi_b, uint64_t* pi_c, std::unique_lock<std::mutex>* lk = nullptr) {
   ProvingKey* pk = find_pk(h, 1);
   if (!pk) return fail(B200_EINVAL, "groth16_prove: bad proving-key handle");
   if (!w || !px || !r || !s || !pi_a || !pi_b || !pi_c) return fail(B200_EINVAL, "groth16_prove: null pointer");
@@ -569,7 +582,7 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
     return fail(B200_EINVAL, "groth16_prove: sharded key (rank %d/%d) without a matching communicator: call b200_comm_init, "
                              "or use b200_groth16_prove_device + b200_groth16_finalize_device around your own all-gather",
                 pk->rank, pk->world);
-  cudaStream_t st = g_stream;
+  cudaStream_t st = pk->main();   // context 1 keys: their own main stream (a second host thread's proof in flight)
   CU(pk->px.ensure(npx * sizeof(Fr)));
   CU(pk->w_stage.ensure(nw * sizeof(Fr)));
   bool need_px = true;
@@ -595,13 +608,13 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
   // px is only needed by the division on side stream 3: copy it there so the transfer overlaps the sort of w
   // (same-stream order makes the division see it; the previous proof's use of pk->px finished before its combine)
   // (measurement mode runs the division on `st`, so the copy goes there too)
-  if (need_px) CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : g_side[2]));
+  if (need_px) CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : pk->side()[2]));
   Fq* o = pk->out_std.as<Fq>();
   int rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, pk->px.as<Fr>(), npx, r, s, o, st);
   if (rc) return rc;
-  uint64_t host_out[48];
-  CU(cudaMemcpyAsync(host_out, o, sizeof host_out, cudaMemcpyDeviceToHost, st));
-  rc = check_err_flag<Fr>("groth16_prove");  // synchronises
+  uint64_t* host_out = pk->h_out;
+  CU(cudaMemcpyAsync(host_out, o, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  rc = check_err_flag<Fr>("groth16_prove", st, lk, reinterpret_cast<int*>(host_out + 48));  // synchronises (the wait runs with the library mutex released)
   if (rc) return rc;
   memcpy(pi_a, host_out, 12 * 8);
   memcpy(pi_c, host_out + 12, 12 * 8);
@@ -701,7 +714,7 @@ int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* p
   if (gather && !(g_comm.active() && g_comm.world == pk->world && g_comm.rank == pk->rank))
     return fail(B200_EINVAL, "pinocchio_prove: sharded key (rank %d/%d) without a matching communicator (b200_comm_init)",
                 pk->rank, pk->world);
-  cudaStream_t st = g_stream, side[3] = {g_side[0], g_side[1], g_side[2]};
+  cudaStream_t st = g_stream, side[3] = {pk->side()[0], pk->side()[1], pk->side()[2]};
   cudaEvent_t e_in = pk->ev[0], e_sorted[2] = {pk->ev[1], pk->ev[2]}, e_done[3] = {pk->ev[3], pk->ev[4], pk->ev[5]};
   Fr* dw = pk->s1.as<Fr>();
   Fr* dh = pk->s3.as<Fr>();
@@ -722,7 +735,7 @@ int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* p
     cudaStream_t s3 = side[2];
     used[2] = true;
     EV_WAIT(s3, e_in);
-    CU(poly_div_device(*g_poly, pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, s3));
+    CU(poly_div_device(pk->poly(), pk->Z, pk->px.as<Fr>(), npx, 0, dh, nullptr, g_d_err, s3));
     if ((rc = msm_enqueue<Fq>(pk->g[7].get(), dh, nq, 0, slot_g1(7), s3))) return rc;
   }
   // two scalar vectors: w[l+1..m) feeds PiA, PiAp (snark.go:265-268); w feeds PiB, PiBp, PiC, PiCp, PiKp (:270-278).
@@ -770,7 +783,7 @@ int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* p
   Fq* o = pk->out_std.as<Fq>();
   if (gather) {
     CU(pk->gather.ensure(kPinRecordBytes * (size_t)pk->world));
-    ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPinRecordBytes, ncclUint8, g_comm.comm, st);
+    ncclResult_t nrc = g_comm.api.AllGather(res, pk->gather.p, kPinRecordBytes, ncclUint8, g_comm.of(pk->ctx), st);
     if (nrc != ncclSuccess) return fail(B200_ECOMM, "ncclAllGather: %s", g_comm.api.GetErrorString(nrc));
     k_pinocchio_gather_finalize<<<1, 64, 0, st>>>(pk->gather.as<uint8_t>(), pk->world, o, reinterpret_cast<Fq2*>(o + 21));
   } else {

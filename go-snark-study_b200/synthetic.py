@@ -93,13 +93,13 @@ class SyntheticGroth16:
                 "G2": {"Beta": _unflatten_g2(self.beta2)[0], "Delta": _unflatten_g2(self.delta2)[0],
                        "BACGamma": _unflatten_g2(self.b2)}}
 
-    def expected_dlogs(self):
+    def expected_dlogs(self, r=None, s=None):
         """Discrete logs (w.r.t. the generators) of PiA, PiB, PiC that
-        groth16.GenerateProofs (groth16.go:225-278) yields on this input."""
+        groth16.GenerateProofs (groth16.go:225-278) yields on this input (blinding r, s: this instance's unless given)."""
         w = limbs_to_ints(self.w)
         dot = lambda ks, ws: sum(a * b for a, b in zip(limbs_to_ints(ks), ws)) % R
         alpha, beta, delta = (limbs_to_ints(k)[0] for k in (self.k_alpha, self.k_beta, self.k_delta))
-        r, s = self.r, self.s
+        r, s = (self.r if r is None else r), (self.s if s is None else s)
         a = (dot(self.k_at, w) + alpha + r * delta) % R
         b = (dot(self.k_b, w) + beta + s * delta) % R
         l1 = self.npublic + 1

@@ -59,6 +59,21 @@ int b200_version(void);
  * register-load kernel: measured FASTER (18.92 vs 20.17 ms per 2^20 proof, profiles/r2_notes.md: the kernel is bound by
  * the multiply pipe, not by the fetch); 1 staged in every round, 2 staged in rounds >= 2 only.  Same results.          */
 #define B200_CFG_TMA_STAGING 2
+/* B200_CFG_PK_CONTEXT: prove context (0 or 1) of proving keys loaded AFTERWARDS.  The two contexts own separate side
+ * streams and polynomial workspaces, so a device-resident proof on a context-1 key (b200_groth16_prove_device on the
+ * caller's second stream) may be in flight beside one on a context-0 key: a prover that keeps two proofs in flight hides
+ * the latency-bound sort / bucket-tail / blinding-product chains of one behind the accumulation of the other (bench.py
+ * `proofs_in_flight`; the keys are independent objects, each with its own tables and scratch).                       */
+#define B200_CFG_PK_CONTEXT 4
+/* Partition tuning of SHARDED proving keys loaded afterwards (defaults = the measured best for one proof at a time,
+ * profiles/r2_notes.md section 8): cost weight x100 of an A / B1 term (10) and of a G2 term (11) in C||PTD terms, and the
+ * smallest per-rank set that still takes the batched-affine tree, in G1 (12) / G2 (13) terms — below it the set runs
+ * the XYZZ kernel, whose single launch has the shorter latency chain.  With two proofs in flight (B200_CFG_PK_CONTEXT)
+ * that latency is hidden and the affine tree's 6 multiplications per add win at every shard size: set 12 and 13 to 1. */
+#define B200_CFG_SHARD_W_AB 10
+#define B200_CFG_SHARD_W_G2 11
+#define B200_CFG_SHARD_AFFINE_MIN_G1 12
+#define B200_CFG_SHARD_AFFINE_MIN_G2 13
 int b200_config(int key, int value);
 
 /* ---- base-point sets (the CRS arrays of groth16.Pk / snark.Pk) ---------- */

@@ -189,3 +189,103 @@ def test_groth16_prove_named_sizes_known_dlogs(mods, logn, mode):
         assert G2.affine(_unflatten_g2(pb)[0]) == G2.affine(G2.mul_scalar(G2.G, eb))
         assert G1.affine(_unflatten_g1(pc)[0]) == G1.affine(G1.mul_scalar(G1.G, ec))
     check(lib().b200_pk_free(pk))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("logn", [10, 14])
+def test_two_proofs_in_flight_on_two_contexts(mods, logn):
+    """B200_CFG_PK_CONTEXT: two proving keys loaded under contexts 0 and 1 prove DIFFERENT statements (different r, s)
+    interleaved on two streams with no host synchronisation in between (what bench.py's `proofs_in_flight` does); every
+    proof of every round equals its known-discrete-log expectation — groth16.GenerateProofs (groth16.go:225-278) on the
+    same key, witness, px, r, s."""
+    import numpy as np
+    import torch
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+    from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+    from gosnark_b200.synthetic import SyntheticGroth16
+    syn = SyntheticGroth16(logn)
+    L = lib()
+    pks = []
+    try:
+        for k in range(2):
+            check(L.b200_config(_lib.CFG_PK_CONTEXT, k))
+            pks.append(syn.load_pk())
+    finally:
+        check(L.b200_config(_lib.CFG_PK_CONTEXT, 0))
+    d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
+    d_px = torch.from_numpy(syn.px.view(np.int64)).cuda()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    rounds = 4
+    outs = [[torch.zeros(48, dtype=torch.int64, device="cuda") for _ in range(rounds)] for _ in range(2)]
+    rs = [[(syn.r + 17 * (2 * j + k)) % o.R, (syn.s + 29 * (2 * j + k)) % o.R] for j in range(rounds) for k in range(2)]
+    torch.cuda.synchronize()
+    for j in range(rounds):
+        for k in range(2):
+            r_, s_ = rs[2 * j + k]
+            rr, ss = ints_to_limbs([r_]), ints_to_limbs([s_])
+            check(L.b200_groth16_prove_device(pks[k], d_w.data_ptr(), syn.m, d_px.data_ptr(), syn.px.shape[0], ptr(rr), ptr(ss),
+                                              outs[k][j].data_ptr(), streams[k].cuda_stream))
+    torch.cuda.synchronize()
+    for j in range(rounds):
+        for k in range(2):
+            r_, s_ = rs[2 * j + k]
+            ea, eb, ec = syn.expected_dlogs(r_, s_)
+            out = outs[k][j].cpu().numpy().view(np.uint64)
+            pa, pc = _unflatten_g1(out[:24])
+            pb = _unflatten_g2(out[24:])[0]
+            assert G1.affine(pa) == G1.affine(G1.mul_scalar(G1.G, ea)), (j, k)
+            assert G2.affine(pb) == G2.affine(G2.mul_scalar(G2.G, eb)), (j, k)
+            assert G1.affine(pc) == G1.affine(G1.mul_scalar(G1.G, ec)), (j, k)
+    for pk in pks:
+        check(L.b200_pk_free(pk))
+
+
+@pytest.mark.timeout(600)
+def test_two_host_threads_prove_on_two_contexts(mods):
+    """The host-pointer entry point b200_groth16_prove from two threads, thread k on the context-k key: a call enqueues
+    under the library mutex and waits for its proof with the mutex released, so the two proofs are in flight together;
+    every proof equals the known-discrete-log expectation for its own (r, s)."""
+    import threading
+    import numpy as np
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
+    from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
+    from gosnark_b200.synthetic import SyntheticGroth16
+    syn = SyntheticGroth16(13)
+    L = lib()
+    pks = []
+    try:
+        for k in range(2):
+            check(L.b200_config(_lib.CFG_PK_CONTEXT, k))
+            pks.append(syn.load_pk())
+    finally:
+        check(L.b200_config(_lib.CFG_PK_CONTEXT, 0))
+    rounds = 5
+    results, errs = {}, []
+
+    def worker(k):
+        try:
+            for j in range(rounds):
+                r_, s_ = (syn.r + 101 * (2 * j + k)) % o.R, (syn.s + 103 * (2 * j + k)) % o.R
+                pa, pb, pc = np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+                check(L.b200_groth16_prove(pks[k], ptr(syn.w), syn.m, ptr(syn.px), syn.px.shape[0], ptr(ints_to_limbs([r_])),
+                                           ptr(ints_to_limbs([s_])), ptr(pa), ptr(pb), ptr(pc)))
+                results[(k, j)] = (r_, s_, pa, pb, pc)
+        except Exception as e:
+            errs.append(e)
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert len(results) == 2 * rounds
+    for (k, j), (r_, s_, pa, pb, pc) in results.items():
+        ea, eb, ec = syn.expected_dlogs(r_, s_)
+        assert G1.affine(_unflatten_g1(pa)[0]) == G1.affine(G1.mul_scalar(G1.G, ea)), (k, j)
+        assert G2.affine(_unflatten_g2(pb)[0]) == G2.affine(G2.mul_scalar(G2.G, eb)), (k, j)
+        assert G1.affine(_unflatten_g1(pc)[0]) == G1.affine(G1.mul_scalar(G1.G, ec)), (k, j)
+    for pk in pks:
+        check(L.b200_pk_free(pk))
