@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2],
                     help="prove workload: independent proofs kept in flight (2 = two proving-key contexts on two streams, the "
                          "latency chains of one proof overlap the accumulation of the other; 1 = one proof at a time)")
+    ap.add_argument("--pairing-kernel", type=int, default=None, choices=[0, 1, 2], help="A/B (verify workload): b200_pairing_batch with one thread (1) / one warp (2) per pairing")
     ap.add_argument("--tma-staging", type=int, default=None, choices=[0, 1, 2], help="A/B: staged backward pass off / all rounds / rounds >= 2")
     return ap.parse_args()
 
@@ -553,9 +554,14 @@ def run_prove(args, c):
         def e2e_threads(total):
             ths = [threading.Thread(target=e2e_worker, args=(k, total // n_fly + (1 if k < total % n_fly else 0))) for k in range(n_fly)]
             for t in ths:
+                t.daemon = True
                 t.start()
+            deadline = time.time() + 300.0
             for t in ths:
-                t.join()
+                t.join(max(0.0, deadline - time.time()))
+            if any(t.is_alive() for t in ths):       # never leave the box hung: a stuck collective cannot be recovered in-process
+                print(json.dumps({"error": "host-pointer proofs in flight did not finish within 300 s"}), flush=True)
+                os._exit(3)
             if errs:
                 raise errs[0]
 
@@ -794,6 +800,8 @@ def run_verify(args, c):
         raise SystemExit("--workload verify is a single-GPU measurement")
     logn = args.logn if args.logn is not None else default_logn("verify")
     n = 1 << logn
+    if args.pairing_kernel is not None:
+        check(L.b200_config(_lib.CFG_PAIRING_KERNEL, args.pairing_kernel))
     k1, k2 = rand_limbs(n, 11), rand_limbs(n, 12)
     p1 = np.zeros((n, 12), dtype=np.uint64)
     p2 = np.zeros((n, 24), dtype=np.uint64)
@@ -812,6 +820,16 @@ def run_verify(args, c):
     check(L.b200_g1_mul_batch_bcast(ptr(_flatten_g1([G1_GEN])), ptr(ints_to_limbs([ab])), 1, ptr(q1)))
     check(L.b200_pairing_batch(ptr(q1), ptr(q2), 1, ptr(o2)))
     parity = bool((o2[0] == out[0]).all())
+    # the two kernels (one thread / one warp per pairing) agree on a sample of this batch, coefficient for coefficient
+    ns = min(n, 256)
+    outs = []
+    for kern in (1, 2):
+        check(L.b200_config(_lib.CFG_PAIRING_KERNEL, kern))
+        o_k = np.zeros((ns, 48), dtype=np.uint64)
+        check(L.b200_pairing_batch(ptr(p1), ptr(p2), ns, ptr(o_k)))
+        outs.append(o_k)
+    check(L.b200_config(_lib.CFG_PAIRING_KERNEL, args.pairing_kernel if args.pairing_kernel is not None else 0))
+    parity = parity and bool((outs[0] == outs[1]).all()) and bool((outs[0] == out[:ns]).all())
     clocks = ClockSampler(c.local)
     clocks.start()
     for _ in range(args.warmup):

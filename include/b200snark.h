@@ -65,6 +65,12 @@ int b200_version(void);
  * the latency-bound sort / bucket-tail / blinding-product chains of one behind the accumulation of the other (bench.py
  * `proofs_in_flight`; the keys are independent objects, each with its own tables and scratch).                       */
 #define B200_CFG_PK_CONTEXT 4
+/* B200_CFG_PAIRING_KERNEL: b200_pairing_batch with one THREAD per pairing (1: the step-by-step restatement of
+ * bn128.go:179-421, ~10 ms of dependent multiplications per pairing) or one WARP per pairing (2: F_q^12 in shared
+ * memory, 27 F_q^2 products of a tower multiplication on 27 lanes; csrc/pairing_warp.cuh: 3.4 ms); 0 = auto: a warp per
+ * pairing up to 2048 pairings per call (latency), a thread per pairing above (462 k vs 204 k pairings/s at 2^16).
+ * Bit-identical F_q^12 values.  b200_groth16_verify always runs four warps (5.4 ms per verification, was 20).          */
+#define B200_CFG_PAIRING_KERNEL 5
 /* Partition tuning of SHARDED proving keys loaded afterwards (defaults = the measured best for one proof at a time,
  * profiles/r2_notes.md section 8): cost weight x100 of an A / B1 term (10) and of a G2 term (11) in C||PTD terms, and the
  * smallest per-rank set that still takes the batched-affine tree, in G1 (12) / G2 (13) terms — below it the set runs

@@ -21,6 +21,7 @@ template <class K> void stub_launch_cta(unsigned nblocks, unsigned nthreads, K k
 #define B200_LAUNCH(kernel, grid, block, stream, ...) stub_launch_threads((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
 #define B200_LAUNCH_CTA(kernel, grid, block, stream, ...) stub_launch_cta((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
 #include "qap_sparse.cuh"
+#include "pairing_warp.cuh"
 
 using namespace b200;
 
@@ -563,6 +564,63 @@ int t_poly_mul_kernels(const uint32_t* a, uint32_t la, const uint32_t* b, uint32
 // sum_i scalars[i] * P_i through every kernel of the pipeline; S = 0: XYZZ accumulation, else batched-affine slices of S
 int t_msm_full(int group, const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, uint32_t c, uint32_t S, uint32_t* out_std) {
   return group == 1 ? msm_full<Fq>(jac_std, scalars_std, n, c, S, out_std) : msm_full<Fq2>(jac_std, scalars_std, n, c, S, out_std);
+}
+// One-warp-per-pairing code (pairing_warp.cuh) on a 32-thread emulated warp.  g1 = (x, y), g2 = (x.c0, x.c1, y.c0, y.c1), affine
+// standard form; out = 12 field elements in the reference's [2][3][2] order.  mode 0: the whole pairing; mode 1: only an
+// F_q^12 product of in (12 elements) with in2 -> out (the tower product against f12_mul is checked by the caller).
+// Returns the number of coefficient mismatches against the thread-per-pairing restatement of pairing.cuh.
+int t_pairing_warp(const uint32_t* g1, const uint32_t* g2, uint32_t* out) {
+  F2::B px = load_std<F2::B>(g1), py = load_std<F2::B>(g1 + 8);
+  F2 qx = load_std<F2>(g2), qy = load_std<F2>(g2 + 16);
+  static wp::Ws ws;
+  run_cta(0, 32, 1, [&] { wp::pairing(ws, px, py, qx, qy); });
+  F12 ref = pairing_affine_t<true>(px, py, qx, qy);
+  const F2* parts[6] = {&ref.a.a, &ref.a.b, &ref.a.c, &ref.b.a, &ref.b.b, &ref.b.c};
+  int bad = 0;
+  for (int k = 0; k < 6; k++) {
+    if (!(ws.r[wp::RF][k] == *parts[k])) bad++;
+    store_std(out + 16 * k, ws.r[wp::RF][k]);
+  }
+  return bad;
+}
+int t_f12_warp_ops(const uint32_t* a_std, const uint32_t* b_std, uint32_t* out_mul, uint32_t* out_frob2, uint32_t* out_expu_conj) {
+  static wp::Ws ws;
+  F12 x, y;
+  F2* xs[6] = {&x.a.a, &x.a.b, &x.a.c, &x.b.a, &x.b.b, &x.b.c};
+  F2* ys[6] = {&y.a.a, &y.a.b, &y.a.c, &y.b.a, &y.b.b, &y.b.c};
+  for (int k = 0; k < 6; k++) {
+    *xs[k] = load_std<F2>(a_std + 16 * k);
+    *ys[k] = load_std<F2>(b_std + 16 * k);
+    ws.r[2][k] = *xs[k];
+    ws.r[3][k] = *ys[k];
+  }
+  F2 qd = F2::one();
+  run_cta(0, 32, 1, [&] {
+    wp::pairing_constants(ws);
+    wp::f12_mul(ws, 4, 2, 3);
+    wp::f12_frobenius(ws, 5, 2, 2);
+    wp::f12_exp_u(ws, 6, 2);
+    wp::f12_conj(ws, 6, 6);
+    wp::f12_mul(ws, 2, 2, 2);      // aliased square
+    wp::f12_inverse(ws, 7, 3);
+    wp::f12_frobenius(ws, 8, 3, 1);
+    wp::f12_frobenius(ws, 9, 3, 3);
+  });
+  (void)qd;
+  auto cmp = [&](int reg, const F12& r) {
+    const F2* parts[6] = {&r.a.a, &r.a.b, &r.a.c, &r.b.a, &r.b.b, &r.b.c};
+    int bad = 0;
+    for (int k = 0; k < 6; k++) bad += !(ws.r[reg][k] == *parts[k]);
+    return bad;
+  };
+  int bad = cmp(4, f12_mul(x, y)) + 10 * cmp(5, f12_frobenius<2>(x)) + 100 * cmp(6, f12_conj(f12_exp_u(x))) + 1000 * cmp(2, f12_sqr(x)) +
+            10000 * cmp(7, f12_inverse(y)) + 100000 * cmp(8, f12_frobenius<1>(y)) + 1000000 * cmp(9, f12_frobenius<3>(y));
+  for (int k = 0; k < 6; k++) {
+    store_std(out_mul + 16 * k, ws.r[4][k]);
+    store_std(out_frob2 + 16 * k, ws.r[5][k]);
+    store_std(out_expu_conj + 16 * k, ws.r[6][k]);
+  }
+  return bad;
 }
 int t_msm_tail(int group, const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t nbuckets, uint32_t seg, uint32_t* out_std) {
   return group == 1 ? msm_tail<Fq>(slice_pts_std, slice_off, nbuckets, seg, out_std)

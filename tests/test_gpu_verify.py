@@ -138,3 +138,29 @@ def test_pinocchio_setup_and_verify_on_gpu(mods, golden_dir):
     gproof = {k: (t2(v) if k == "PiB" else t3(v)) for k, v in pr.items()}
     assert snark.VerifyProof(vk, gproof, [35])
     assert not snark.VerifyProof(vk, gproof, [34])
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_both_pairing_kernels(mods, golden_dir, kernel):
+    """B200_CFG_PAIRING_KERNEL: one thread per pairing (1, the step-by-step restatement) and one warp per pairing (2,
+    csrc/pairing_warp.cuh) give the same F_q^12 coefficients: the snarkjs golden (K8), the bn128_test.go literal, the oracle
+    on random points and a G1 infinity, and the same errors (G2 infinity, coordinate >= q)."""
+    from gosnark_b200 import _lib
+    bn, _, _ = mods
+    vk, _, _, gold = _circom(golden_dir)
+    _lib.check(_lib.lib().b200_config(_lib.CFG_PAIRING_KERNEL, kernel))
+    try:
+        assert bn.Pairing(vk["G1"]["Alpha"], vk["G2"]["Beta"]) == gold
+        rng = random.Random(50 + kernel)
+        ps = [G1.mul_scalar(G1.G, 25)] + [G1.mul_scalar(G1.G, rng.randrange(1, R)) for _ in range(5)] + [G1.zero3()]
+        qs = [G2.mul_scalar(G2.G, 30)] + [G2.mul_scalar(G2.G, rng.randrange(1, R)) for _ in range(5)] + [G2.G]
+        got = bn.PairingBatch(ps, qs)
+        assert got[0][0][0][0] == 8016119724813186033542830391460394070015218389456422587891475873290878009957
+        for p, q, e in zip(ps, qs, got):
+            assert e == o.BN.pairing(p, q)
+        with pytest.raises(Exception, match="Fq2.One"):
+            bn.Pairing(G1.G, G2.zero3())
+        with pytest.raises(Exception, match=">= q"):
+            bn.Pairing((o.Q, 2, 1), G2.G)
+    finally:
+        _lib.check(_lib.lib().b200_config(_lib.CFG_PAIRING_KERNEL, 0))

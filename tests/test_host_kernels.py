@@ -334,3 +334,29 @@ def test_division_orchestration_on_the_cpu(lib, na, nb):
     assert lib.t_poly_div_orch(_ptr(_u32(a)), na, _ptr(_u32(b)), nb, _ptr(q), _ptr(rem)) == 0
     assert _limbs_to_ints(q, na - nb + 1) == q0
     assert _limbs_to_ints(rem, nb - 1) == r0
+
+
+def test_warp_pairing_on_the_cpu(lib):
+    """csrc/pairing_warp.cuh — one warp per pairing: F_q^12 in shared memory, the 27 F_q^2 products of a tower
+    multiplication on 27 lanes, the line functions level by level — run as 32 emulated lanes: the tower operations
+    (product, aliased square, Frobenius 1-3, x^u, conjugation, inversion) and a whole pairing agree coefficient for
+    coefficient with the thread-per-pairing restatement of pairing.cuh, and e(25 G1, 30 G2) carries the literal of
+    bn128_test.go:66."""
+    rng = random.Random(77)
+    for _ in range(3):
+        a = _u32([rng.randrange(o.Q) for _ in range(12)])
+        b = _u32([rng.randrange(o.Q) for _ in range(12)])
+        o1, o2, o3 = (np.zeros(96, dtype=np.uint32) for _ in range(3))
+        assert lib.t_f12_warp_ops(_ptr(a), _ptr(b), _ptr(o1), _ptr(o2), _ptr(o3)) == 0
+    G1, G2 = o.BN.G1, o.BN.G2
+    for k1, k2 in ((25, 30), (rng.randrange(1, R_), rng.randrange(1, R_))):
+        p = G1.affine(G1.mul_scalar(G1.G, k1))
+        q = G2.affine(G2.mul_scalar(G2.G, k2))
+        out = np.zeros(96, dtype=np.uint32)
+        assert lib.t_pairing_warp(_ptr(_u32([p[0], p[1]])), _ptr(_u32([q[0][0], q[0][1], q[1][0], q[1][1]])), _ptr(out)) == 0
+        raw = out.tobytes()
+        v = [int.from_bytes(raw[32 * i:32 * (i + 1)], "little") for i in range(12)]
+        got = tuple(tuple((v[6 * h + 2 * k], v[6 * h + 2 * k + 1]) for k in range(3)) for h in range(2))
+        assert got == o.BN.pairing((p[0], p[1], 1), (q[0], q[1], (1, 0)))
+        if (k1, k2) == (25, 30):
+            assert v[0] == 8016119724813186033542830391460394070015218389456422587891475873290878009957
