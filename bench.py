@@ -637,6 +637,11 @@ def run_prove(args, c):
     }
     if args.with_qap:
         line["verified_under_real_vk"] = verified
+    if not args.no_extras and world == 1 and not args.with_qap:
+        try:
+            line["g1_msm_2p20"] = side_g1_msm(c)
+        except Exception as e:   # a side measurement must never take the bench line down
+            line["g1_msm_2p20"] = {"error": str(e)}
     if not args.no_extras and world == 1:
         try:
             ref = CpuReference()
@@ -648,6 +653,60 @@ def run_prove(args, c):
             line["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(line))
     return 0
+
+
+def side_g1_msm(c, logn=20, steps=10, warmup=3):
+    """The other half of BASELINE.json's metric inside the default line: a stand-alone BN128 G1 MSM of 2^logn random scalars /
+    points (config 3), device-resident — two MSMs in flight on two base-set objects, and one at a time."""
+    torch, L = c.torch, c.L
+    from gosnark_b200 import _lib
+    from gosnark_b200._lib import check, ptr
+    from gosnark_b200.bn128 import _flatten_g1, _unflatten_g1
+    from gosnark_b200.synthetic import SEED_POINTS, SEED_SCALARS, rand_limbs
+    n = 1 << logn
+    ks = rand_limbs(n, SEED_POINTS)
+    ks[:, 0] |= np.uint64(1)
+    ss = rand_limbs(n, SEED_SCALARS)
+    pts = np.zeros((n, 12), dtype=np.uint64)
+    check(L.b200_g1_mul_batch_bcast(ptr(_flatten_g1([G1_GEN])), ptr(ks), n, ptr(pts)))
+    hbs = []
+    for _ in range(2):
+        h_ = _lib._h(0)
+        check(L.b200_g1_bases_load(ptr(pts), n, 0, h_))
+        hbs.append(h_)
+    del pts
+    d_s = torch.from_numpy(ss.view(np.int64)).cuda()
+    d_parts = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(2)]
+    streams = [c.stream, torch.cuda.Stream()]
+    ctr = [0]
+    torch.cuda.synchronize()
+
+    def step2():
+        k = ctr[0] % 2
+        ctr[0] += 1
+        check(L.b200_msm_device(hbs[k].value, d_s.data_ptr(), n, 0, d_parts[k].data_ptr(), streams[k].cuda_stream))
+
+    def step1():
+        check(L.b200_msm_device(hbs[0].value, d_s.data_ptr(), n, 0, d_parts[0].data_ptr(), c.st))
+
+    for _ in range(2 * warmup):
+        step2()
+    torch.cuda.synchronize()
+    ms2 = timed(c, step2, steps, extra_streams=streams[1:]) / steps
+    ms1 = timed(c, step1, steps) / steps
+    from oracle import ref_py as o          # checker only
+    out = np.zeros(12, dtype=np.uint64)
+    parity = True
+    expect = sum(int(a) * int(b) for a, b in zip(_lib.limbs_to_ints(ks), _lib.limbs_to_ints(ss))) % R_MOD
+    for d_p in d_parts:
+        check(L.b200_g1_sum_partials(d_p.data_ptr(), 1, ptr(out), c.st))
+        parity = parity and o.BN.G1.affine(_unflatten_g1(out)[0]) == o.BN.G1.affine(o.BN.G1.mul_scalar(o.BN.G1.G, expect))
+    for h_ in hbs:
+        check(L.b200_bases_free(h_.value))
+    return {"n": n, "ms_per_msm": ms2, "mscalar_mul_per_sec": n / ms2 / 1e3, "msms_in_flight": 2,
+            "one_at_a_time_ms": ms1, "one_at_a_time_mscalar_mul_per_sec": n / ms1 / 1e3, "parity_vs_known_dlog": bool(parity),
+            "whole_msm_hbm_algorithmic_GBps": 96.0 * n / (ms2 * 1e-3) / 1e9,
+            "note": "stand-alone G1 MSM (BASELINE config 3) measured in the same run; `bench.py --workload g1msm` is its full line"}
 
 
 def run_msm(args, c):
