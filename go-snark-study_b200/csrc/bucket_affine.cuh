@@ -33,6 +33,16 @@ namespace b200 {
 constexpr int kAffBlock = 128;    // threads per block
 constexpr int kAffPairs = 32;     // pairs per thread per round
 
+// Tree nodes of a round, x- and y-coordinates in SEPARATE arrays: the forward pass of the next round needs only the two
+// x-coordinates of a pair — 64 (G1) / 128 (G2) contiguous bytes here instead of two whole points — and the backward pass
+// reads / writes the same bytes either way.  (The window-precomputed CRS table stays point-interleaved: its gathers are
+// random, and a 64-byte point is one DRAM access.)
+template <class F>
+struct NodeBuf {
+  F* x;
+  F* y;
+};
+
 template <class F>
 struct AffineRound {
   const Affine<F>* table;     // precomputed points (round 1 leaves)
@@ -40,8 +50,8 @@ struct AffineRound {
   const uint32_t* slice_start;
   const uint32_t* slice_end;
   const uint32_t* nslices_ptr;  // device: slice_off[m]
-  const Affine<F>* prev;      // nodes of the previous round (r > 1): nslices * 2q
-  Affine<F>* out;             // nodes of this round: nslices * q
+  NodeBuf<F> prev;            // nodes of the previous round (r > 1): nslices * 2q
+  NodeBuf<F> out;             // nodes of this round: nslices * q
   F* pre;                     // prefix products, one per pair
   F* others;                  // per thread: product of the other threads' totals in its block
   F* btot;                    // per block: product of all denominators (then inverted in place)
@@ -72,8 +82,8 @@ __device__ __forceinline__ bool aff_operands(const AffineRound<F>& a, uint32_t p
     }
   } else {
     size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
-    P = ld_affine(&a.prev[base]);
-    Q = ld_affine(&a.prev[base + 1]);
+    P = Affine<F>{ld_fe(&a.prev.x[base]), ld_fe(&a.prev.y[base])};
+    Q = Affine<F>{ld_fe(&a.prev.x[base + 1]), ld_fe(&a.prev.y[base + 1])};
   }
   return true;
 }
@@ -113,7 +123,7 @@ template <class F>
 __device__ __forceinline__ bool aff_forward_denominator(const AffineRound<F>& a, uint32_t p, uint32_t npairs, F& d) {
   if (p >= npairs) return false;
   uint32_t slice = p >> a.q_log, j = p & ((1u << a.q_log) - 1u);
-  const Affine<F>*pp, *qp;
+  F x1, x2;
   if (a.round == 1) {
     uint32_t s = a.slice_start[slice], e = a.slice_end[slice];
     uint32_t i0 = s + 2 * j, i1 = i0 + 1;
@@ -124,15 +134,13 @@ __device__ __forceinline__ bool aff_forward_denominator(const AffineRound<F>& a,
     }
     uint32_t e0 = a.entries[i0], e1 = a.entries[i1];
     if (a.pair_ids) a.pair_ids[p] = make_uint2(e0, e1);
-    pp = &a.table[e0 >> 1];
-    qp = &a.table[e1 >> 1];
+    x1 = ld_x_gather(&a.table[e0 >> 1]);
+    x2 = ld_x_gather(&a.table[e1 >> 1]);
   } else {
     size_t base = ((size_t)slice << (a.q_log + 1)) + 2 * j;
-    pp = &a.prev[base];
-    qp = &a.prev[base + 1];
+    x1 = ld_fe(&a.prev.x[base]);
+    x2 = ld_fe(&a.prev.x[base + 1]);
   }
-  F x1 = a.round == 1 ? ld_x_gather(pp) : ld_fe(&pp->x);
-  F x2 = a.round == 1 ? ld_x_gather(qp) : ld_fe(&qp->x);
   F dx = x2 - x1;
   if (x1.is_zero() || x2.is_zero() || dx.is_zero()) {
     Affine<F> P, Q;
@@ -260,7 +268,8 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward(AffineRound
     } else {
       Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
     }
-    a.out[p] = Rr;
+    a.out.x[p] = Rr.x;
+    a.out.y[p] = Rr.y;
   }
 }
 
@@ -285,7 +294,8 @@ constexpr uint32_t kNoEntry = 0xffffffffu;
 template <class F>
 struct AffStageLayout {
   static constexpr uint32_t kPairBytes = 2 * sizeof(Affine<F>);                        // 128 B (G1) / 256 B (G2)
-  static constexpr uint32_t kPQ = 0, kPre = kAffBlock * kPairBytes, kBar = kPre + kAffBlock * sizeof(F);
+  // per thread: [P.x | Q.x] in the X region, [P.y | Q.y] in the Y region (the node arrays are x / y separated), one prefix product
+  static constexpr uint32_t kX = 0, kY = kAffBlock * 2 * sizeof(F), kPre = kAffBlock * kPairBytes, kBar = kPre + kAffBlock * sizeof(F);
   static constexpr uint32_t kSmem = kBar + (kAffBlock / 32) * 8;                       // 20.5 KB (G1) / 41 KB (G2)
 };
 
@@ -414,7 +424,8 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(Affi
   const uint32_t block_base = blockIdx.x * (kAffBlock * kAffT);
   if (block_base >= npairs) return;
   const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-  uint8_t* row_pq = smem + L::kPQ + (size_t)t * L::kPairBytes;
+  uint8_t* row_x = smem + L::kX + (size_t)t * 2 * sizeof(F);
+  uint8_t* row_y = smem + L::kY + (size_t)t * 2 * sizeof(F);
   uint8_t* row_pre = smem + L::kPre + (size_t)t * sizeof(F);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar) + warp;
   const bool leaves = a.round == 1;
@@ -425,16 +436,23 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(Affi
   auto issue = [&](uint32_t p, uint2 ids) {
     if (leaves) {   // per-thread gathers
       if (p < npairs) {
-        if (ids.x != kNoEntry) tma::cp_async<(int)sizeof(Affine<F>)>(row_pq, &a.table[ids.x >> 1]);
-        if (ids.y != kNoEntry) tma::cp_async<(int)sizeof(Affine<F>)>(row_pq + sizeof(Affine<F>), &a.table[ids.y >> 1]);
+        if (ids.x != kNoEntry) {
+          tma::cp_async<(int)sizeof(F)>(row_x, &a.table[ids.x >> 1].x);
+          tma::cp_async<(int)sizeof(F)>(row_y, &a.table[ids.x >> 1].y);
+        }
+        if (ids.y != kNoEntry) {
+          tma::cp_async<(int)sizeof(F)>(row_x + sizeof(F), &a.table[ids.y >> 1].x);
+          tma::cp_async<(int)sizeof(F)>(row_y + sizeof(F), &a.table[ids.y >> 1].y);
+        }
         tma::cp_async<(int)sizeof(F)>(row_pre, &a.pre[p]);
       }
       tma::cp_async_commit();
-    } else if (lane == 0) {   // one lane per warp: two bulk copies for the warp's 32 contiguous pairs
+    } else if (lane == 0) {   // one lane per warp: three bulk copies for the warp's 32 contiguous pairs (x's, y's, prefix products)
       uint32_t valid = p < npairs ? (npairs - p < 32u ? npairs - p : 32u) : 0u;
       tma::mbar_arrive_expect_tx(bar, valid * (L::kPairBytes + (uint32_t)sizeof(F)));
       if (valid) {
-        tma::bulk_g2s(row_pq, &a.prev[2 * (size_t)p], valid * L::kPairBytes, bar);
+        tma::bulk_g2s(row_x, &a.prev.x[2 * (size_t)p], valid * 2 * (uint32_t)sizeof(F), bar);
+        tma::bulk_g2s(row_y, &a.prev.y[2 * (size_t)p], valid * 2 * (uint32_t)sizeof(F), bar);
         tma::bulk_g2s(row_pre, &a.pre[p], valid * (uint32_t)sizeof(F), bar);
       }
     }
@@ -463,13 +481,13 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(Affi
     if (live) {
       const bool has_p = !leaves || ids_cur.x != kNoEntry, has_q = !leaves || ids_cur.y != kNoEntry;
       if (has_p) {
-        P.x = tma::ld_row(row_pq, (F*)nullptr);
-        P.y = tma::ld_row(row_pq + sizeof(F), (F*)nullptr);
+        P.x = tma::ld_row(row_x, (F*)nullptr);
+        P.y = tma::ld_row(row_y, (F*)nullptr);
         if (leaves && (ids_cur.x & 1) && !P.is_inf()) P.y = P.y.neg();
       }
       if (has_q) {
-        Q.x = tma::ld_row(row_pq + sizeof(Affine<F>), (F*)nullptr);
-        Q.y = tma::ld_row(row_pq + sizeof(Affine<F>) + sizeof(F), (F*)nullptr);
+        Q.x = tma::ld_row(row_x + sizeof(F), (F*)nullptr);
+        Q.y = tma::ld_row(row_y + sizeof(F), (F*)nullptr);
         if (leaves && (ids_cur.y & 1) && !Q.is_inf()) Q.y = Q.y.neg();
       }
       pre = tma::ld_row(row_pre, (F*)nullptr);
@@ -495,14 +513,15 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(Affi
     } else {
       Rr = P.is_inf() ? Q : (Q.is_inf() ? P : Affine<F>::inf());
     }
-    a.out[p] = Rr;
+    a.out.x[p] = Rr.x;
+    a.out.y[p] = Rr.y;
   }
 }
 
 // buckets[b-1] = sum of the (affine) slice results of bucket b.
 template <class F>
 __global__ void __launch_bounds__(128)
-k_merge_slices_affine(const Affine<F>* __restrict__ slice_pts, SliceTables st, uint32_t nbuckets,
+k_merge_slices_affine(NodeBuf<F> slice_pts, SliceTables st, uint32_t nbuckets,
                       XYZZ<F>* __restrict__ buckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
   uint32_t lane = threadIdx.x & 31;
@@ -512,7 +531,7 @@ k_merge_slices_affine(const Affine<F>* __restrict__ slice_pts, SliceTables st, u
     cnt = st.slice_off[b + 1] - first;
     if (cnt <= 12) {  // the common case: a handful of slices per bucket
       XYZZ<F> acc = XYZZ<F>::inf();
-      for (uint32_t k = 0; k < cnt; k++) xyzz_madd(acc, ld_affine(&slice_pts[first + k]));
+      for (uint32_t k = 0; k < cnt; k++) xyzz_madd(acc, Affine<F>{ld_fe(&slice_pts.x[first + k]), ld_fe(&slice_pts.y[first + k])});
       buckets[b - 1] = acc;
     }
   }
@@ -523,7 +542,7 @@ k_merge_slices_affine(const Affine<F>* __restrict__ slice_pts, SliceTables st, u
     uint32_t f = __shfl_sync(0xffffffffu, first, j), c = __shfl_sync(0xffffffffu, cnt, j);
     uint32_t bj = __shfl_sync(0xffffffffu, b, j);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lane; k < c; k += 32) xyzz_madd(acc, ld_affine(&slice_pts[f + k]));
+    for (uint32_t k = lane; k < c; k += 32) xyzz_madd(acc, Affine<F>{ld_fe(&slice_pts.x[f + k]), ld_fe(&slice_pts.y[f + k])});
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       XYZZ<F> other = shfl_down_struct(acc, off, 32);

@@ -428,8 +428,10 @@ int msm_buckets(Bases* b, const SortScratch& ss, size_t n_terms, XYZZ<F>* d_out,
     ar.others = b->aff_others.as<F>();
     ar.btot = b->aff_btot.as<F>();
     ar.pair_ids = g_tma_staging == 1 ? b->aff_ids.as<uint2>() : nullptr;
-    Affine<F>* bufs[2] = {b->nodeA.as<Affine<F>>(), b->nodeB.as<Affine<F>>()};
-    const Affine<F>* prev = nullptr;
+    // node buffers, x- and y-coordinates in separate halves (bucket_affine.cuh NodeBuf)
+    const size_t capA = (size_t)ss.max_slices * (S / 2), capB = (size_t)ss.max_slices * (S / 4 ? S / 4 : 1);
+    NodeBuf<F> bufs[2] = {{b->nodeA.as<F>(), b->nodeA.as<F>() + capA}, {b->nodeB.as<F>(), b->nodeB.as<F>() + capB}};
+    NodeBuf<F> prev{nullptr, nullptr};
     // all R rounds affine: inside a proof the per-round inversion latency is hidden by the other MSMs' streams
     for (uint32_t r = 1; r <= R; r++) {
       ar.round = r;

@@ -179,7 +179,8 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
     table[i].y = load_std<F>(table_std + (size_t)i * 2 * W + W);
   }
   const uint32_t S = 1u << R;
-  std::vector<Affine<F>> bufA((size_t)nslices * (S / 2)), bufB((size_t)nslices * (S / 2));
+  const size_t cap = (size_t)nslices * (S / 2);
+  std::vector<F> bufA(2 * cap), bufB(2 * cap);        // x-coordinates in the first half, y-coordinates in the second (NodeBuf)
   std::vector<F> pre((size_t)nslices * (S / 2));
   std::vector<uint2> ids((size_t)nslices * (S / 2));
   unsigned nb_max = (nslices * (S / 2) + kAffBlock * T - 1) / (kAffBlock * T);
@@ -194,8 +195,8 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
   ar.others = others.data();
   ar.btot = btot.data();
   ar.pair_ids = ids.data();
-  const Affine<F>* prev = nullptr;
-  Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
+  NodeBuf<F> prev{nullptr, nullptr};
+  NodeBuf<F> bufs[2] = {{bufA.data(), bufA.data() + cap}, {bufB.data(), bufB.data() + cap}};
   for (uint32_t r = 1; r <= R; r++) {
     ar.round = r;
     ar.q_log = R - r;
@@ -223,8 +224,8 @@ int affine_rounds(int variant, int fwd_variant, const uint32_t* table_std, uint3
     prev = ar.out;
   }
   for (uint32_t s = 0; s < nslices; s++) {
-    store_std(out_std + (size_t)s * 2 * W, prev[s].x);
-    store_std(out_std + (size_t)s * 2 * W + W, prev[s].y);
+    store_std(out_std + (size_t)s * 2 * W, prev.x[s]);
+    store_std(out_std + (size_t)s * 2 * W + W, prev.y[s]);
   }
   return 0;
 }
@@ -235,15 +236,16 @@ template <class F>
 int msm_tail(const uint32_t* slice_pts_std, const uint32_t* slice_off, uint32_t nbuckets, uint32_t seg, uint32_t* out_std) {
   constexpr int W = sizeof(F) / 4;
   uint32_t nsl = slice_off[nbuckets + 1];
-  std::vector<Affine<F>> pts(nsl ? nsl : 1);
+  const size_t cap_t = nsl ? nsl : 1;
+  std::vector<F> pts(2 * cap_t);
   for (uint32_t i = 0; i < nsl; i++) {
-    pts[i].x = load_std<F>(slice_pts_std + (size_t)i * 2 * W);
-    pts[i].y = load_std<F>(slice_pts_std + (size_t)i * 2 * W + W);
+    pts[i] = load_std<F>(slice_pts_std + (size_t)i * 2 * W);
+    pts[cap_t + i] = load_std<F>(slice_pts_std + (size_t)i * 2 * W + W);
   }
   std::vector<XYZZ<F>> buckets(nbuckets);
   SliceTables st{const_cast<uint32_t*>(slice_off), nullptr, nullptr};
   unsigned nb = (nbuckets + 127) / 128;
-  for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_merge_slices_affine<F>(pts.data(), st, nbuckets, buckets.data()); });
+  for (unsigned b = 0; b < nb; b++) run_cta(b, 128, nb, [&] { k_merge_slices_affine<F>(NodeBuf<F>{pts.data(), pts.data() + cap_t}, st, nbuckets, buckets.data()); });
   XYZZ<F> total;
   if (seg == 0) {   // the rows / columns + bit planes + Horner tail (nbuckets = 2^(c-1)), as launch_bucket_tail issues it
     uint32_t bits = 0;
@@ -339,7 +341,8 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     uint32_t R = 0;
     while ((1u << R) < S) R++;
     constexpr int T = 8;
-    std::vector<Affine<F>> bufA((size_t)nslices * (S / 2) + 1), bufB((size_t)nslices * (S / 2) + 1);
+    const size_t cap = (size_t)nslices * (S / 2) + 1;
+    std::vector<F> bufA(2 * cap), bufB(2 * cap);      // x | y halves (NodeBuf)
     std::vector<F> pre((size_t)nslices * (S / 2) + 1);
     std::vector<uint2> ids((size_t)nslices * (S / 2) + 1);
     unsigned nb_max = cdiv((size_t)nslices * (S / 2), kAffBlock * T) + 1;
@@ -354,8 +357,8 @@ int msm_full(const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, u
     ar.others = others.data();
     ar.btot = btot.data();
     ar.pair_ids = ids.data();
-    const Affine<F>* prev = nullptr;
-    Affine<F>* bufs[2] = {bufA.data(), bufB.data()};
+    NodeBuf<F> prev{nullptr, nullptr};
+    NodeBuf<F> bufs[2] = {{bufA.data(), bufA.data() + cap}, {bufB.data(), bufB.data() + cap}};
     for (uint32_t r = 1; r <= R; r++) {
       ar.round = r;
       ar.q_log = R - r;
