@@ -462,7 +462,9 @@ def run_prove(args, c):
             else:
                 ranges.append((lo, hi))
     needs_px = bool(info[8])
-    h2d_bytes = (32 * m + (0 if qap else 32 * npx)) if world == 1 else (sum(32 * (hi - lo) for lo, hi in ranges) + (32 * npx if needs_px else 0))
+    # the library stages only the top len(px) - len(Z) + 1 = n - 1 coefficients of px (all the quotient depends on; csrc/prove_host.cuh)
+    px_staged = npx - n
+    h2d_bytes = (32 * m + (0 if qap else 32 * px_staged)) if world == 1 else (sum(32 * (hi - lo) for lo, hi in ranges) + (32 * px_staged if needs_px else 0))
 
     # ---- correctness of what we time (every step function): proof == the known-discrete-log expectation
     from oracle import ref_py as o          # checker only
@@ -610,8 +612,9 @@ def run_prove(args, c):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 384,
                 "proofs_in_flight": n_fly, "one_at_a_time_ms_per_step": e2e_one_ms,
                 "note": ("b200_groth16_prove_witness: pinned witness in, px computed on the device, proof out" if qap else
-                         "the host-pointer C ABI call b200_groth16_prove on every rank (pinned witness and px in, proof out); at N > 1 "
-                         "each rank stages only the witness ranges it reads (+ px on ranks holding PowersTauDelta) and the NCCL "
+                         "the host-pointer C ABI call b200_groth16_prove on every rank (pinned witness and px in, proof out; of px only the top "
+                         "len(px) - len(Z) + 1 coefficients cross PCIe: the quotient depends on nothing else); at N > 1 "
+                         "each rank stages only the witness ranges it reads (+ the top n - 1 coefficients of px on ranks holding PowersTauDelta) and the NCCL "
                          "all-gather of the 1 KB partial records runs inside the library; h2d bytes are rank 0's")},
         "gpu_launches": int(prof[6]),
         "clocks": clk,

@@ -582,6 +582,7 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
     return fail(B200_EINVAL, "groth16_prove: sharded key (rank %d/%d) without a matching communicator: call b200_comm_init, "
                              "or use b200_groth16_prove_device + b200_groth16_finalize_device around your own all-gather",
                 pk->rank, pk->world);
+  if (npx < pk->Z.nb) return fail(B200_EINVAL, "groth16_prove: len(px) < len(Z)");
   cudaStream_t st = pk->main();   // context 1 keys: their own main stream (a second host thread's proof in flight)
   CU(pk->px.ensure(npx * sizeof(Fr)));
   CU(pk->w_stage.ensure(nw * sizeof(Fr)));
@@ -608,7 +609,14 @@ int groth16_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* px,
   // px is only needed by the division on side stream 3: copy it there so the transfer overlaps the sort of w
   // (same-stream order makes the division see it; the previous proof's use of pk->px finished before its combine)
   // (measurement mode runs the division on `st`, so the copy goes there too)
-  if (need_px) CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, g_serial ? st : pk->side()[2]));
+  // Only the TOP len(px) - len(Z) + 1 coefficients are staged: the quotient of the division depends on nothing else
+  // (poly_div_device reads rev(px) mod x^nq; the remainder is never formed on the prove path) — at 2^20 constraints that
+  // is 32 MB over PCIe instead of 64 MB.  They land at their own offset, so the device layout of px is unchanged.
+  if (need_px) {
+    const size_t px_off = pk->Z.nb - 1;
+    CU(cudaMemcpyAsync(pk->px.as<Fr>() + px_off, reinterpret_cast<const Fr*>(px) + px_off, (npx - px_off) * sizeof(Fr),
+                       cudaMemcpyHostToDevice, g_serial ? st : pk->side()[2]));
+  }
   Fq* o = pk->out_std.as<Fq>();
   int rc = groth16_enqueue(pk, pk->w_stage.as<Fr>(), nw, pk->px.as<Fr>(), npx, r, s, o, st);
   if (rc) return rc;
@@ -723,7 +731,8 @@ int pinocchio_prove(b200_pk_t h, const uint64_t* w, size_t nw, const uint64_t* p
   CU(cudaMemsetAsync(res, 0, kPinRecordBytes, st));        // slots this rank does not own stay at infinity
   if (pk->g[7]) {
     CU(pk->px.ensure(npx * sizeof(Fr)));
-    CU(cudaMemcpyAsync(pk->px.p, px, npx * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    const size_t px_off = pk->Z.nb - 1;   // the top nq coefficients are all the division reads (see groth16_prove)
+    CU(cudaMemcpyAsync(pk->px.as<Fr>() + px_off, reinterpret_cast<const Fr*>(px) + px_off, nq * sizeof(Fr), cudaMemcpyHostToDevice, st));
   }
   EV_REC(e_in, st);
   int rc;

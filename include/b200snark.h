@@ -147,7 +147,9 @@ int b200_groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t*
  * supplied by the caller (the Go shim draws them with Fq.Rand, fields/fq.go:116-132,
  * exactly as the reference does at groth16.go:231-238).  w: nw = NVars witness
  * scalars (|w_i| mod r); px: npx coefficients.  Outputs are Jacobian points (Z != 1
- * in general, like the reference's own), standard form.                           */
+ * in general, like the reference's own), standard form.  Like DivisorPolynomial
+ * (r1csqap.go:213-216: quotient kept, remainder dropped) the proof depends only on the
+ * top npx - len(Z) + 1 coefficients of px; only those are read from the host buffer. */
 int b200_groth16_prove(b200_pk_t pk, const uint64_t* w, size_t nw, const uint64_t* px, size_t npx,
                        const uint64_t r[4], const uint64_t s[4], uint64_t pi_a[12], uint64_t pi_b[24],
                        uint64_t pi_c[12]);

@@ -161,6 +161,31 @@ def test_prove_argument_errors(mods, golden_dir):
     assert affeq(G1, ok["PiC"], ref["PiC"]) and affeq(G1, ok["PiA"], ref["PiA"])
 
 
+def test_proofs_depend_only_on_the_quotient_of_px(mods, golden_dir):
+    """hx = DivisorPolynomial(px, Z) keeps the quotient and drops the remainder (r1csqap.go:213-216), and the quotient is
+    fixed by the top len(px) - len(Z) + 1 coefficients of px — the only ones the host-pointer entry points stage over
+    PCIe (csrc/prove_host.cuh).  A px whose LOW coefficients are garbage (not a multiple of Z any more) must therefore
+    give the same proof, on the device and in the oracle's restatement of the reference's long division."""
+    groth16, snark = mods
+    g = load(golden_dir, "gobin_chain21.json")
+    cc = g["compiledcircuit"]
+    px = list(g["px"])
+    nq = len(px) - len(g["groth16_setup"]["Pk"]["Z"]) + 1
+    rng = random.Random(7)
+    bad = [rng.randrange(o.R) for _ in range(len(px) - nq)] + px[len(px) - nq:]
+    assert bad != px and len(bad) == len(px)
+    pk = groth_pk(g["groth16_setup"])
+    got = groth16.GenerateProofs(cc, pk, g["witness"], bad, r=11, s=13)
+    for ref_px in (px, bad):
+        exp, _ = o.groth16_prove(cc["NVars"], cc["NPublic"], pk, g["witness"], ref_px, 11, 13)
+        assert affeq(G1, got["PiA"], exp["PiA"]) and affeq(G2, got["PiB"], exp["PiB"]) and affeq(G1, got["PiC"], exp["PiC"])
+    ppk = pinocchio_pk(g["pinocchio_setup"])
+    nq_p = len(px) - len(ppk["Z"]) + 1
+    bad_p = [rng.randrange(o.R) for _ in range(len(px) - nq_p)] + px[len(px) - nq_p:]
+    proof = snark.GenerateProofs(cc, ppk, g["witness"], bad_p)
+    assert affeq(G1, proof["PiH"], t3(g["pinocchio_proofs"]["PiH"]))
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("logn", [12, 16])
