@@ -88,6 +88,17 @@ def build_host_kernels(force=False):
     return target
 
 
+def build_shard_partition(force=False):
+    """g++ build of csrc/shard_partition.h behind a C entry point (CPU test vehicle, tests/test_shard_partition.py)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    target = os.path.join(LIBDIR, "libb200_shard_partition.so")
+    srcs = [os.path.join(HOSTTEST, "shard_partition_test.cpp"), os.path.join(CSRC, "shard_partition.h")]
+    if not force and not _newer(target, srcs):
+        return target
+    _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, "-o", target, srcs[0]])
+    return target
+
+
 def build_oracle(force=False):
     out = os.path.join(ORACLE, "_build")
     os.makedirs(out, exist_ok=True)

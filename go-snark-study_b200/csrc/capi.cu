@@ -21,6 +21,7 @@
 #include "qap.cuh"
 #include "qap_sparse.cuh"
 #include "comm.cuh"
+#include "shard_partition.h"
 #ifndef B200_NO_PAIRING
 #include "pairing.cuh"
 #include "pairing_warp.cuh"
@@ -53,6 +54,7 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 int g_acc_mode = 0;
 // partition tuning (b200_config keys 10..13; defaults = the measured best, profiles/r2_notes.md §8)
 int g_w_ab = 100, g_w_g2 = 280, g_aff_min_g1 = 700000, g_aff_min_g2 = 400000;
+int g_phase_cost = 0;    // B200_CFG_SHARD_PHASE_COST: fixed cost of a piece of a sharded key, in G1 terms (shard_partition.h)
 int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
@@ -883,29 +885,30 @@ __global__ void __launch_bounds__(128) k_groth16_verify(const Fq* pts1, const Fq
     if (lane == 0) *ok = all == 0xffffffffu ? 1 : 0;
   }
 }
-// icPubl = IC[0] + sum publicSignals[i] * IC[i+1], reference order and formulas (groth16.go:283-286)
-__global__ void k_ic_publ(const Fq* ic, const Fr* sig, size_t npub, Fq* out, int* err) {
+// icPubl = IC[0] + sum publicSignals[i] * IC[i+1] (groth16.go:283-286).  The products are independent: one half-warp each,
+// with the GLV split of prove_host.cuh (128 doublings + ~12 additions deep instead of the 254 + ~127 of MulScalar's
+// double-and-add; the same group element, which is all the pairing — it normalises its inputs — can see); the sum then runs
+// in the reference's order with the reference's Add, so its degenerate cases (equal operands give Z = 0) are the reference's.
+struct GlvScalar {
+  uint64_t k[4];
+  uint32_t neg[2];
+};
+__global__ void __launch_bounds__(32) k_ic_terms(const Fq* ic, const GlvScalar* gs, size_t npub, Jacobian<Fq>* terms, int* err) {
+  const uint32_t t = threadIdx.x & 31u;
+  const size_t i = (size_t)blockIdx.x * 2 + (t >> 4);
+  const size_t ii = i < npub ? i : npub - 1;   // an odd count leaves the last half-warp a duplicate: every lane joins the shuffles
+  const Fq* src = ic + 3 * (ii + 1);
+  if (src[0].geq_modulus() || src[1].geq_modulus() || src[2].geq_modulus()) atomicOr(err, 1);
+  Jacobian<Fq> p{src[0].to_mont(), src[1].to_mont(), src[2].to_mont()};
+  GlvScalar g = gs[ii];
+  Jacobian<Fq> r = glv_mul_halfwarp(p, g.k, g.neg, t);
+  if (i < npub && (t & 15u) == 0) terms[i] = r;
+}
+__global__ void k_ic_sum(const Fq* ic, const Jacobian<Fq>* terms, size_t npub, Fq* out, int* err) {
   if (threadIdx.x | blockIdx.x) return;
-  for (size_t i = 0; i < 3 * (npub + 1); i++)
-    if (ic[i].geq_modulus()) atomicOr(err, 1);
-  for (size_t i = 0; i < npub; i++)
-    if (sig[i].geq_modulus()) atomicOr(err, 2);
+  if (ic[0].geq_modulus() || ic[1].geq_modulus() || ic[2].geq_modulus()) atomicOr(err, 1);
   Jacobian<Fq> acc{ic[0].to_mont(), ic[1].to_mont(), ic[2].to_mont()};
-  for (size_t i = 0; i < npub; i++) {
-    Jacobian<Fq> p{ic[3 * (i + 1)].to_mont(), ic[3 * (i + 1) + 1].to_mont(), ic[3 * (i + 1) + 2].to_mont()};
-    Fr s = sig[i];
-    Jacobian<Fq> q = Jacobian<Fq>::inf();
-    bool started = false;
-    for (int w = 7; w >= 0; w--)
-      for (int b = 31; b >= 0; b--) {
-        uint32_t bit = (s.l[w] >> b) & 1;
-        if (!started && !bit) continue;
-        started = true;
-        q = jac_double_ref(q);
-        if (bit) q = jac_add_ref(q, p);
-      }
-    acc = jac_add_ref(acc, q);
-  }
+  for (size_t i = 0; i < npub; i++) acc = jac_add_ref(acc, terms[i]);
   out[0] = acc.X.from_mont();
   out[1] = acc.Y.from_mont();
   out[2] = acc.Z.from_mont();
@@ -957,15 +960,23 @@ int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1,
   if (!ic || !alpha1 || !beta2 || !gamma2 || !delta2 || !pi_a || !pi_b || !pi_c || !ok || (npub && !pub))
     return fail(B200_EINVAL, "groth16_verify: null pointer");
   if (n_ic < npub + 1) return fail(B200_EINVAL, "groth16_verify: len(IC) < len(publicSignals) + 1");
-  DevBuf dic, dsig, d1, d2, dok;
+  // GLV split of every public signal on the host (they are the caller's host scalars anyway)
+  std::vector<GlvScalar> gs(npub ? npub : 1);
+  for (size_t i = 0; i < npub; i++) {
+    Fr v = fr_load_std(pub + 4 * i);
+    if (v.geq_modulus()) return fail(B200_ERANGE, "groth16_verify: scalar / coefficient >= r");
+    if (glv_decompose(v, gs[i].k, gs[i].neg)) return fail(B200_EINVAL, "groth16_verify: GLV decomposition out of range");
+  }
+  DevBuf dic, dsig, dterms, d1, d2, dok;
   CU(dic.alloc(n_ic * 3 * sizeof(Fq)));
-  CU(dsig.alloc((npub ? npub : 1) * sizeof(Fr)));
+  CU(dsig.alloc(gs.size() * sizeof(GlvScalar)));
+  CU(dterms.alloc(gs.size() * sizeof(Jacobian<Fq>)));
   CU(d1.alloc(4 * 3 * sizeof(Fq)));
   CU(d2.alloc(4 * 3 * sizeof(Fq2)));
   CU(dok.alloc(sizeof(int)));
   cudaStream_t st = g_stream;
   CU(cudaMemcpyAsync(dic.p, ic, n_ic * 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
-  if (npub) CU(cudaMemcpyAsync(dsig.p, pub, npub * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  if (npub) CU(cudaMemcpyAsync(dsig.p, gs.data(), npub * sizeof(GlvScalar), cudaMemcpyHostToDevice, st));
   Fq* p1 = d1.as<Fq>();
   Fq2* p2 = d2.as<Fq2>();
   CU(cudaMemcpyAsync(p1, pi_a, 3 * sizeof(Fq), cudaMemcpyHostToDevice, st));
@@ -975,7 +986,8 @@ int groth16_verify_host(const uint64_t* ic, size_t n_ic, const uint64_t* alpha1,
   CU(cudaMemcpyAsync(p2 + 3, beta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(p2 + 6, gamma2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(p2 + 9, delta2, 3 * sizeof(Fq2), cudaMemcpyHostToDevice, st));
-  k_ic_publ<<<1, 32, 0, st>>>(dic.as<Fq>(), dsig.as<Fr>(), npub, p1 + 6, g_d_err);
+  if (npub) k_ic_terms<<<(unsigned)((npub + 1) / 2), 32, 0, st>>>(dic.as<Fq>(), dsig.as<GlvScalar>(), npub, dterms.as<Jacobian<Fq>>(), g_d_err);
+  k_ic_sum<<<1, 32, 0, st>>>(dic.as<Fq>(), dterms.as<Jacobian<Fq>>(), npub, p1 + 6, g_d_err);
   k_groth16_verify<<<1, 128, 0, st>>>(p1, p2, dok.as<int>(), g_d_err);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1276,6 +1288,10 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
+    return B200_OK;
+  }
+  if (key == B200_CFG_SHARD_PHASE_COST && value >= 0 && value <= (1 << 24)) {
+    g_phase_cost = value;
     return B200_OK;
   }
   if (key >= 10 && key <= 13 && value > 0) {   // shard-partition tuning (tools/shard_times.py sweeps them)

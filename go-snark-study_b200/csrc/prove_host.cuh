@@ -176,19 +176,15 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   // also pay the two GLV products s*A_part + r*B1_part (1 ms of single-warp latency) on their critical path when sharded.
   const double w_ab = world > 1 ? g_w_ab / 100.0 : 1.0;
   const double wgt[4] = {w_ab, w_ab, g_w_g2 / 100.0, 1.0};
-  double off[5] = {0, 0, 0, 0, 0};
-  for (int k = 0; k < 4; k++) off[k + 1] = off[k] + wgt[k] * (double)len[k];
-  auto cut = [&](int g, int k) -> size_t {   // first index of set k at or after the g-th cut of the line
-    double pos = off[4] * (double)g / (double)world;
-    double x = (pos - off[k]) / wgt[k];
-    if (g >= world) return len[k];
-    if (x <= 0) return 0;
-    if (x >= (double)len[k]) return len[k];
-    return (size_t)x;
-  };
+  // Fixed cost of every piece a rank holds (its own sort, slice merge and bucket tail), in the same unit; a G2 piece's tail
+  // costs about twice a G1 piece's (profiles/r2_notes.md section 8).  0 = equal pieces of the weighted line (shard_partition.h).
+  const double f_phase = world > 1 ? (double)g_phase_cost : 0.0;
+  const double fix[4] = {f_phase, f_phase, 2.0 * f_phase, f_phase};
+  std::vector<ShardCut> cuts((size_t)world);
+  shard_partition(len, wgt, fix, world, cuts.data());
   for (int k = 0; k < 4; k++) {
-    pk->lo[k] = cut(rank, k);
-    pk->hi[k] = cut(rank + 1, k);
+    pk->lo[k] = cuts[(size_t)rank].lo[k];
+    pk->hi[k] = cuts[(size_t)rank].hi[k];
     pk->tail[k] = pk->hi[k] == len[k] && (pk->lo[k] < pk->hi[k] || (rank == world - 1 && len[k] == 0));
   }
   // a set whose end falls exactly on a cut: the rank holding its last element owns the tail (checked above);
@@ -291,15 +287,14 @@ __device__ Jacobian<Fq> jac_add_complete(const Jacobian<Fq>& a, const Jacobian<F
   return r;
 }
 
-// One warp, all 32 lanes: lanes 0..15 -> prod[0] = s*A, lanes 16..31 -> prod[1] = r*B1 (res layout as in k_groth16_finalize).
-// Inside a product, lanes 0..7 take the eight 16-bit chunks of |k1| on P and lanes 8..15 those of |k2| on phi(P): a chunk is
-// 16 doublings + <= 16 additions, lane q then shifts by 16 q doublings, and a 3-level shuffle tree + one addition join the
-// sixteen partial products.  Depth: 128 Jacobian doublings + ~12 additions (the doublings are the floor of any
-// double-and-add on a 128-bit GLV half), against 128 + ~36 with four 64-bit chunks.
-__global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* prod) {
-  const uint32_t t = threadIdx.x & 31u;
-  const uint32_t grp = t >> 4, half = (t >> 3) & 1u, q = t & 7u;
-  Jacobian<Fq> p = xyzz_to_jacobian(*reinterpret_cast<const XYZZ<Fq>*>(res + (grp ? 256 : 0)));
+// k * P by the sixteen lanes of a half-warp (lanes t with the same t >> 4; ALL 32 lanes of the warp must call).  k1 = k[0..1],
+// k2 = k[2..3], signs in neg[0..1].  Lanes 0..7 of the half take the eight 16-bit chunks of |k1| on P and lanes 8..15 those of
+// |k2| on phi(P): a chunk is 16 doublings + <= 16 additions, lane q then shifts by 16 q doublings, and a 3-level shuffle tree
+// + one addition join the sixteen partial products.  Depth: 128 Jacobian doublings + ~12 additions (the doublings are the
+// floor of any double-and-add on a 128-bit GLV half), against 128 + ~36 with four 64-bit chunks.  The product is returned
+// in the half's first lane (t & 15 == 0); P at infinity or k = 0 give the point at infinity.
+__device__ Jacobian<Fq> glv_mul_halfwarp(Jacobian<Fq> p, const uint64_t k[4], const uint32_t neg[2], uint32_t t) {
+  const uint32_t half = (t >> 3) & 1u, q = t & 7u;
   if (half) {  // phi(P): x -> beta * x
     Fq beta;
     const uint32_t bm[8] = {0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu, 0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du};
@@ -307,8 +302,8 @@ __global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* p
     for (int i = 0; i < 8; i++) beta.l[i] = bm[i];
     p.X = p.X * beta;
   }
-  if (g.neg[grp][half]) p.Y = p.Y.neg();
-  const uint64_t word = g.k[grp][2 * half + (q >> 2)];
+  if (neg[half]) p.Y = p.Y.neg();
+  const uint64_t word = k[2 * half + (q >> 2)];
   const uint32_t chunk = (uint32_t)(word >> (16 * (q & 3u))) & 0xffffu;
   Jacobian<Fq> r = Jacobian<Fq>::inf();
   bool started = false;
@@ -328,10 +323,17 @@ __global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* p
     if ((int)q < off) r = jac_add_complete(r, other);
   }
   Jacobian<Fq> k2part = shfl_jac(r, (int)((t & ~15u) + 8));
-  if ((t & 15u) == 0) {
-    r = jac_add_complete(r, k2part);
-    prod[grp] = jacobian_to_xyzz(r);
-  }
+  if ((t & 15u) == 0) r = jac_add_complete(r, k2part);
+  return r;
+}
+
+// One warp, all 32 lanes: lanes 0..15 -> prod[0] = s*A, lanes 16..31 -> prod[1] = r*B1 (res layout as in k_groth16_finalize).
+__global__ void k_groth16_products(const uint8_t* res, GlvScalars g, XYZZ<Fq>* prod) {
+  const uint32_t t = threadIdx.x & 31u;
+  const uint32_t grp = t >> 4;
+  Jacobian<Fq> p = xyzz_to_jacobian(*reinterpret_cast<const XYZZ<Fq>*>(res + (grp ? 256 : 0)));
+  Jacobian<Fq> r = glv_mul_halfwarp(p, g.k[grp], g.neg[grp], t);
+  if ((t & 15u) == 0) prod[grp] = jacobian_to_xyzz(r);
 }
 __global__ void k_groth16_combine(const uint8_t* res, const XYZZ<Fq>* prod, Fq* out_a, Fq* out_c, Fq2* out_b) {
   uint32_t t = threadIdx.x;

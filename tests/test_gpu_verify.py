@@ -90,6 +90,32 @@ def test_minimal_flow_all_gpu(mods):
         groth16.VerifyProof(setup["Vk"], proof, [35, 1, 2])              # more signals than IC entries
 
 
+def test_verify_many_public_signals_edge_values(mods):
+    """icPubl = IC[0] + sum publicSignals[i]*IC[i+1] (groth16.go:283-286) with eight signals — 0, 1, r-1, 2^128-ish values on
+    either side of the GLV split, random full-width ones — on a verification key and proof built from known discrete logs
+    so that e(A,B) == e(alpha,beta) * e(icPubl,gamma) * e(C,delta) holds exactly: accepted (device and oracle), rejected
+    when any one signal moves, and an odd signal count exercises the half-empty warp of k_ic_terms."""
+    _, groth16, _ = mods
+    rng = random.Random(77)
+    rnd = lambda: rng.randrange(1, R)
+    for pubs in ([0, 1, R - 1, (1 << 128) - 1, 1 << 128, rnd(), rnd(), rnd()], [rnd(), 0, rnd()], [R - 2]):
+        al, be, ga, de, a, b = (rnd() for _ in range(6))
+        ic = [rnd() for _ in range(len(pubs) + 1)]
+        ic_pub = (ic[0] + sum(p * k for p, k in zip(pubs, ic[1:]))) % R
+        c = (a * b - al * be - ic_pub * ga) * pow(de, -1, R) % R
+        g1 = lambda k: G1.mul_scalar(G1.G, k)
+        g2 = lambda k: G2.mul_scalar(G2.G, k)
+        vk = {"IC": [g1(k) for k in ic], "G1": {"Alpha": g1(al)}, "G2": {"Beta": g2(be), "Gamma": g2(ga), "Delta": g2(de)}}
+        proof = {"PiA": g1(a), "PiB": g2(b), "PiC": g1(c)}
+        assert groth16.VerifyProof(vk, proof, pubs)
+        for j in range(len(pubs)):
+            moved = list(pubs)
+            moved[j] = (moved[j] + 1) % R
+            assert not groth16.VerifyProof(vk, proof, moved), j
+        assert groth16.VerifyProof(vk, proof, [p + R for p in pubs])          # publicSignals are taken mod r (MulScalar of a big.Int)
+    assert o.groth16_verify(vk, proof, pubs)
+
+
 def test_fq12_mul_batch(mods):
     """fields/fq12.go:72-84 on the device, against the oracle (random elements and the identity)."""
     bn, _, _ = mods
