@@ -247,7 +247,8 @@ def make_config(args, logn, world):
         "in_flight_note": "independent proofs / MSMs the GPU arm keeps in flight (own key objects, streams, outputs); the K timed steps "
                           "are K complete proofs either way, and the one-at-a-time figures are reported beside `value` and `e2e`"}
     return {"workload": wl, "constraints" if args.workload == "prove" else "n": n, **fly,
-            "parallelism": (f"msm-cost-shard x{world}, all-gather inside libb200snark" if args.workload == "prove" else
+            "parallelism": ((f"msm-cost-shard x{world}" + (" (A / B1 term 0.85, G2 term 2.75 of a C||PTD term)" if not args.with_qap and args.in_flight > 1 else "")
+                             + ", all-gather inside libb200snark") if args.workload == "prove" else
                             f"index-shard x{world}") if world > 1 else "single-gpu",
             "l2": "inputs larger than L2 (>= 1 GB of precomputed CRS tables gathered per MSM)"}
 
@@ -414,6 +415,10 @@ def run_prove(args, c):
     if n_fly > 1 and world > 1:    # latency hidden by the second proof: every shard takes the batched-affine tree (6 vs 10 multiplies per add)
         check(L.b200_config(_lib.CFG_SHARD_AFFINE_MIN_G1, 1))
         check(L.b200_config(_lib.CFG_SHARD_AFFINE_MIN_G2, 1))
+        # partition weights for that mode (profiles/r2_notes.md section 16, every rank of the 2 / 4 / 8-way split timed on one GPU):
+        # the C||PTD ranks also run the division, so their terms weigh more — A / B1 terms 0.85, G2 terms 2.75 of a C||PTD term
+        check(L.b200_config(_lib.CFG_SHARD_W_AB, 85))
+        check(L.b200_config(_lib.CFG_SHARD_W_G2, 275))
     pks = []
     for k in range(n_fly):
         check(L.b200_config(_lib.CFG_PK_CONTEXT, k))

@@ -9,7 +9,6 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200snark.so")
 CFG_ACC_MODE, ACC_AUTO, ACC_AFFINE, ACC_XYZZ = 1, 0, 1, 2
 CFG_TMA_STAGING = 2
 CFG_SHARD_W_AB, CFG_SHARD_W_G2, CFG_SHARD_AFFINE_MIN_G1, CFG_SHARD_AFFINE_MIN_G2 = 10, 11, 12, 13
-CFG_SHARD_PHASE_COST = 14   # fixed cost of a piece of a sharded key, in G1 terms (csrc/shard_partition.h)
 CFG_PAIRING_KERNEL = 5  # b200_pairing_batch: 0 default (one warp per pairing), 1 one thread per pairing, 2 one warp
 CFG_PK_CONTEXT = 4    # prove context (0 / 1) of proving keys loaded afterwards: two proofs in flight
 

@@ -54,7 +54,6 @@ Comm g_comm;  // NCCL communicator of this process (b200_comm_init); world 1 = n
 int g_acc_mode = 0;
 // partition tuning (b200_config keys 10..13; defaults = the measured best, profiles/r2_notes.md §8)
 int g_w_ab = 100, g_w_g2 = 280, g_aff_min_g1 = 700000, g_aff_min_g2 = 400000;
-int g_phase_cost = 0;    // B200_CFG_SHARD_PHASE_COST: fixed cost of a piece of a sharded key, in G1 terms (shard_partition.h)
 int g_tma_staging = 0;   // B200_CFG_TMA_STAGING: 1 staged backward pass in every round, 2 only in the contiguous rounds (>= 2)
 
 // ---- instrumentation (bench.py): kernel-launch counter and optional CUDA-event
@@ -1288,10 +1287,6 @@ int b200_config(int key, int value) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (key == B200_CFG_ACC_MODE && value >= 0 && value <= 2) {
     g_acc_mode = value;
-    return B200_OK;
-  }
-  if (key == B200_CFG_SHARD_PHASE_COST && value >= 0 && value <= (1 << 24)) {
-    g_phase_cost = value;
     return B200_OK;
   }
   if (key >= 10 && key <= 13 && value > 0) {   // shard-partition tuning (tools/shard_times.py sweeps them)

@@ -176,12 +176,8 @@ int groth16_pk_load(const uint64_t* at, const uint64_t* b1, const uint64_t* b2, 
   // also pay the two GLV products s*A_part + r*B1_part (1 ms of single-warp latency) on their critical path when sharded.
   const double w_ab = world > 1 ? g_w_ab / 100.0 : 1.0;
   const double wgt[4] = {w_ab, w_ab, g_w_g2 / 100.0, 1.0};
-  // Fixed cost of every piece a rank holds (its own sort, slice merge and bucket tail), in the same unit; a G2 piece's tail
-  // costs about twice a G1 piece's (profiles/r2_notes.md section 8).  0 = equal pieces of the weighted line (shard_partition.h).
-  const double f_phase = world > 1 ? (double)g_phase_cost : 0.0;
-  const double fix[4] = {f_phase, f_phase, 2.0 * f_phase, f_phase};
   std::vector<ShardCut> cuts((size_t)world);
-  shard_partition(len, wgt, fix, world, cuts.data());
+  shard_partition(len, wgt, world, cuts.data());   // equal pieces of the weighted line (shard_partition.h)
   for (int k = 0; k < 4; k++) {
     pk->lo[k] = cuts[(size_t)rank].lo[k];
     pk->hi[k] = cuts[(size_t)rank].hi[k];

@@ -80,10 +80,6 @@ int b200_version(void);
 #define B200_CFG_SHARD_W_G2 11
 #define B200_CFG_SHARD_AFFINE_MIN_G1 12
 #define B200_CFG_SHARD_AFFINE_MIN_G2 13
-/* B200_CFG_SHARD_PHASE_COST: fixed cost, in G1 terms, of every PIECE of a set a rank of a sharded Groth16 key holds (a piece
- * is one more MSM on that rank: its own digit sort, slice merge and bucket tail; a G2 piece counts twice).  0 cuts the weighted
- * line into equal pieces; > 0 fills the ranks greedily to the smallest common capacity (csrc/shard_partition.h).            */
-#define B200_CFG_SHARD_PHASE_COST 14
 int b200_config(int key, int value);
 
 /* ---- base-point sets (the CRS arrays of groth16.Pk / snark.Pk) ---------- */

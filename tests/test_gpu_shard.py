@@ -10,12 +10,12 @@ from oracle import ref_py as o
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("logn,world,phase_cost", [(6, 2, 0), (8, 3, 0), (10, 8, 0), (8, 3, 25), (10, 8, 60), (10, 8, 4000)])
-def test_sharded_equals_single(logn, world, phase_cost):
-    """phase_cost > 0: the greedy partition of csrc/shard_partition.h (B200_CFG_SHARD_PHASE_COST) — other cuts, ranks that hold
-    nothing at all when the fixed cost dwarfs the sets, same proof."""
+@pytest.mark.parametrize("logn,world,weights", [(6, 2, None), (8, 3, None), (10, 8, None), (10, 8, (85, 275)), (8, 3, (130, 330))])
+def test_sharded_equals_single(logn, world, weights):
+    """weights: the partition weights x100 (B200_CFG_SHARD_W_AB / _W_G2) — other cuts, same proof; every rank's cut is the one
+    the Python mirror of csrc/shard_partition.h computes (b200_groth16_shard_info)."""
     import torch
-    from gosnark_b200 import _lib
+    from gosnark_b200 import _lib, shard
     from gosnark_b200._lib import check, ints_to_limbs, lib, ptr
     from gosnark_b200.bn128 import _unflatten_g1, _unflatten_g2
     from gosnark_b200.synthetic import SyntheticGroth16
@@ -33,25 +33,26 @@ def test_sharded_equals_single(logn, world, phase_cost):
         pa, pc = _unflatten_g1(out[:24])
         return pa, _unflatten_g2(out[24:])[0], pc
 
-    check(L.b200_config(_lib.CFG_SHARD_PHASE_COST, phase_cost))
     pk1 = syn.load_pk(0, 1)
     d_single = torch.zeros(48, dtype=torch.int64, device="cuda")
     check(L.b200_groth16_prove_device(pk1, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
                                       d_single.data_ptr(), None))
     parts = torch.zeros(128 * world, dtype=torch.int64, device="cuda")
-    pks = [syn.load_pk(rk, world) for rk in range(world)]
-    check(L.b200_config(_lib.CFG_SHARD_PHASE_COST, 0))
-    if phase_cost:          # the library cut the key exactly as the Python mirror says
-        from gosnark_b200 import shard
-        shard.PHASE_COST = float(phase_cost)
-        try:
-            for rk, pk in enumerate(pks):
-                info = np.zeros(12, dtype=np.uint64)
-                check(L.b200_groth16_shard_info(pk, ptr(info)))
-                sets = shard.shard_ranges(m, syn.npublic, syn.n_ptd, rk, world)["sets"]
-                assert [int(x) for x in info[:6]] == [v for k in range(3) for v in (sets[k]["lo"], sets[k]["hi"])]
-        finally:
-            shard.PHASE_COST = 0.0
+    w_ab, w_g2 = weights or (100, 280)
+    check(L.b200_config(_lib.CFG_SHARD_W_AB, w_ab))
+    check(L.b200_config(_lib.CFG_SHARD_W_G2, w_g2))
+    shard.W_AB, shard.W_G2 = w_ab / 100.0, w_g2 / 100.0
+    try:
+        pks = [syn.load_pk(rk, world) for rk in range(world)]
+        for rk, pk in enumerate(pks):      # the library cut the key exactly as the Python mirror says
+            info = np.zeros(12, dtype=np.uint64)
+            check(L.b200_groth16_shard_info(pk, ptr(info)))
+            sets = shard.shard_ranges(m, syn.npublic, syn.n_ptd, rk, world)["sets"]
+            assert [int(x) for x in info[:6]] == [v for k in range(3) for v in (sets[k]["lo"], sets[k]["hi"])]
+    finally:
+        check(L.b200_config(_lib.CFG_SHARD_W_AB, 100))
+        check(L.b200_config(_lib.CFG_SHARD_W_G2, 280))
+        shard.W_AB, shard.W_G2 = 1.0, 2.8
     for rk, pk in enumerate(pks):
         check(L.b200_groth16_prove_device(pk, d_w.data_ptr(), m, d_px.data_ptr(), npx, ptr(r_l), ptr(s_l),
                                           parts[128 * rk:].data_ptr(), None))

@@ -13,14 +13,14 @@ import torch.multiprocessing as mp
 R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 
 
-def _worker(rank, world, port, n, ret, phase_cost=0.0):
+def _worker(rank, world, port, n, ret, weights=(1.0, 2.8)):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from gosnark_b200 import shard as _shard
     from gosnark_b200.shard import shard_ranges
-    _shard.PHASE_COST = phase_cost              # B200_CFG_SHARD_PHASE_COST mirror: 0 = equal pieces, > 0 = greedy fill
+    _shard.W_AB, _shard.W_G2 = weights          # partition weights (B200_CFG_SHARD_W_AB / _W_G2 mirror)
     rng = random.Random(7)                       # same data on every rank (replicated inputs)
     m, npublic, n_ptd = n + 2, 1, n + 1
     ka, kb, kc, kp = ([rng.randrange(R) for _ in range(k)] for k in (m, m, m, n_ptd))
@@ -68,12 +68,12 @@ def _worker(rank, world, port, n, ret, phase_cost=0.0):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,phase_cost", [(2, 64, 0.0), (3, 50, 0.0), (3, 50, 7.0)])
-def test_sharded_sums_over_gloo(world, n, phase_cost):
+@pytest.mark.parametrize("world,n,weights", [(2, 64, (1.0, 2.8)), (3, 50, (1.0, 2.8)), (3, 50, (0.85, 2.75))])
+def test_sharded_sums_over_gloo(world, n, weights):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = 29500 + random.randrange(2000)
-    procs = [ctx.Process(target=_worker, args=(rk, world, port, n, ret, phase_cost)) for rk in range(world)]
+    procs = [ctx.Process(target=_worker, args=(rk, world, port, n, ret, weights)) for rk in range(world)]
     for p in procs:
         p.start()
     for p in procs:

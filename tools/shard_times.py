@@ -14,8 +14,7 @@ logn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 _lib.init(0)
 L = lib()
-# optional tuning: key=value pairs for b200_config (10 w_ab x100, 11 w_g2 x100, 12 affine min G1 terms, 13 affine min G2 terms,
-# 14 fixed cost of a piece in G1 terms)
+# optional tuning: key=value pairs for b200_config (10 w_ab x100, 11 w_g2 x100, 12 affine min G1 terms, 13 affine min G2 terms)
 from gosnark_b200 import shard as _shard
 FLY = 1     # fly=2: two proofs in flight per emulated rank (two key contexts, two streams), as bench.py's default
 for kv in sys.argv[3:]:
@@ -28,8 +27,6 @@ for kv in sys.argv[3:]:
         _shard.W_AB = int(v) / 100.0
     if int(k) == 11:
         _shard.W_G2 = int(v) / 100.0
-    if int(k) == 14:
-        _shard.PHASE_COST = float(v)
 syn = SyntheticGroth16(logn)
 r_l, s_l = ints_to_limbs([syn.r]), ints_to_limbs([syn.s])
 d_w = torch.from_numpy(syn.w.view(np.int64)).cuda()
