@@ -69,7 +69,7 @@ int b200_version(void);
  * bn128.go:179-421, ~10 ms of dependent multiplications per pairing) or one WARP per pairing (2: F_q^12 in shared
  * memory, 27 F_q^2 products of a tower multiplication on 27 lanes; csrc/pairing_warp.cuh: 3.4 ms); 0 = auto: a warp per
  * pairing up to 2048 pairings per call (latency), a thread per pairing above (462 k vs 204 k pairings/s at 2^16).
- * Bit-identical F_q^12 values.  b200_groth16_verify always runs four warps (5.4 ms per verification, was 20).          */
+ * Bit-identical F_q^12 values.  b200_groth16_verify always runs four warps (4.2 ms per verification, was 20).          */
 #define B200_CFG_PAIRING_KERNEL 5
 /* Partition tuning of SHARDED proving keys loaded afterwards (defaults = the measured best for one proof at a time,
  * profiles/r2_notes.md section 8): cost weight x100 of an A / B1 term (10) and of a G2 term (11) in C||PTD terms, and the
