@@ -519,6 +519,12 @@ __global__ void __launch_bounds__(kAffBlock, MINB) k_affine_backward_staged(Affi
 }
 
 // buckets[b-1] = sum of the (affine) slice results of bucket b.
+// A thread folds up to kMergeSeq slices itself; only buckets beyond that (skewed scalar distributions) take the warp path.
+// bases_create picks S so that the MEAN bucket holds 6..12 slices, and the population spreads around it: with the bound at 12
+// (rounds 1-2 of this kernel) nearly half the buckets of a set whose mean sat just under 12 slices went down the warp path,
+// one after the other — a 832 k-term G1 MSM took 4.89 ms where a 845 k-term one (next S, 6 slices) took 3.67
+// (profiles/r2_slice_cliff.log).  Twice the largest mean leaves the warp path to the genuinely skewed buckets.
+constexpr uint32_t kMergeSeq = 24;
 template <class F>
 __global__ void __launch_bounds__(128)
 k_merge_slices_affine(NodeBuf<F> slice_pts, SliceTables st, uint32_t nbuckets,
@@ -529,13 +535,13 @@ k_merge_slices_affine(NodeBuf<F> slice_pts, SliceTables st, uint32_t nbuckets,
   if (b <= nbuckets) {
     first = st.slice_off[b];
     cnt = st.slice_off[b + 1] - first;
-    if (cnt <= 12) {  // the common case: a handful of slices per bucket
+    if (cnt <= kMergeSeq) {  // the common case: a handful of slices per bucket
       XYZZ<F> acc = XYZZ<F>::inf();
       for (uint32_t k = 0; k < cnt; k++) xyzz_madd(acc, Affine<F>{ld_fe(&slice_pts.x[first + k]), ld_fe(&slice_pts.y[first + k])});
       buckets[b - 1] = acc;
     }
   }
-  uint32_t multi = __ballot_sync(0xffffffffu, cnt > 12);  // skewed buckets: the whole warp sums them
+  uint32_t multi = __ballot_sync(0xffffffffu, cnt > kMergeSeq);  // skewed buckets: the whole warp sums them
   while (multi) {
     int j = __ffs(multi) - 1;
     multi &= multi - 1;

@@ -123,7 +123,7 @@ def test_g2_forward_kernel_cta_emulation(lib):
                                                 # seg = 0: rows / columns + bit planes + Horner tail, nbuckets = 2^(c-1)
                                                 (1, 64, 0), (1, 128, 0), (1, 2048, 0), (2, 256, 0)])
 def test_msm_tail_kernels(lib, group, nbuckets, seg):
-    """k_merge_slices_affine (thread-per-bucket path and the warp path for buckets with > 12 slices, ballot + shuffles),
+    """k_merge_slices_affine (thread-per-bucket path and the warp path for buckets with > 24 slices, ballot + shuffles),
     k_bucket_reduce (running sums + small scalar multiple per segment), k_sum_points (one and two levels) and k_finalize:
     sum_b b * (sum of the slices of bucket b) against the oracle."""
     G = o.BN.G1 if group == 1 else o.BN.G2
@@ -135,7 +135,7 @@ def test_msm_tail_kernels(lib, group, nbuckets, seg):
     pts = []
     acc = G.zero3()
     for b in range(1, nbuckets + 1):
-        cnt = rng.choice([0, 1, 1, 2, 3, 12, 13, 40]) if b % 7 else rng.choice([0, 33])
+        cnt = rng.choice([0, 1, 1, 2, 3, 12, 13, 24, 25, 40]) if b % 7 else rng.choice([0, 33])
         bsum = G.zero3()
         for _ in range(cnt):
             p = rng.choice(pool)
