@@ -387,6 +387,19 @@ func CommInit(id [128]byte, rank, world int) error {
 }
 func CommDestroy() error { return check(C.b200_comm_destroy()) }
 
+// TuneShardsForTwoInFlight sets the partition of sharded keys loaded AFTERWARDS the way bench.py does when it keeps two
+// proofs in flight (LoadGroth16Pair on every rank): every shard on the batched-affine tree, an A / B1 term 0.85 and a G2
+// term 2.75 of a C||PTD term (profiles/r2_notes.md sections 11 and 16).  The defaults suit one proof at a time.
+func TuneShardsForTwoInFlight() error {
+	for _, kv := range [][2]C.int{{C.B200_CFG_SHARD_AFFINE_MIN_G1, 1}, {C.B200_CFG_SHARD_AFFINE_MIN_G2, 1},
+		{C.B200_CFG_SHARD_W_AB, 85}, {C.B200_CFG_SHARD_W_G2, 275}} {
+		if err := check(C.b200_config(kv[0], kv[1])); err != nil {
+			return err
+		}
+	}
+	return nil
+}
+
 func LoadGroth16Shard(at, b1 [][3]*big.Int, b2 [][3][2]*big.Int, bacDelta, ptd [][3]*big.Int, z []*big.Int,
 	alpha1, beta1, delta1 [3]*big.Int, beta2, delta2 [3][2]*big.Int, nVars, nPublic, rank, world int) (*Groth16Key, error) {
 	fa, fb1, fb2, fc, fp := FlatG1(at[:nVars]), FlatG1(b1[:nVars]), FlatG2(b2[:nVars]), FlatG1(bacDelta[:nVars]), FlatG1(ptd)
