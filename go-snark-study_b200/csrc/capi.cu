@@ -22,6 +22,7 @@
 #include "qap_sparse.cuh"
 #include "comm.cuh"
 #include "shard_partition.h"
+#include "glv.cuh"
 #ifndef B200_NO_PAIRING
 #include "pairing.cuh"
 #include "pairing_warp.cuh"

@@ -22,6 +22,7 @@ template <class K> void stub_launch_cta(unsigned nblocks, unsigned nthreads, K k
 #define B200_LAUNCH_CTA(kernel, grid, block, stream, ...) stub_launch_cta((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
 #include "qap_sparse.cuh"
 #include "pairing_warp.cuh"
+#include "glv.cuh"
 
 using namespace b200;
 
@@ -567,6 +568,31 @@ int t_poly_mul_kernels(const uint32_t* a, uint32_t la, const uint32_t* b, uint32
 // sum_i scalars[i] * P_i through every kernel of the pipeline; S = 0: XYZZ accumulation, else batched-affine slices of S
 int t_msm_full(int group, const uint32_t* jac_std, const uint32_t* scalars_std, uint32_t n, uint32_t c, uint32_t S, uint32_t* out_std) {
   return group == 1 ? msm_full<Fq>(jac_std, scalars_std, n, c, S, out_std) : msm_full<Fq2>(jac_std, scalars_std, n, c, S, out_std);
+}
+// glv.cuh on a 32-thread emulated warp: lanes 0..15 compute k0 * P0, lanes 16..31 k1 * P1 — the two half-warps of
+// k_groth16_products / k_ic_terms — with the scalars split by glv_decompose exactly as the host side of the library does.
+// pts: two Jacobian points (X, Y, Z standard form, 24 words each); ks: two scalars (standard form, < r); out: two Jacobian
+// points, standard form.  Returns glv_decompose's status.
+int t_glv_mul(const uint32_t* pts, const uint32_t* ks, uint32_t* out) {
+  GlvScalars g;
+  Jacobian<Fq> p[2], res[2];
+  for (int i = 0; i < 2; i++) {
+    Fr k;
+    std::memcpy(&k, ks + 8 * i, sizeof(Fr));
+    if (glv_decompose(k, g.k[i], g.neg[i])) return 1;
+    p[i] = Jacobian<Fq>{load_std<Fq>(pts + 24 * i), load_std<Fq>(pts + 24 * i + 8), load_std<Fq>(pts + 24 * i + 16)};
+  }
+  run_cta(0, 32, 1, [&] {
+    const uint32_t t = threadIdx.x & 31u, grp = t >> 4;
+    Jacobian<Fq> r = glv_mul_halfwarp(p[grp], g.k[grp], g.neg[grp], t);
+    if ((t & 15u) == 0) res[grp] = r;
+  });
+  for (int i = 0; i < 2; i++) {
+    store_std(out + 24 * i, res[i].X);
+    store_std(out + 24 * i + 8, res[i].Y);
+    store_std(out + 24 * i + 16, res[i].Z);
+  }
+  return 0;
 }
 // One-warp-per-pairing code (pairing_warp.cuh) on a 32-thread emulated warp.  g1 = (x, y), g2 = (x.c0, x.c1, y.c0, y.c1), affine
 // standard form; out = 12 field elements in the reference's [2][3][2] order.  mode 0: the whole pairing; mode 1: only an

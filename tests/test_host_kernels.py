@@ -360,3 +360,41 @@ def test_warp_pairing_on_the_cpu(lib):
         assert got == o.BN.pairing((p[0], p[1], 1), (q[0], q[1], (1, 0)))
         if (k1, k2) == (25, 30):
             assert v[0] == 8016119724813186033542830391460394070015218389456422587891475873290878009957
+
+
+def test_glv_half_warp_multiplication_on_the_cpu(lib):
+    """csrc/glv.cuh — the sixteen-lane GLV scalar multiplication behind the prover's blinding products s*A, r*B1
+    (groth16.go:272-273) and the verifier's public-input sum (groth16.go:283-286) — on an emulated warp, with the scalars
+    split by the library's own glv_decompose: k * P equals the oracle's double-and-add (bn128/g1.go:140-155) as a group
+    element for edge scalars (0, 1, 2, r-1, either side of 2^128, lambda-sized values), random full-width scalars, points in
+    non-normalised Jacobian form, and the point at infinity."""
+    G = o.BN.G1
+    rng = random.Random(91)
+    lam = 4407920970296243842393367215006156084916469457145843978461       # an element of order 3 mod r (the GLV eigenvalue's size)
+    edge = [0, 1, 2, R_ - 1, R_ - 2, (1 << 128) - 1, 1 << 128, (1 << 128) + 1, (1 << 127), lam % R_, (R_ - lam) % R_, (1 << 253)]
+    scalars = edge + [rng.randrange(R_) for _ in range(12)]
+    if len(scalars) % 2:
+        scalars.append(rng.randrange(R_))
+    inf = (0, 0, 0)
+    for i in range(0, len(scalars), 2):
+        pts = []
+        for j in range(2):
+            if i == 4 and j == 1:
+                pts.append(inf)                                   # the point at infinity times a scalar
+            elif (i // 2 + j) % 3 == 0:
+                pts.append(G.mul_scalar(G.G, rng.randrange(1, R_)))  # Jacobian with Z != 1 (the reference's own MulScalar output)
+            else:
+                a = G.affine(G.mul_scalar(G.G, rng.randrange(1, R_)))
+                pts.append((a[0], a[1], 1))
+        ks = scalars[i:i + 2]
+        out = np.zeros(48, dtype=np.uint32)
+        assert lib.t_glv_mul(_ptr(_u32([c for p in pts for c in p])), _ptr(_u32(ks)), _ptr(out)) == 0
+        raw = out.tobytes()
+        v = [int.from_bytes(raw[32 * n:32 * (n + 1)], "little") for n in range(6)]
+        for j in range(2):
+            got = (v[3 * j], v[3 * j + 1], v[3 * j + 2])
+            exp = G.mul_scalar(pts[j], ks[j])
+            if G.is_zero(exp):
+                assert got[2] == 0, (ks[j], pts[j])
+            else:
+                assert got[2] != 0 and G.affine(got) == G.affine(exp), (ks[j], pts[j])
