@@ -164,7 +164,9 @@ def test_msm_tail_kernels(lib, group, nbuckets, seg):
 
 
 @pytest.mark.parametrize("group,n,c,S", [(1, 150, 5, 0), (1, 150, 5, 16), (1, 97, 4, 64), (1, 40, 9, 0), (2, 48, 4, 8),
-                                         (1, 300, 8, 8), (2, 60, 7, 0)])
+                                         (1, 300, 8, 8), (2, 60, 7, 0),
+                                         # ~17 slices per bucket: above the old thread-path bound of k_merge_slices_affine (12), inside the new one (24)
+                                         (1, 100, 6, 8), (2, 110, 6, 8)])
 def test_whole_msm_pipeline_on_the_cpu(lib, group, n, c, S):
     """Every kernel of an MSM in the library's order (window precompute, signed-digit recode, counting sort, slice tables,
     bucket accumulation in both modes, slice merge, weighted bucket reduction, tree sum, normalisation) on the CPU
