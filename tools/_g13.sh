@@ -1,4 +1,6 @@
 # GLV icPubl + phase-cost partition: full GPU suite, verify bench, 8- and 4-way shard emulation sweeps on one GPU
+# (record of the command that produced profiles/r2_shard_phase_cost.log; config key 14 — the phase cost — was measured worse and
+#  removed from the library afterwards, so this script no longer runs as is)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputest_part.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/r2_gputest_part.log
